@@ -1,0 +1,159 @@
+/*
+ * rodeo_b200 -- C ABI of the B200-native probabilistic-ODE filtering hot path.
+ *
+ * This is the drop-in boundary for the batched-theta path of mlysy/rodeo (reference v1.1.3).  The reference has
+ * no FFI of its own (it is pure JAX); each entry point below replaces one reference *Python* function executed
+ * under jax.jit(jax.vmap(...)) over a leading theta axis, and is what a jax.ffi / ctypes / cffi binding for that
+ * function would call (see INTEGRATION.md for the binding stubs):
+ *
+ *   rodeo_b200_solve_mv_*      rodeo.solve_mv            src/rodeo/solve.py:208-302
+ *   rodeo_b200_solve_sim_*     rodeo.solve_sim           src/rodeo/solve.py:125-205
+ *   rodeo_b200_dalton_*        rodeo.inference.dalton    src/rodeo/inference/dalton.py:39-235
+ *   rodeo_b200_fenrir_*        rodeo.inference.fenrir    src/rodeo/inference/fenrir.py:261-328
+ *   rodeo_b200_basic_gather_*  Xt[searchsorted(...)] of  rodeo.inference.basic   src/rodeo/inference/basic.py:60-61
+ *   rodeo_b200_ode_init_pad_*  ode_init() returned by    rodeo.utils.first_order_pad   src/rodeo/utils.py:94-96
+ *
+ * Conventions
+ *   - every array is C-contiguous with the reference's own layout plus a leading theta axis B;
+ *   - the `_f64` / `_f32` suffix is the arithmetic type of every floating-point buffer;
+ *   - all buffer pointers are DEVICE pointers (cudaMalloc / torch CUDA tensor .data_ptr()) unless a parameter
+ *     is documented as HOST; the `*_host` convenience wrappers take HOST buffers for everything and perform the
+ *     H2D / D2H copies themselves on an internal cached arena;
+ *   - calls are asynchronous and stream ordered on `stream` (a cudaStream_t passed as void*, NULL = default
+ *     stream); the library never allocates on this path and keeps no pointer after return;
+ *   - the caller provides `workspace` of at least rodeo_b200_workspace_bytes() bytes (may be NULL if that is 0);
+ *   - return value 0 = success; non-zero = error, text via rodeo_b200_last_error() (thread local);
+ *   - numerical failures (singular prior, NaN inputs) propagate as NaN/Inf exactly as in the reference -- there
+ *     is no device-side exception;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns RODEO_ERR_CUDA.
+ */
+#ifndef RODEO_B200_H
+#define RODEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RODEO_B200_ABI_VERSION 1
+
+/* rodeo.interrogate.interrogate_*   (src/rodeo/interrogate.py) */
+enum { RODEO_INTERROGATE_KRAMER = 0, RODEO_INTERROGATE_CHKREBTII = 1, RODEO_INTERROGATE_SCHOBER = 2,
+       RODEO_INTERROGATE_RODEO = 3 };
+/* kalman_type (src/rodeo/solve.py:236-241); only the covariance form is built so far */
+enum { RODEO_KALMAN_STANDARD = 0, RODEO_KALMAN_SQUARE_ROOT = 1 };
+/* built-in ODE right-hand sides; ids >= RODEO_MODEL_USER_BASE come from rodeo_b200_register_model_nvrtc() */
+enum { RODEO_MODEL_FITZHUGH_NAGUMO = 0, RODEO_MODEL_LORENZ63 = 1, RODEO_MODEL_SECOND_ORDER_SIN = 2,
+       RODEO_MODEL_HES1 = 3, RODEO_MODEL_SEIRAH = 4, RODEO_MODEL_USER_BASE = 1000 };
+/* ops, for rodeo_b200_workspace_bytes() */
+enum { RODEO_OP_SOLVE_MV = 0, RODEO_OP_SOLVE_SIM = 1, RODEO_OP_DALTON = 2, RODEO_OP_FENRIR = 3,
+       RODEO_OP_BASIC_GATHER = 4, RODEO_OP_ODE_INIT_PAD = 5 };
+enum { RODEO_OK = 0, RODEO_ERR_UNSUPPORTED = 1, RODEO_ERR_INVALID = 2, RODEO_ERR_WORKSPACE = 3,
+       RODEO_ERR_CUDA = 4, RODEO_ERR_NVRTC = 5 };
+
+/* Problem description shared by all ops (the reference's positional / keyword scalars). */
+typedef struct RodeoProblem {
+  int64_t B;               /* number of thetas (leading batch axis)                                        */
+  int64_t particle_offset; /* global index of theta 0: keeps random streams independent of GPU sharding    */
+  int32_t n_steps;         /* N                                                                            */
+  int32_t n_block;         /* ode_weight.shape[0]                                                          */
+  int32_t n_bstate;        /* ode_weight.shape[2]                                                          */
+  int32_t n_bmeas;         /* ode_weight.shape[1]                                                          */
+  int32_t n_theta;         /* len(theta)                                                                   */
+  int32_t model_id;        /* RODEO_MODEL_*                                                                */
+  int32_t interrogate;     /* RODEO_INTERROGATE_*                                                          */
+  int32_t kalman_type;     /* RODEO_KALMAN_*                                                               */
+  int32_t n_obs;           /* dalton / fenrir / basic_gather                                               */
+  int32_t n_bobs;          /* obs_weight.shape[2]                                                          */
+  uint32_t key[2];         /* the jax PRNG key (uint32[2]); only sampling paths read it                    */
+  double t_min, t_max;
+} RodeoProblem;
+
+/* Bytes of device workspace the op needs for this problem (0 on unsupported input). */
+size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* prob, int elem_bytes);
+
+const char* rodeo_b200_last_error(void);
+int rodeo_b200_abi_version(void);
+
+/*
+ * Common inputs:
+ *   ode_weight   (n_block, n_bmeas, n_bstate)  HOST   W          -- tiny; copied into the kernel parameter bank
+ *   prior_weight (n_block, n_bstate, n_bstate) HOST   Q
+ *   prior_var    (n_block, n_bstate, n_bstate) HOST   R
+ *   ode_init     (B, n_block, n_bstate)        device X0 per theta
+ *   theta        (B, n_theta)                  device
+ *   z_interr     optional (may be NULL) device normals for interrogate_chkrebtii,
+ *                (B, n_steps, n_stream, n_block, n_bstate); n_stream = 2 for dalton (joint, marginal), else 1
+ */
+int rodeo_b200_solve_mv_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                            const double* prior_var, const double* ode_init, const double* theta,
+                            const double* z_interr,
+                            double* mean_out /* (B, N+1, n_block, n_bstate) */,
+                            double* var_out /* (B, N+1, n_block, n_bstate, n_bstate) */,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* z_smooth: optional (may be NULL) device normals (B, N+1, n_block, n_bstate) for the backward draws */
+int rodeo_b200_solve_sim_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                             const double* prior_var, const double* ode_init, const double* theta,
+                             const double* z_interr, const double* z_smooth,
+                             double* x_out /* (B, N+1, n_block, n_bstate) */,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ *   obs_ind    (n_obs) int32 device: searchsorted(linspace(t_min, t_max, N+1), obs_times), left insertion
+ *   obs_data   (n_obs, n_block, n_bobs) device
+ *   obs_weight (n_obs, n_block, n_bobs, n_bstate) device
+ *   obs_var    (n_obs, n_block, n_bobs, n_bobs) device
+ */
+int rodeo_b200_dalton_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                          const double* prior_var, const double* ode_init, const double* theta,
+                          const double* z_interr,
+                          const int32_t* obs_ind, const double* obs_data, const double* obs_weight,
+                          const double* obs_var,
+                          double* loglik_out /* (B) */,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+int rodeo_b200_fenrir_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                          const double* prior_var, const double* ode_init, const double* theta,
+                          const double* z_interr,
+                          const int32_t* obs_ind, const double* obs_data, const double* obs_weight,
+                          const double* obs_var,
+                          double* loglik_out /* (B) */,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ode_data[b, i] = Xt[b, obs_ind[i]]   (rows of n_block*n_bstate) */
+int rodeo_b200_basic_gather_f64(const RodeoProblem* prob, const double* Xt /* (B, N+1, n_block, n_bstate) */,
+                                const int32_t* obs_ind,
+                                double* ode_data /* (B, n_obs, n_block, n_bstate) */, void* stream);
+
+/* X0[b] = [x0[b], f(x0[b], t, theta[b]), 0, ...]   x0: (B, n_block) device; X0: (B, n_block, n_bstate) device */
+int rodeo_b200_ode_init_pad_f64(const RodeoProblem* prob, double t, const double* theta, const double* x0,
+                                double* X0, void* stream);
+
+/*
+ * Host-buffer convenience wrapper for the headline op: every pointer is HOST memory (pinned or pageable).
+ * Copies inputs to an internal cached device arena, runs rodeo_b200_dalton_f64, copies loglik back and
+ * synchronises the stream.  This is the call a ctypes / cffi / jax CPU-callback binding makes.
+ */
+int rodeo_b200_dalton_f64_host(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                               const double* prior_var, const double* ode_init, const double* theta,
+                               const int32_t* obs_ind, const double* obs_data, const double* obs_weight,
+                               const double* obs_var, double* loglik_out);
+int rodeo_b200_solve_mv_f64_host(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                                 const double* prior_var, const double* ode_init, const double* theta,
+                                 double* mean_out, double* var_out);
+/* release the cached arena of the *_host wrappers */
+void rodeo_b200_host_arena_release(void);
+
+/* measured FP64 FMA throughput (TFLOP/s) of the current device: the roofline denominator bench.py reports against */
+int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out);
+
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+int64_t rodeo_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RODEO_B200_H */

@@ -1,0 +1,165 @@
+"""Argument marshalling shared by the drop-in entry points (host side only; no arithmetic of the hot path).
+
+Everything the reference takes un-batched and vmaps over (theta, ode_init) may carry a leading batch axis here;
+an un-batched call is B = 1 and the outputs lose the batch axis again, so that a user of the reference sees the
+reference's own shapes.  Tensors live on the current CUDA device; the kernels run on torch's current stream.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, interrogate as _interrogate, models as _models
+
+_DT = torch.float64
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise _lib.RodeoError("rodeo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_dev(x, dtype=_DT):
+    """array-like / numpy / torch (any device) -> contiguous tensor on the current CUDA device"""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    return t.to(device=device(), dtype=dtype, non_blocking=True).contiguous()
+
+
+def to_host(x):
+    """array-like / torch -> float64 C-contiguous numpy (for the tiny W, Q, R that go in the parameter bank)"""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def parse_key(key):
+    """jax-style PRNG key (uint32[2]), a python int, or None -> (k0, k1)"""
+    if key is None:
+        return 0, 0
+    if isinstance(key, torch.Tensor):
+        key = key.detach().cpu().numpy()
+    k = np.asarray(key)
+    if k.ndim == 0:
+        v = int(k) & 0xFFFFFFFFFFFFFFFF
+        return (v >> 32) & 0xFFFFFFFF, v & 0xFFFFFFFF
+    k = k.astype(np.uint64).ravel()
+    if k.size != 2:
+        raise ValueError("key must be None, an int, or a uint32[2] PRNG key")
+    return int(k[0]) & 0xFFFFFFFF, int(k[1]) & 0xFFFFFFFF
+
+
+def prior_from(prior_pars, prior_weight, prior_var):
+    """Accept both spellings: prior_pars=(Q, R) (reference HEAD, solve.py:208-212) and the <=1.1.2 keywords
+    prior_weight=, prior_var= that BASELINE's north_star and the reference's examples/timings.py:30-35 use."""
+    if prior_pars is not None:
+        if prior_weight is not None or prior_var is not None:
+            raise TypeError("give either prior_pars or prior_weight/prior_var, not both")
+        prior_weight, prior_var = prior_pars
+    if prior_weight is None or prior_var is None:
+        raise TypeError("missing prior: pass prior_pars=(prior_weight, prior_var)")
+    return to_host(prior_weight), to_host(prior_var)
+
+
+def kalman_id(kalman_type):
+    # reference src/rodeo/solve.py:236-241
+    if kalman_type == "standard":
+        return _lib.KALMAN_STANDARD
+    if kalman_type == "square-root":
+        raise NotImplementedError('kalman_type="square-root" is not built yet (SURVEY 8(f1))')
+    raise NotImplementedError
+
+
+class Problem:
+    """Validated, device-resident inputs of one batched call."""
+
+    def __init__(self, key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
+                 prior_weight, prior_var, kalman_type, params, particle_offset=0):
+        self.model = _models.resolve(ode_fun)
+        self.W = to_host(ode_weight)
+        if self.W.ndim != 3:
+            raise ValueError("ode_weight must have shape (n_block, n_bmeas, n_bstate)")
+        self.nb, self.m, self.p = self.W.shape
+        self.Q, self.R = prior_from(prior_pars, prior_weight, prior_var)
+        if self.Q.shape != (self.nb, self.p, self.p) or self.R.shape != (self.nb, self.p, self.p):
+            raise ValueError(f"prior matrices must have shape {(self.nb, self.p, self.p)}; per-theta priors are "
+                             f"not supported yet (got {self.Q.shape}, {self.R.shape})")
+        extra = set(params) - {"theta"}
+        if extra:
+            raise TypeError(f"unsupported ODE parameters {sorted(extra)}: device models take `theta` only")
+        theta = params.get("theta")
+        if theta is None:
+            if self.model.n_theta:
+                raise TypeError(f"model {self.model.name} needs theta=({self.model.n_theta},)")
+            theta = np.zeros((1, 0))
+        theta = to_dev(theta)
+        x0 = to_dev(ode_init)
+        self.batched = theta.ndim == 2 or x0.ndim == 3
+        if theta.ndim == 1:
+            theta = theta[None]
+        if x0.ndim == 2:
+            x0 = x0[None]
+        if theta.ndim != 2 or x0.ndim != 3 or x0.shape[1:] != (self.nb, self.p):
+            raise ValueError("theta must be (n_theta,) or (B, n_theta); ode_init (n_block, n_bstate) or (B, ...)")
+        B = max(theta.shape[0], x0.shape[0])
+        if theta.shape[0] not in (1, B) or x0.shape[0] not in (1, B):
+            raise ValueError("theta and ode_init disagree on the batch size")
+        self.B = B
+        self.theta = theta.expand(B, theta.shape[1]).contiguous()
+        self.x0 = x0.expand(B, self.nb, self.p).contiguous()
+        self.n_steps = int(n_steps)
+        self.t_min, self.t_max = float(t_min), float(t_max)
+        k0, k1 = parse_key(key)
+        c = _lib.RodeoProblem()
+        c.B, c.particle_offset, c.n_steps = B, int(particle_offset), self.n_steps
+        c.n_block, c.n_bstate, c.n_bmeas, c.n_theta = self.nb, self.p, self.m, self.theta.shape[1]
+        c.model_id = self.model.model_id
+        c.interrogate = _interrogate.resolve(interrogate, kalman_type)
+        c.kalman_type = kalman_id(kalman_type)
+        c.n_obs, c.n_bobs = 0, 0
+        c.key[0], c.key[1] = k0, k1
+        c.t_min, c.t_max = self.t_min, self.t_max
+        self.c = c
+        self.lib = _lib.load()
+
+    # --- helpers -------------------------------------------------------------------------------------------------
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def workspace(self, op):
+        n = self.lib.rodeo_b200_workspace_bytes(op, ctypes.byref(self.c), 8)
+        ws = torch.empty(max(n, 1), dtype=torch.uint8, device=device())
+        return ws, n
+
+    def set_obs(self, obs_data, obs_times, obs_weight=None, obs_var=None):
+        """searchsorted(linspace(t_min,t_max,N+1), obs_times), left insertion, on the host exactly as the
+        reference computes it (dalton.py:86-87), then the observation arrays on the device."""
+        sim_times = np.linspace(self.t_min, self.t_max, self.n_steps + 1)
+        ot = obs_times.detach().cpu().numpy() if isinstance(obs_times, torch.Tensor) else np.asarray(obs_times)
+        ind = np.searchsorted(sim_times, ot.astype(np.float64)).astype(np.int32)
+        self.obs_ind_host = ind
+        self.obs_ind = torch.from_numpy(ind).to(device())
+        self.c.n_obs = len(ind)
+        self.obs_data = to_dev(obs_data)
+        if obs_weight is not None:
+            self.obs_weight, self.obs_var = to_dev(obs_weight), to_dev(obs_var)
+            n_obs, nb, n_bobs, p = self.obs_weight.shape
+            if (n_obs, nb, p) != (len(ind), self.nb, self.p) or self.obs_var.shape != (n_obs, nb, n_bobs, n_bobs) \
+                    or self.obs_data.shape != (n_obs, nb, n_bobs):
+                raise ValueError("obs_data (n_obs,n_block,n_bobs), obs_weight (n_obs,n_block,n_bobs,n_bstate), "
+                                 "obs_var (n_obs,n_block,n_bobs,n_bobs) expected")
+            self.c.n_bobs = n_bobs
+
+    def unbatch(self, t):
+        return t if self.batched else t[0]

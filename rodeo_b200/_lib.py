@@ -1,0 +1,95 @@
+"""ctypes binding of the C ABI declared in include/rodeo_b200.h.
+
+The shared library is built in-tree (``make`` / ``__graft_entry__.build()``) as ``rodeo_b200/librodeo_b200.so``.
+There is no CPU fallback: if the library is missing, or a compute entry point is called without a CUDA device,
+the call fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librodeo_b200.so")
+
+c_double_p = ctypes.c_void_p
+c_int32_p = ctypes.c_void_p
+
+
+class RodeoProblem(ctypes.Structure):
+    """Mirror of ``struct RodeoProblem`` (include/rodeo_b200.h)."""
+    _fields_ = [
+        ("B", ctypes.c_int64),
+        ("particle_offset", ctypes.c_int64),
+        ("n_steps", ctypes.c_int32),
+        ("n_block", ctypes.c_int32),
+        ("n_bstate", ctypes.c_int32),
+        ("n_bmeas", ctypes.c_int32),
+        ("n_theta", ctypes.c_int32),
+        ("model_id", ctypes.c_int32),
+        ("interrogate", ctypes.c_int32),
+        ("kalman_type", ctypes.c_int32),
+        ("n_obs", ctypes.c_int32),
+        ("n_bobs", ctypes.c_int32),
+        ("key", ctypes.c_uint32 * 2),
+        ("t_min", ctypes.c_double),
+        ("t_max", ctypes.c_double),
+    ]
+
+
+# enums of include/rodeo_b200.h
+INTERROGATE_KRAMER, INTERROGATE_CHKREBTII, INTERROGATE_SCHOBER, INTERROGATE_RODEO = 0, 1, 2, 3
+KALMAN_STANDARD, KALMAN_SQUARE_ROOT = 0, 1
+OP_SOLVE_MV, OP_SOLVE_SIM, OP_DALTON, OP_FENRIR, OP_BASIC_GATHER, OP_ODE_INIT_PAD = range(6)
+ERR_NAMES = {1: "UNSUPPORTED", 2: "INVALID", 3: "WORKSPACE", 4: "CUDA", 5: "NVRTC"}
+
+_P = ctypes.POINTER(RodeoProblem)
+_vp, _sz, _i, _d = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_double
+
+# name -> (restype, argtypes); every symbol include/rodeo_b200.h declares
+SIGNATURES = {
+    "rodeo_b200_workspace_bytes": (_sz, [_i, _P, _i]),
+    "rodeo_b200_last_error": (ctypes.c_char_p, []),
+    "rodeo_b200_abi_version": (_i, []),
+    "rodeo_b200_launch_count": (ctypes.c_int64, []),
+    "rodeo_b200_solve_mv_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "rodeo_b200_solve_sim_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "rodeo_b200_dalton_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
+    "rodeo_b200_fenrir_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
+    "rodeo_b200_basic_gather_f64": (_i, [_P, _vp, _vp, _vp, _vp]),
+    "rodeo_b200_ode_init_pad_f64": (_i, [_P, _d, _vp, _vp, _vp, _vp]),
+    "rodeo_b200_dalton_f64_host": (_i, [_P] + [_vp] * 10),
+    "rodeo_b200_solve_mv_f64_host": (_i, [_P] + [_vp] * 7),
+    "rodeo_b200_host_arena_release": (None, []),
+    "rodeo_b200_fp64_peak_probe": (_i, [_i, _vp]),
+}
+
+_lib = None
+
+
+class RodeoError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RodeoError(
+            f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "rodeo_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.rodeo_b200_abi_version() != 1:
+        raise RodeoError("librodeo_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().rodeo_b200_last_error().decode(errors="replace")
+        exc = NotImplementedError if rc == 1 else (ValueError if rc == 2 else RodeoError)
+        raise exc(f"{what} failed [{ERR_NAMES.get(rc, rc)}]: {msg}")

@@ -1,0 +1,141 @@
+// C-ABI entry points that are not tied to one op: error text, versioning, workspace sizing, the small
+// gather / initial-value kernels.  See include/rodeo_b200.h.
+#include "rodeo_host.h"
+
+namespace rodeo {
+namespace host {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+template <typename T>
+__global__ void gather_rows_kernel(i64 B, int n_rows_in, int n_obs, int row, const int* __restrict__ ind,
+                                   const T* __restrict__ in, T* __restrict__ out) {
+  // out[b, i, :] = in[b, ind[i], :]
+  const i64 total = B * n_obs * row;
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (i64)gridDim.x * blockDim.x) {
+    const int c = (int)(k % row);
+    const i64 bi = k / row;
+    const int i = (int)(bi % n_obs);
+    const i64 b = bi / n_obs;
+    int src = ind[i];
+    src = src < 0 ? 0 : (src >= n_rows_in ? n_rows_in - 1 : src);   // traced gathers clamp
+    out[k] = in[(b * n_rows_in + src) * row + c];
+  }
+}
+
+// FP64 pipe probe: 8 independent DFMA chains per thread, enough warps to saturate every SM sub-partition.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
+template <class Model, int INTERR, int QK>
+struct InitPadRun {
+  static int run(const RodeoProblem& p, double t, const double* theta, const double* x0, double* X0, cudaStream_t s) {
+    if (p.B == 0) return RODEO_OK;
+    ode_init_pad_kernel<double, Model><<<grid_for(p.B, 128), 128, 0, s>>>(p.B, t, theta, x0, X0);
+    g_launches++;
+    RODEO_CUDA_OK(cudaGetLastError());
+    return RODEO_OK;
+  }
+};
+
+}  // namespace host
+}  // namespace rodeo
+
+using namespace rodeo;
+using namespace rodeo::host;
+
+extern "C" {
+
+const char* rodeo_b200_last_error(void) { return g_err; }
+int rodeo_b200_abi_version(void) { return RODEO_B200_ABI_VERSION; }
+int64_t rodeo_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes) {
+  if (!p || (elem_bytes != 8 && elem_bytes != 4)) return 0;
+  switch (op) {
+    case RODEO_OP_SOLVE_MV:
+    case RODEO_OP_SOLVE_SIM:
+    case RODEO_OP_FENRIR: {
+      // stash of filt[1..N-1]: (N-1) * n_block * (p + p(p+1)/2) * ldb elements
+      const size_t nstate = (size_t)p->n_block * (p->n_bstate + p->n_bstate * (p->n_bstate + 1) / 2);
+      const size_t steps = p->n_steps > 1 ? (size_t)(p->n_steps - 1) : 0;
+      return steps * nstate * (size_t)stash_ldb(p->B) * (size_t)elem_bytes;
+    }
+    default:
+      return 0;
+  }
+}
+
+// Measured FP64 FMA throughput of the current device in TFLOP/s (2 flop per DFMA), best of `reps` timed launches.
+// bench.py uses it as the roofline denominator for the FP64-bound kernels (MEASURED_PEAKS.json has no FP64 figure).
+int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out) {
+  if (!tflops_out) { set_error("tflops_out is NULL"); return RODEO_ERR_INVALID; }
+  int dev = 0, sms = 0;
+  RODEO_CUDA_OK(cudaGetDevice(&dev));
+  RODEO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* d = nullptr;
+  RODEO_CUDA_OK(cudaMalloc((void**)&d, 8));
+  cudaEvent_t e0, e1;
+  RODEO_CUDA_OK(cudaEventCreate(&e0));
+  RODEO_CUDA_OK(cudaEventCreate(&e1));
+  const int iters = 4096, grid = sms * 8, block = 256;
+  double best = 0.0;
+  for (int r = 0; r < reps + 2; ++r) {
+    RODEO_CUDA_OK(cudaEventRecord(e0, 0));
+    fp64_probe_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-9);
+    RODEO_CUDA_OK(cudaEventRecord(e1, 0));
+    RODEO_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RODEO_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * (double)iters * (double)grid * (double)block;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (r >= 2 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops_out = best;
+  return RODEO_OK;
+}
+
+int rodeo_b200_basic_gather_f64(const RodeoProblem* p, const double* Xt, const int32_t* obs_ind, double* ode_data,
+                                void* stream) {
+  if (int rc = check_common(p)) return rc;
+  if (p->n_obs < 0) { set_error("n_obs < 0"); return RODEO_ERR_INVALID; }
+  const long long total = p->B * (long long)p->n_obs * p->n_block * p->n_bstate;
+  if (total == 0) return RODEO_OK;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  gather_rows_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(p->B, p->n_steps + 1, p->n_obs,
+                                                                    p->n_block * p->n_bstate, obs_ind, Xt, ode_data);
+  g_launches++;
+  RODEO_CUDA_OK(cudaGetLastError());
+  return RODEO_OK;
+}
+
+int rodeo_b200_ode_init_pad_f64(const RodeoProblem* p, double t, const double* theta, const double* x0, double* X0,
+                                void* stream) {
+  if (int rc = check_common(p)) return rc;
+  if (p->n_bstate < 2) { set_error("first_order_pad needs n_deriv >= 2"); return RODEO_ERR_INVALID; }
+  RodeoProblem q = *p;
+  q.interrogate = RODEO_INTERROGATE_KRAMER;
+  return dispatch_model<InitPadRun>(q, QK_DENSE, q, t, theta, x0, X0, (cudaStream_t)stream);
+}
+
+}  // extern "C"

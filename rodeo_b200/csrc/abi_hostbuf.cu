@@ -1,0 +1,109 @@
+// Host-buffer convenience entry points (include/rodeo_b200.h: rodeo_b200_*_host): every pointer is HOST memory.
+// They stage inputs into a cached device arena, call the device-pointer entry point, copy the result back and
+// synchronise.  The arena only ever grows, so steady-state calls perform no allocation.
+#include <mutex>
+
+#include "rodeo_host.h"
+
+using namespace rodeo;
+using namespace rodeo::host;
+
+namespace {
+
+struct Arena {
+  std::mutex mu;
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaStream_t stream = nullptr;
+
+  int reserve(size_t bytes) {
+    used = 0;
+    if (!stream) RODEO_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (bytes <= cap) return RODEO_OK;
+    if (base) { RODEO_CUDA_OK(cudaFree(base)); base = nullptr; cap = 0; }
+    RODEO_CUDA_OK(cudaMalloc((void**)&base, bytes));
+    cap = bytes;
+    return RODEO_OK;
+  }
+  void* take(size_t bytes) {
+    void* p = base + used;
+    used += round_up(bytes, 256);
+    return p;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    if (stream) cudaStreamDestroy(stream);
+    base = nullptr; cap = used = 0; stream = nullptr;
+  }
+};
+Arena g_arena;
+
+inline size_t al(size_t b) { return round_up(b, 256); }
+
+}  // namespace
+
+extern "C" void rodeo_b200_host_arena_release(void) {
+  std::lock_guard<std::mutex> lk(g_arena.mu);
+  g_arena.release();
+}
+
+extern "C" int rodeo_b200_dalton_f64_host(const RodeoProblem* p, const double* ode_weight, const double* prior_weight,
+                                          const double* prior_var, const double* ode_init, const double* theta,
+                                          const int32_t* obs_ind, const double* obs_data, const double* obs_weight,
+                                          const double* obs_var, double* loglik_out) {
+  if (int rc = check_common(p)) return rc;
+  if (p->n_obs < 1) { set_error("dalton needs n_obs >= 1"); return RODEO_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(g_arena.mu);
+  const size_t B = (size_t)p->B, nb = p->n_block, ps = p->n_bstate, no = p->n_obs, nob = p->n_bobs;
+  const size_t b_init = B * nb * ps * 8, b_theta = B * p->n_theta * 8, b_ll = B * 8;
+  const size_t b_ind = no * 4, b_y = no * nb * nob * 8, b_D = no * nb * nob * ps * 8, b_Om = no * nb * nob * nob * 8;
+  if (int rc = g_arena.reserve(al(b_init) + al(b_theta) + al(b_ll) + al(b_ind) + al(b_y) + al(b_D) + al(b_Om) + 256))
+    return rc;
+  double* d_init = (double*)g_arena.take(b_init);
+  double* d_theta = (double*)g_arena.take(b_theta);
+  double* d_ll = (double*)g_arena.take(b_ll);
+  int32_t* d_ind = (int32_t*)g_arena.take(b_ind);
+  double* d_y = (double*)g_arena.take(b_y);
+  double* d_D = (double*)g_arena.take(b_D);
+  double* d_Om = (double*)g_arena.take(b_Om);
+  cudaStream_t s = g_arena.stream;
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_init, ode_init, b_init, cudaMemcpyHostToDevice, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_theta, theta, b_theta, cudaMemcpyHostToDevice, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_ind, obs_ind, b_ind, cudaMemcpyHostToDevice, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_y, obs_data, b_y, cudaMemcpyHostToDevice, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_D, obs_weight, b_D, cudaMemcpyHostToDevice, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_Om, obs_var, b_Om, cudaMemcpyHostToDevice, s));
+  if (int rc = rodeo_b200_dalton_f64(p, ode_weight, prior_weight, prior_var, d_init, d_theta, nullptr, d_ind, d_y,
+                                     d_D, d_Om, d_ll, nullptr, 0, s))
+    return rc;
+  RODEO_CUDA_OK(cudaMemcpyAsync(loglik_out, d_ll, b_ll, cudaMemcpyDeviceToHost, s));
+  RODEO_CUDA_OK(cudaStreamSynchronize(s));
+  return RODEO_OK;
+}
+
+extern "C" int rodeo_b200_solve_mv_f64_host(const RodeoProblem* p, const double* ode_weight, const double* prior_weight,
+                                            const double* prior_var, const double* ode_init, const double* theta,
+                                            double* mean_out, double* var_out) {
+  if (int rc = check_common(p)) return rc;
+  std::lock_guard<std::mutex> lk(g_arena.mu);
+  const size_t B = (size_t)p->B, nb = p->n_block, ps = p->n_bstate, N1 = (size_t)p->n_steps + 1;
+  const size_t b_init = B * nb * ps * 8, b_theta = B * p->n_theta * 8;
+  const size_t b_mean = B * N1 * nb * ps * 8, b_var = b_mean * ps;
+  const size_t b_ws = rodeo_b200_workspace_bytes(RODEO_OP_SOLVE_MV, p, 8);
+  if (int rc = g_arena.reserve(al(b_init) + al(b_theta) + al(b_mean) + al(b_var) + al(b_ws) + 256)) return rc;
+  double* d_init = (double*)g_arena.take(b_init);
+  double* d_theta = (double*)g_arena.take(b_theta);
+  double* d_mean = (double*)g_arena.take(b_mean);
+  double* d_var = (double*)g_arena.take(b_var);
+  void* d_ws = g_arena.take(b_ws);
+  cudaStream_t s = g_arena.stream;
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_init, ode_init, b_init, cudaMemcpyHostToDevice, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(d_theta, theta, b_theta, cudaMemcpyHostToDevice, s));
+  if (int rc = rodeo_b200_solve_mv_f64(p, ode_weight, prior_weight, prior_var, d_init, d_theta, nullptr, d_mean, d_var,
+                                       d_ws, b_ws, s))
+    return rc;
+  RODEO_CUDA_OK(cudaMemcpyAsync(mean_out, d_mean, b_mean, cudaMemcpyDeviceToHost, s));
+  RODEO_CUDA_OK(cudaMemcpyAsync(var_out, d_var, b_var, cudaMemcpyDeviceToHost, s));
+  RODEO_CUDA_OK(cudaStreamSynchronize(s));
+  return RODEO_OK;
+}

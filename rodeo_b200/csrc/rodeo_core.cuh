@@ -1,0 +1,494 @@
+// rodeo_b200 device library: register-resident small linear algebra for the block Kalman recursions.
+//
+// Everything here is a __device__ __forceinline__ template over the scalar type T (double primary, float
+// secondary) and compile-time sizes, so that one (theta) filter lives entirely in registers for all n_steps.
+// Symmetric matrices are stored packed (upper triangle, row-major): only p(p+1)/2 entries are carried.
+//
+// The recurrences follow the reference's covariance-form Kalman functions
+//   predict      src/rodeo/kalmantv/standard.py:31-60
+//   update       src/rodeo/kalmantv/standard.py:63-103   (+ rodeo.utils.solve_var, src/rodeo/utils.py:105-119)
+//   forecast     src/rodeo/kalmantv/standard.py:308-336
+//   _smooth, smooth_mv, smooth_sim, smooth_cond   src/rodeo/kalmantv/standard.py:160-255,339-371
+//   multivariate_normal_logpdf                    src/rodeo/utils.py:60-78
+// but are restated for a thread-per-theta execution model; no line of the reference is translated.
+//
+// This header is also compiled at run time by NVRTC for user-supplied ODE right-hand sides, so it must not
+// include any host or CUDA toolkit header.
+#pragma once
+
+#define RD_DEV __device__ __forceinline__
+#define RD_UNROLL _Pragma("unroll")
+
+namespace rodeo {
+
+// ---- enums shared with the C ABI (include/rodeo_b200.h) -------------------------------------------------
+enum : int { INTERR_KRAMER = 0, INTERR_CHKREBTII = 1, INTERR_SCHOBER = 2, INTERR_RODEO = 3 };
+enum : int { QK_DENSE = 0, QK_UNIT_UPPER = 1 };   // structure of the prior transition matrix Q
+
+// packed index of a symmetric PxP matrix, requires i <= j
+template <int P>
+RD_DEV constexpr int sidx(int i, int j) { return i * P - (i * (i - 1)) / 2 + (j - i); }
+template <int P>
+RD_DEV constexpr int sym(int i, int j) { return i <= j ? sidx<P>(i, j) : sidx<P>(j, i); }
+template <int P>
+struct NSym { static constexpr int value = P * (P + 1) / 2; };
+
+template <typename T> RD_DEV T rd_fma(T a, T b, T c);
+template <> RD_DEV double rd_fma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> RD_DEV float rd_fma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+template <typename T> struct Lim;
+template <> struct Lim<double> {
+  RD_DEV static double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  RD_DEV static double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+};
+template <> struct Lim<float> {
+  RD_DEV static float inf() { return __int_as_float(0x7f800000); }
+  RD_DEV static float nan() { return __int_as_float(0x7fc00000); }
+};
+
+// ---- constants that live in the kernel-parameter constant bank ------------------------------------------
+// Q, R, W are shared by every theta of a launch (reference layouts (nb,p,p), (nb,p,p), (nb,m,p)); passing them
+// by value as a __grid_constant__ kernel parameter lets every DFMA take them as c[0][..] operands: they cost
+// no registers and no loads inside the time loop.
+template <typename T, int NB, int P, int M>
+struct FilterConsts {
+  T Q[NB][P][P];
+  T R[NB][P * (P + 1) / 2];
+  T W[NB][M][P];
+};
+
+// ---- predict ----------------------------------------------------------------------------------------------
+// mu_p = Q mu ;  S_p = Q S Q^T + R        (mean_state == 0 in the solver, reference src/rodeo/solve.py:52)
+template <typename T, int P, int QK>
+RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], const T (&mu)[P],
+                    const T (&S)[P * (P + 1) / 2], T (&mup)[P], T (&Sp)[P * (P + 1) / 2]) {
+  T A[P][P];  // A = Q S
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    if (QK == QK_UNIT_UPPER) {
+      T m = mu[i];
+      RD_UNROLL for (int j = i + 1; j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+      mup[i] = m;
+      RD_UNROLL for (int k = 0; k < P; ++k) {
+        T a = S[sym<P>(i, k)];
+        RD_UNROLL for (int j = i + 1; j < P; ++j) a = rd_fma(Q[i][j], S[sym<P>(j, k)], a);
+        A[i][k] = a;
+      }
+    } else {
+      T m = Q[i][0] * mu[0];
+      RD_UNROLL for (int j = 1; j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+      mup[i] = m;
+      RD_UNROLL for (int k = 0; k < P; ++k) {
+        T a = Q[i][0] * S[sym<P>(0, k)];
+        RD_UNROLL for (int j = 1; j < P; ++j) a = rd_fma(Q[i][j], S[sym<P>(j, k)], a);
+        A[i][k] = a;
+      }
+    }
+  }
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    RD_UNROLL for (int j = i; j < P; ++j) {
+      T s;
+      if (QK == QK_UNIT_UPPER) {
+        s = A[i][j];
+        RD_UNROLL for (int k = j + 1; k < P; ++k) s = rd_fma(A[i][k], Q[j][k], s);
+      } else {
+        s = A[i][0] * Q[j][0];
+        RD_UNROLL for (int k = 1; k < P; ++k) s = rd_fma(A[i][k], Q[j][k], s);
+      }
+      Sp[sidx<P>(i, j)] = s + R[sidx<P>(i, j)];
+    }
+  }
+}
+
+// mean-only predict (used when the covariance recursion is not needed)
+template <typename T, int P, int QK>
+RD_DEV void predict_mean(const T (&Q)[P][P], const T (&mu)[P], T (&mup)[P]) {
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T m = (QK == QK_UNIT_UPPER) ? mu[i] : Q[i][0] * mu[0];
+    RD_UNROLL for (int j = (QK == QK_UNIT_UPPER ? i + 1 : 1); j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+    mup[i] = m;
+  }
+}
+
+// ---- log-determinant accumulator -------------------------------------------------------------------------
+// sum_k log(w_k) is accumulated as log(prod mantissa_k) + ln2 * sum exponent_k: one DMUL plus integer work
+// per term instead of one FP64 log per term.  A negative or non-finite w poisons the product with NaN, which
+// is what log(w) would have produced in the reference.
+template <typename T> struct LogAcc;
+template <> struct LogAcc<double> {
+  double prod; int esum;
+  RD_DEV void init() { prod = 1.0; esum = 0; }
+  RD_DEV void add(double w, bool keep) {
+    int hi = __double2hiint(w), lo = __double2loint(w);
+    int e = ((hi >> 20) & 0x7ff);
+    bool bad = (hi < 0) || (e == 0x7ff);   // negative, inf or nan: log(w) is nan (or inf) in the reference
+    double mant = bad ? Lim<double>::nan() : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    prod *= keep ? mant : 1.0;
+    esum += (keep && !bad) ? e - 1023 : 0;
+  }
+  RD_DEV void renorm() {  // call at least every ~500 add()s
+    int hi = __double2hiint(prod), lo = __double2loint(prod);
+    int e = ((hi >> 20) & 0x7ff);
+    if (e != 0x7ff && e != 0) {
+      esum += e - 1023;
+      prod = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo);
+    }
+  }
+  RD_DEV double value() const { return log(prod) + 0.6931471805599453094 * (double)esum; }
+};
+template <> struct LogAcc<float> {
+  float prod; int esum;
+  RD_DEV void init() { prod = 1.0f; esum = 0; }
+  RD_DEV void add(float w, bool keep) {
+    int b = __float_as_int(w);
+    int e = (b >> 23) & 0xff;
+    bool bad = (b < 0) || (e == 0xff);
+    float mant = bad ? Lim<float>::nan() : __int_as_float((b & 0x007fffff) | 0x3f800000);
+    prod *= keep ? mant : 1.0f;
+    esum += (keep && !bad) ? e - 127 : 0;
+  }
+  RD_DEV void renorm() {  // call at least every ~100 add()s
+    int b = __float_as_int(prod);
+    int e = (b >> 23) & 0xff;
+    if (e != 0xff && e != 0) {
+      esum += e - 127;
+      prod = __int_as_float((b & 0x807fffff) | 0x3f800000);
+    }
+  }
+  RD_DEV float value() const { return logf(prod) + 0.69314718056f * (float)esum; }
+};
+
+// Gaussian log-density accumulator: logdens = -1/2 (quad + logdet) - 1/2 cnt log(2 pi), with the reference's
+// absolute eigenvalue cut-off |w| > 1e-8 (src/rodeo/utils.py:74, jnp.isclose default atol) applied per term.
+template <typename T>
+struct LogPdfAcc {
+  T quad; LogAcc<T> ld; int cnt;
+  RD_DEV void init() { quad = T(0); ld.init(); cnt = 0; }
+  // one eigen-direction: eigenvalue w, projected residual z
+  RD_DEV void term(T w, T z, T rw /* = 1/w */) {
+    bool keep = !(fabs(w) <= T(1e-8));   // nan counts as kept, as ~isclose(nan, 0) does
+    quad = keep ? rd_fma(z * z, rw, quad) : quad;
+    ld.add(w, keep);
+    cnt += keep ? 1 : 0;
+  }
+  RD_DEV T value() const {
+    return T(-0.5) * (quad + ld.value()) - T(0.5) * T(1.8378770664093454836) * (T)cnt;
+  }
+};
+
+// ---- tiny dense solves -------------------------------------------------------------------------------------
+// Solve S X = Bm for X (MM x P right-hand sides stored as rows r of Bm[r][:]) by Gaussian elimination with
+// partial pivoting, the algorithm behind jnp.linalg.solve (LAPACK getrf/getrs) in rodeo.utils.solve_var.
+// S is symmetric, given packed; it is expanded to a full MM x MM working copy.
+template <typename T, int MM, int P>
+RD_DEV void solve_small(const T (&Ss)[MM * (MM + 1) / 2], T (&Bm)[MM][P]) {
+  if (MM == 1) {
+    T r = T(1) / Ss[0];
+    RD_UNROLL for (int i = 0; i < P; ++i) Bm[0][i] *= r;
+    return;
+  }
+  T A[MM][MM];
+  RD_UNROLL for (int r = 0; r < MM; ++r)
+    RD_UNROLL for (int c = 0; c < MM; ++c) A[r][c] = Ss[sym<MM>(r, c)];
+  RD_UNROLL for (int k = 0; k < MM; ++k) {
+    // pivot search + row swap by selects (no divergent control flow)
+    RD_UNROLL for (int r = k + 1; r < MM; ++r) {
+      bool sw = fabs(A[r][k]) > fabs(A[k][k]);
+      RD_UNROLL for (int c = 0; c < MM; ++c) {
+        T a = A[k][c], b = A[r][c];
+        A[k][c] = sw ? b : a; A[r][c] = sw ? a : b;
+      }
+      RD_UNROLL for (int c = 0; c < P; ++c) {
+        T a = Bm[k][c], b = Bm[r][c];
+        Bm[k][c] = sw ? b : a; Bm[r][c] = sw ? a : b;
+      }
+    }
+    T rp = T(1) / A[k][k];
+    RD_UNROLL for (int r = k + 1; r < MM; ++r) {
+      T l = A[r][k] * rp;
+      RD_UNROLL for (int c = k + 1; c < MM; ++c) A[r][c] = rd_fma(-l, A[k][c], A[r][c]);
+      RD_UNROLL for (int c = 0; c < P; ++c) Bm[r][c] = rd_fma(-l, Bm[k][c], Bm[r][c]);
+    }
+  }
+  RD_UNROLL for (int k = MM - 1; k >= 0; --k) {
+    T rp = T(1) / A[k][k];
+    RD_UNROLL for (int c = 0; c < P; ++c) {
+      T s = Bm[k][c];
+      RD_UNROLL for (int j = k + 1; j < MM; ++j) s = rd_fma(-A[k][j], Bm[j][c], s);
+      Bm[k][c] = s * rp;
+    }
+  }
+}
+
+// Symmetric 2x2 eigen-decomposition [[a,b],[b,c]] -> rt1 >= rt2 (by absolute value as LAPACK dlaev2 orders
+// them: |rt1| >= |rt2|), unit eigenvector (cs1, sn1) of rt1; the eigenvector of rt2 is (-sn1, cs1).
+template <typename T>
+RD_DEV void eig2(T a, T b, T c, T& rt1, T& rt2, T& cs1, T& sn1) {
+  T sm = a + c, df = a - c, adf = fabs(df), tb = b + b, ab = fabs(tb);
+  T acmx = fabs(a) > fabs(c) ? a : c, acmn = fabs(a) > fabs(c) ? c : a;
+  T rt;
+  if (adf > ab) { T q = ab / adf; rt = adf * sqrt(T(1) + q * q); }
+  else if (adf < ab) { T q = adf / ab; rt = ab * sqrt(T(1) + q * q); }
+  else rt = ab * sqrt(T(2));
+  int sgn1;
+  if (sm < T(0)) { rt1 = T(0.5) * (sm - rt); sgn1 = -1; rt2 = (acmx / rt1) * acmn - (b / rt1) * b; }
+  else if (sm > T(0)) { rt1 = T(0.5) * (sm + rt); sgn1 = 1; rt2 = (acmx / rt1) * acmn - (b / rt1) * b; }
+  else { rt1 = T(0.5) * rt; rt2 = T(-0.5) * rt; sgn1 = 1; }
+  int sgn2; T cs;
+  if (df >= T(0)) { cs = df + rt; sgn2 = 1; } else { cs = df - rt; sgn2 = -1; }
+  if (fabs(cs) > ab) { T ct = -tb / cs; sn1 = T(1) / sqrt(T(1) + ct * ct); cs1 = ct * sn1; }
+  else if (ab == T(0)) { cs1 = T(1); sn1 = T(0); }
+  else { T tn = -cs / tb; cs1 = T(1) / sqrt(T(1) + tn * tn); sn1 = tn * cs1; }
+  if (sgn1 == sgn2) { T tn = cs1; cs1 = -sn1; sn1 = tn; }
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric MM x MM matrix (MM >= 3 fall-back for the log-pdf).
+// On exit A's diagonal holds the eigenvalues and the columns of V the eigenvectors.
+template <typename T, int MM>
+RD_DEV void eig_jacobi(T (&A)[MM][MM], T (&V)[MM][MM]) {
+  RD_UNROLL for (int i = 0; i < MM; ++i)
+    RD_UNROLL for (int j = 0; j < MM; ++j) V[i][j] = (i == j) ? T(1) : T(0);
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    T off = T(0);
+    RD_UNROLL for (int p = 0; p < MM; ++p)
+      RD_UNROLL for (int q = p + 1; q < MM; ++q) off += A[p][q] * A[p][q];
+    if (off == T(0)) break;
+    RD_UNROLL for (int p = 0; p < MM; ++p) {
+      RD_UNROLL for (int q = p + 1; q < MM; ++q) {
+        T apq = A[p][q];
+        if (apq != T(0)) {
+          T tau = (A[q][q] - A[p][p]) / (T(2) * apq);
+          T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
+          T c = T(1) / sqrt(T(1) + t * t), s = t * c;
+          RD_UNROLL for (int k = 0; k < MM; ++k) {
+            T akp = A[k][p], akq = A[k][q];
+            A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
+          }
+          RD_UNROLL for (int k = 0; k < MM; ++k) {
+            T apk = A[p][k], aqk = A[q][k];
+            A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
+          }
+          RD_UNROLL for (int k = 0; k < MM; ++k) {
+            T vkp = V[k][p], vkq = V[k][q];
+            V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+          }
+        }
+      }
+    }
+  }
+}
+
+// log N(x; mu, S) contribution(s) into `acc`, S symmetric MM x MM packed, res = x - mu.
+template <typename T, int MM>
+RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], LogPdfAcc<T>& acc) {
+  if (MM == 1) {
+    acc.term(Ss[0], res[0], T(1) / Ss[0]);
+  } else if (MM == 2) {
+    T w1, w2, c, s;
+    eig2<T>(Ss[0], Ss[1], Ss[2], w1, w2, c, s);
+    T z1 = c * res[0] + s * res[1], z2 = -s * res[0] + c * res[1];
+    acc.term(w1, z1, T(1) / w1);
+    acc.term(w2, z2, T(1) / w2);
+  } else {
+    T A[MM][MM], V[MM][MM];
+    RD_UNROLL for (int r = 0; r < MM; ++r)
+      RD_UNROLL for (int c = 0; c < MM; ++c) A[r][c] = Ss[sym<MM>(r, c)];
+    eig_jacobi<T, MM>(A, V);
+    RD_UNROLL for (int k = 0; k < MM; ++k) {
+      T z = T(0);
+      RD_UNROLL for (int r = 0; r < MM; ++r) z = rd_fma(V[r][k], res[r], z);
+      acc.term(A[k][k], z, T(1) / A[k][k]);
+    }
+  }
+}
+
+// ---- update (with optional forecast log-density) --------------------------------------------------------------
+// Measurement model  z = wm x + d + N(0, V),  observed value xm, MM rows; `res` = xm - (wm mu_p + d) is supplied by
+// the caller (see Fwd::interrogate for why the solver never forms d).
+//   S = wm S_p wm^T + V ;  K = S_p wm^T S^{-1} ;  mu_f = mu_p + K res ;  S_f = S_p - K (wm S_p)
+// WITH_LOGPDF adds log N(xm; mu_z, S) to `acc` (reference fenrir._forecast_update, fenrir.py:40-81).
+// In-place: mu, S hold the predicted moments on entry and the filtered moments on exit.
+template <typename T, int P, int MM, bool WITH_LOGPDF>
+RD_DEV void update(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], const T (&res)[MM],
+                   const T (&V)[MM * (MM + 1) / 2], LogPdfAcc<T>& acc) {
+  T v[MM][P];    // v[r] = S_p wm[r]^T   (== (wm S_p)[r] by symmetry)
+  T Kt[MM][P];
+  T Sm[MM * (MM + 1) / 2];
+  RD_UNROLL for (int r = 0; r < MM; ++r) {
+    RD_UNROLL for (int i = 0; i < P; ++i) {
+      T a = S[sym<P>(i, 0)] * wm[r][0];
+      RD_UNROLL for (int j = 1; j < P; ++j) a = rd_fma(S[sym<P>(i, j)], wm[r][j], a);
+      v[r][i] = a; Kt[r][i] = a;
+    }
+  }
+  RD_UNROLL for (int r = 0; r < MM; ++r)
+    RD_UNROLL for (int s = r; s < MM; ++s) {
+      T a = V[sidx<MM>(r, s)];
+      RD_UNROLL for (int i = 0; i < P; ++i) a = rd_fma(wm[r][i], v[s][i], a);
+      Sm[sidx<MM>(r, s)] = a;
+    }
+  if (WITH_LOGPDF) logpdf_terms<T, MM>(Sm, res, acc);
+  solve_small<T, MM, P>(Sm, Kt);
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T m = mu[i];
+    RD_UNROLL for (int r = 0; r < MM; ++r) m = rd_fma(Kt[r][i], res[r], m);
+    mu[i] = m;
+  }
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int j = i; j < P; ++j) {
+      T s = S[sidx<P>(i, j)];
+      RD_UNROLL for (int r = 0; r < MM; ++r) s = rd_fma(-Kt[r][i], v[r][j], s);
+      S[sidx<P>(i, j)] = s;
+    }
+}
+
+// ---- SPD factorisations ---------------------------------------------------------------------------------------
+// L D L^T of a symmetric positive definite matrix (unit lower L packed into Lo[i][j], j<i; reciprocals of D).
+template <typename T, int P>
+RD_DEV void ldlt(const T (&S)[P * (P + 1) / 2], T (&L)[P][P], T (&rD)[P]) {
+  T D[P];
+  RD_UNROLL for (int j = 0; j < P; ++j) {
+    T dj = S[sidx<P>(j, j)];
+    RD_UNROLL for (int k = 0; k < j; ++k) dj = rd_fma(-L[j][k] * L[j][k], D[k], dj);
+    D[j] = dj; rD[j] = T(1) / dj;
+    RD_UNROLL for (int i = j + 1; i < P; ++i) {
+      T s = S[sidx<P>(j, i)];
+      RD_UNROLL for (int k = 0; k < j; ++k) s = rd_fma(-L[i][k] * L[j][k], D[k], s);
+      L[i][j] = s * rD[j];
+    }
+  }
+}
+
+// x <- S^{-1} x given the factorisation
+template <typename T, int P>
+RD_DEV void ldlt_solve(const T (&L)[P][P], const T (&rD)[P], T (&x)[P]) {
+  RD_UNROLL for (int i = 1; i < P; ++i)
+    RD_UNROLL for (int k = 0; k < i; ++k) x[i] = rd_fma(-L[i][k], x[k], x[i]);
+  RD_UNROLL for (int i = 0; i < P; ++i) x[i] *= rD[i];
+  RD_UNROLL for (int i = P - 2; i >= 0; --i)
+    RD_UNROLL for (int k = i + 1; k < P; ++k) x[i] = rd_fma(-L[k][i], x[k], x[i]);
+}
+
+// Guarded Cholesky-type factor A (lower triangular, A A^T = C) of a symmetric positive SEMI-definite matrix:
+// a pivot d_j <= 0 produces a zero column.  The smoothing covariances of a noise-free measurement model are
+// rank deficient, which is why the reference samples with an SVD factor (src/rodeo/solve.py:179,196-198); any
+// factor gives the same distribution.  Mirrors oracle psd_factor(method="ldl").
+template <typename T, int P>
+RD_DEV void psd_factor(const T (&C)[P * (P + 1) / 2], T (&A)[P][P]) {
+  RD_UNROLL for (int j = 0; j < P; ++j) {
+    T d = C[sidx<P>(j, j)];
+    RD_UNROLL for (int k = 0; k < j; ++k) d = rd_fma(-A[j][k], A[j][k], d);
+    bool pos = d > T(0);
+    T dj = sqrt(pos ? d : T(1));
+    T rdj = T(1) / dj;
+    A[j][j] = pos ? dj : T(0);
+    RD_UNROLL for (int i = j + 1; i < P; ++i) {
+      T s = C[sidx<P>(j, i)];
+      RD_UNROLL for (int k = 0; k < j; ++k) s = rd_fma(-A[i][k], A[j][k], s);
+      A[i][j] = pos ? s * rdj : T(0);
+    }
+  }
+}
+
+// ---- smoother gain ---------------------------------------------------------------------------------------------
+// G = S_f Q^T S_p^{-1}   (reference _smooth, standard.py:175-176: solve_var(S_p, (S_f Q^T)^T)^T).
+// S_p is symmetric positive definite (Q S_f Q^T + R with R > 0): an un-pivoted LDL^T replaces the reference's
+// pivoted LU; both are backward stable and agree to rounding.
+// Also returns Ct = S_f Q^T (full P x P), needed by smooth_sim / smooth_cond.
+template <typename T, int P, int QK>
+RD_DEV void smooth_gain(const T (&Q)[P][P], const T (&Sf)[P * (P + 1) / 2], const T (&Sp)[P * (P + 1) / 2],
+                        T (&G)[P][P], T (&Ct)[P][P]) {
+  // Ct[i][j] = sum_k Sf[i][k] Q[j][k]
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int j = 0; j < P; ++j) {
+      T a;
+      if (QK == QK_UNIT_UPPER) {
+        a = Sf[sym<P>(i, j)];
+        RD_UNROLL for (int k = j + 1; k < P; ++k) a = rd_fma(Sf[sym<P>(i, k)], Q[j][k], a);
+      } else {
+        a = Sf[sym<P>(i, 0)] * Q[j][0];
+        RD_UNROLL for (int k = 1; k < P; ++k) a = rd_fma(Sf[sym<P>(i, k)], Q[j][k], a);
+      }
+      Ct[i][j] = a;
+    }
+  T L[P][P], rD[P];
+  ldlt<T, P>(Sp, L, rD);
+  // row i of G solves S_p g = Ct[i]^T
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T x[P];
+    RD_UNROLL for (int j = 0; j < P; ++j) x[j] = Ct[i][j];
+    ldlt_solve<T, P>(L, rD, x);
+    RD_UNROLL for (int j = 0; j < P; ++j) G[i][j] = x[j];
+  }
+}
+
+// sym result of  base + sgn * G D G^T  with D symmetric packed  (smooth_mv, standard.py:215-216)
+template <typename T, int P>
+RD_DEV void add_GDGt(const T (&G)[P][P], const T (&D)[P * (P + 1) / 2], T (&out)[P * (P + 1) / 2]) {
+  T GD[P][P];
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int k = 0; k < P; ++k) {
+      T a = G[i][0] * D[sym<P>(0, k)];
+      RD_UNROLL for (int j = 1; j < P; ++j) a = rd_fma(G[i][j], D[sym<P>(j, k)], a);
+      GD[i][k] = a;
+    }
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int j = i; j < P; ++j) {
+      T a = out[sidx<P>(i, j)];
+      RD_UNROLL for (int k = 0; k < P; ++k) a = rd_fma(GD[i][k], G[j][k], a);
+      out[sidx<P>(i, j)] = a;
+    }
+}
+
+// C = S_f - G Ct^T   (smooth_sim / smooth_cond variance, standard.py:253-254, 370)
+template <typename T, int P>
+RD_DEV void cond_var(const T (&Sf)[P * (P + 1) / 2], const T (&G)[P][P], const T (&Ct)[P][P],
+                     T (&C)[P * (P + 1) / 2]) {
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int j = i; j < P; ++j) {
+      T a = Sf[sidx<P>(i, j)];
+      RD_UNROLL for (int k = 0; k < P; ++k) a = rd_fma(-G[i][k], Ct[j][k], a);
+      C[sidx<P>(i, j)] = a;
+    }
+}
+
+// ---- counter-based RNG -------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Draws are keyed by (user key, global particle index, step, stream tag) so
+// results do not depend on how the theta batch is sharded over GPUs.  Bit-parity with JAX's threefry key
+// splitting is neither attempted nor attainable; sampling paths are checked in distribution and,
+// deterministically, by injecting normals.
+struct Philox {
+  unsigned k0, k1;
+  RD_DEV void operator()(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned (&out)[4]) const {
+    unsigned ka = k0, kb = k1;
+    RD_UNROLL for (int r = 0; r < 10; ++r) {
+      unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ ka; c1 = lo1; c2 = hi0 ^ c3 ^ kb; c3 = lo0;
+      ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+
+// two independent standard normals from 128 random bits (Box-Muller on 53-bit uniforms)
+RD_DEV void normal_pair(const unsigned (&r)[4], double& z0, double& z1) {
+  unsigned long long a = ((unsigned long long)r[0] << 32) | r[1];
+  unsigned long long b = ((unsigned long long)r[2] << 32) | r[3];
+  double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);   // (0,1)
+  double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = rad * c; z1 = rad * s;
+}
+RD_DEV void normal_pair(const unsigned (&r)[4], float& z0, float& z1) {
+  float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float rad = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  z0 = rad * c; z1 = rad * s;
+}
+
+}  // namespace rodeo

@@ -1,0 +1,138 @@
+// Host-side plumbing shared by the C-ABI translation units: error reporting, packing of (W, Q, R) into the
+// kernel-parameter struct, and the (model, interrogation, Q-structure) dispatch over the ahead-of-time
+// instantiations.  One translation unit per op keeps nvcc compile times parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rodeo_b200.h"
+#include "rodeo_kernels.cuh"
+
+namespace rodeo {
+namespace host {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return RODEO_ERR_CUDA;
+}
+
+#define RODEO_CUDA_OK(call)                                             \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return ::rodeo::host::cuda_fail(e__, #call); \
+  } while (0)
+
+// Q is "unit upper triangular" (every IBM prior is: src/rodeo/prior/ibm.py:55-57) iff, exactly,
+// diag == 1 and the strict lower triangle == 0 for every block.
+template <typename T>
+inline int detect_qkind(const T* Q, int nb, int p) {
+  for (int b = 0; b < nb; ++b)
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j <= i; ++j) {
+        T v = Q[(b * p + i) * p + j];
+        if (i == j ? (v != T(1)) : (v != T(0))) return QK_DENSE;
+      }
+  return QK_UNIT_UPPER;
+}
+
+template <typename T, int NB, int P, int M>
+inline void pack_consts(const T* W, const T* Q, const T* R, FilterConsts<T, NB, P, M>& C) {
+  for (int b = 0; b < NB; ++b) {
+    for (int i = 0; i < P; ++i)
+      for (int j = 0; j < P; ++j) C.Q[b][i][j] = Q[(b * P + i) * P + j];
+    int k = 0;
+    for (int i = 0; i < P; ++i)
+      for (int j = i; j < P; ++j) C.R[b][k++] = R[(b * P + i) * P + j];
+    for (int r = 0; r < M; ++r)
+      for (int j = 0; j < P; ++j) C.W[b][r][j] = W[(b * M + r) * P + j];
+  }
+}
+
+template <typename T>
+inline CommonArgs<T> make_common(const RodeoProblem& p, const T* ode_init, const T* theta, const T* z_interr) {
+  CommonArgs<T> a;
+  a.B = p.B; a.particle_offset = p.particle_offset; a.n_steps = p.n_steps;
+  a.t_min = (T)p.t_min; a.t_max = (T)p.t_max;
+  a.theta = theta; a.ode_init = ode_init; a.key0 = p.key[0]; a.key1 = p.key[1]; a.z_interr = z_interr;
+  return a;
+}
+
+template <class Model>
+inline bool dims_match(const RodeoProblem& p) {
+  return p.n_block == Model::NB && p.n_bstate == Model::P && p.n_bmeas == Model::M && p.n_theta == Model::NTHETA;
+}
+
+inline int check_common(const RodeoProblem* p) {
+  if (!p) { set_error("RodeoProblem is NULL"); return RODEO_ERR_INVALID; }
+  if (p->B < 0 || p->n_steps < 1) { set_error("need B >= 0 and n_steps >= 1 (B=%lld, n_steps=%d)", (long long)p->B, p->n_steps); return RODEO_ERR_INVALID; }
+  if (p->kalman_type != RODEO_KALMAN_STANDARD) {
+    // reference src/rodeo/solve.py:236-241 raises NotImplementedError for unknown kalman_type
+    set_error("kalman_type %d is not built (only \"standard\")", p->kalman_type);
+    return RODEO_ERR_UNSUPPORTED;
+  }
+  return RODEO_OK;
+}
+
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+// leading dimension of the theta-innermost stash
+inline long long stash_ldb(long long B) { return (long long)round_up((size_t)(B > 0 ? B : 1), 32); }
+
+// ---- ahead-of-time instantiation set -----------------------------------------------------------------------------
+// X(ModelType, RODEO_MODEL_id)
+#ifdef RODEO_FAST_BUILD
+#define RODEO_AOT_MODELS(X) X(FitzHughNagumo, RODEO_MODEL_FITZHUGH_NAGUMO)
+#else
+#define RODEO_AOT_MODELS(X)                              \
+  X(FitzHughNagumo, RODEO_MODEL_FITZHUGH_NAGUMO)         \
+  X(Lorenz63, RODEO_MODEL_LORENZ63)                      \
+  X(SecondOrderSin, RODEO_MODEL_SECOND_ORDER_SIN)        \
+  X(Hes1, RODEO_MODEL_HES1)                              \
+  X(Seirah, RODEO_MODEL_SEIRAH)
+#endif
+
+// Calls FN<Model, INTERR, QK>::run(args...) for the runtime (model_id, interr, qk); RODEO_ERR_UNSUPPORTED otherwise.
+template <template <class, int, int> class FN, class Model, int INTERR, typename... A>
+inline int dispatch_qk(int qk, A&&... args) {
+  if (qk == QK_UNIT_UPPER) return FN<Model, INTERR, QK_UNIT_UPPER>::run(static_cast<A&&>(args)...);
+  return FN<Model, INTERR, QK_DENSE>::run(static_cast<A&&>(args)...);
+}
+template <template <class, int, int> class FN, class Model, typename... A>
+inline int dispatch_interr(int interr, int qk, A&&... args) {
+  switch (interr) {
+    case RODEO_INTERROGATE_KRAMER: return dispatch_qk<FN, Model, INTERR_KRAMER>(qk, static_cast<A&&>(args)...);
+    case RODEO_INTERROGATE_CHKREBTII: return dispatch_qk<FN, Model, INTERR_CHKREBTII>(qk, static_cast<A&&>(args)...);
+    case RODEO_INTERROGATE_SCHOBER: return dispatch_qk<FN, Model, INTERR_SCHOBER>(qk, static_cast<A&&>(args)...);
+    case RODEO_INTERROGATE_RODEO: return dispatch_qk<FN, Model, INTERR_RODEO>(qk, static_cast<A&&>(args)...);
+  }
+  set_error("unknown interrogate id %d", interr);
+  return RODEO_ERR_UNSUPPORTED;
+}
+template <template <class, int, int> class FN, typename... A>
+inline int dispatch_model(const RodeoProblem& p, int qk, A&&... args) {
+  switch (p.model_id) {
+#define RODEO_CASE(MODEL, ID)                                                                                 \
+  case ID:                                                                                                    \
+    if (!dims_match<MODEL>(p)) {                                                                              \
+      set_error(#MODEL " expects (n_block,n_bstate,n_bmeas,n_theta)=(%d,%d,%d,%d), got (%d,%d,%d,%d)",        \
+                MODEL::NB, MODEL::P, MODEL::M, MODEL::NTHETA, p.n_block, p.n_bstate, p.n_bmeas, p.n_theta);   \
+      return RODEO_ERR_INVALID;                                                                               \
+    }                                                                                                         \
+    return dispatch_interr<FN, MODEL>(p.interrogate, qk, static_cast<A&&>(args)...);
+    RODEO_AOT_MODELS(RODEO_CASE)
+#undef RODEO_CASE
+  }
+  set_error("model id %d is not compiled into the library (register it with rodeo_b200_register_model_nvrtc)", p.model_id);
+  return RODEO_ERR_UNSUPPORTED;
+}
+
+inline unsigned grid_for(long long B, int block) { return (unsigned)((B + block - 1) / block); }
+
+}  // namespace host
+}  // namespace rodeo

@@ -1,0 +1,37 @@
+"""IBM prior (host side) -- same closed forms as reference src/rodeo/prior/ibm.py:21-88.
+
+Q, R are *inputs* to the kernels (tiny, shared by the theta batch); they are built on the host with the
+reference's own formula, including ``exp(gammaln(x+1))`` for the factorials.
+"""
+import math
+
+import numpy as np
+
+
+def _factorial(x):
+    x = np.asarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    for idx in np.ndindex(x.shape):
+        a = float(x[idx]) + 1.0
+        out[idx] = math.inf if (a <= 0.0 and a == math.floor(a)) else math.exp(math.lgamma(a))
+    return out
+
+
+def ibm_state(dt, q, sigma):
+    """reference src/rodeo/prior/ibm.py:37-62"""
+    I, J = np.meshgrid(np.arange(q + 1), np.arange(q + 1), indexing="ij", sparse=True)
+    mesh = (J - I).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        Q = np.nan_to_num(np.float64(dt) ** mesh / _factorial(mesh), nan=0.0)
+    mesh = (2.0 * q + 1.0) - I - J
+    R = sigma ** 2 * (np.float64(dt) ** mesh) / (mesh * _factorial(q - I) * _factorial(q - J))
+    return Q, R
+
+
+def ibm_init(dt, n_deriv, sigma):
+    """(wgt_state, var_state) of shapes (n_block, p, p) -- reference src/rodeo/prior/ibm.py:65-88."""
+    sigma = np.asarray(sigma, dtype=np.float64)
+    Q1, R1 = ibm_state(dt, n_deriv - 1, 1)
+    Q = np.repeat(Q1[None], len(sigma), axis=0)
+    R = np.stack([sigma[b] ** 2 * R1 for b in range(len(sigma))])
+    return Q, R

@@ -1,0 +1,58 @@
+"""Drop-in ``solve_mv`` / ``solve_sim`` (reference src/rodeo/solve.py:125-302) on the B200 kernels."""
+import ctypes
+
+import torch
+
+from . import _host, _lib
+
+
+def solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars=None,
+             kalman_type="standard", prior_weight=None, prior_var=None, _z_interr=None, **params):
+    r"""Mean and variance of the stochastic ODE solver (reference src/rodeo/solve.py:208-302).
+
+    Same arguments as the reference; ``theta`` / ``ode_init`` may carry a leading batch axis ``B``.
+
+    Returns:
+        mean (``[B,] n_steps+1, n_block, n_bstate``), var (``[B,] n_steps+1, n_block, n_bstate, n_bstate``)
+        as float64 CUDA tensors.
+    """
+    pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
+                       prior_weight, prior_var, kalman_type, params)
+    N, dev = pb.n_steps, _host.device()
+    mean = torch.empty((pb.B, N + 1, pb.nb, pb.p), dtype=torch.float64, device=dev)
+    var = torch.empty((pb.B, N + 1, pb.nb, pb.p, pb.p), dtype=torch.float64, device=dev)
+    ws, n = pb.workspace(_lib.OP_SOLVE_MV)
+    zi = None if _z_interr is None else _host.to_dev(_z_interr)
+    rc = pb.lib.rodeo_b200_solve_mv_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
+                                        _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(mean),
+                                        _host.ptr(var), _host.ptr(ws), n, pb.stream())
+    _lib.check(rc, "solve_mv")
+    return pb.unbatch(mean), pb.unbatch(var)
+
+
+def solve_sim(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars=None,
+              kalman_type="standard", prior_weight=None, prior_var=None, _z_interr=None, _z_smooth=None,
+              _particle_offset=0, **params):
+    r"""One draw of the solution posterior per theta (reference src/rodeo/solve.py:125-205).
+
+    Random draws come from a counter-based Philox generator keyed by ``(key, particle index, step)``; they are
+    equal in distribution to the reference's, not bit-identical to JAX's threefry streams.
+    ``_z_smooth`` / ``_z_interr`` inject standard normals instead (testing hook).
+
+    Returns:
+        ``[B,] n_steps+1, n_block, n_bstate`` float64 CUDA tensor.
+    """
+    if key is None and _z_smooth is None:
+        raise TypeError("solve_sim needs a PRNG key")
+    pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
+                       prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
+    N, dev = pb.n_steps, _host.device()
+    x = torch.empty((pb.B, N + 1, pb.nb, pb.p), dtype=torch.float64, device=dev)
+    ws, n = pb.workspace(_lib.OP_SOLVE_SIM)
+    zi = None if _z_interr is None else _host.to_dev(_z_interr)
+    zs = None if _z_smooth is None else _host.to_dev(_z_smooth)
+    rc = pb.lib.rodeo_b200_solve_sim_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
+                                         _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(zs),
+                                         _host.ptr(x), _host.ptr(ws), n, pb.stream())
+    _lib.check(rc, "solve_sim")
+    return pb.unbatch(x)

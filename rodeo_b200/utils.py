@@ -1,0 +1,42 @@
+"""Host-side helpers with the reference's names (src/rodeo/utils.py)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _host, _lib, models as _models
+
+
+def first_order_pad(ode_fun, n_vars, n_deriv):
+    r"""W and the initial-value helper for a first-order ODE (reference src/rodeo/utils.py:80-102).
+
+    Returns ``(W, ode_init)``: ``W`` is the ``(n_vars, 1, n_deriv)`` NumPy matrix with ``W[:, :, 1] = 1``;
+    ``ode_init(x0, t, theta=...)`` returns ``[x0, f(x0, t, theta), 0, ...]`` evaluated **on the device with the
+    same functor the solver uses**, for ``x0`` of shape ``(n_vars,)`` or ``(B, n_vars)``.
+    """
+    model = _models.resolve(ode_fun)
+    if (model.n_block, model.n_bstate) != (n_vars, n_deriv):
+        raise ValueError(f"{model.name} is compiled for n_vars={model.n_block}, n_deriv={model.n_bstate}")
+
+    def ode_init(x0, t, **params):
+        theta = _host.to_dev(params["theta"])
+        x0d = _host.to_dev(x0)
+        batched = theta.ndim == 2 or x0d.ndim == 2
+        theta = theta[None] if theta.ndim == 1 else theta
+        x0d = x0d[None] if x0d.ndim == 1 else x0d
+        B = max(theta.shape[0], x0d.shape[0])
+        theta = theta.expand(B, theta.shape[1]).contiguous()
+        x0d = x0d.expand(B, n_vars).contiguous()
+        c = _lib.RodeoProblem()
+        c.B, c.n_steps, c.n_block, c.n_bstate, c.n_bmeas = B, 1, n_vars, n_deriv, model.n_bmeas
+        c.n_theta, c.model_id = theta.shape[1], model.model_id
+        X0 = torch.empty((B, n_vars, n_deriv), dtype=torch.float64, device=_host.device())
+        lib = _lib.load()
+        rc = lib.rodeo_b200_ode_init_pad_f64(ctypes.byref(c), float(t), _host.ptr(theta), _host.ptr(x0d),
+                                             _host.ptr(X0), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "ode_init")
+        return X0 if batched else X0[0]
+
+    W = np.zeros((n_vars, 1, n_deriv))
+    W[:, :, 1] = 1.0
+    return W, ode_init
