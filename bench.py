@@ -191,7 +191,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     dev = torch.device("cuda", local)
-    B, N = B_PER_GPU, N_STEPS
+    B, N = args.thetas, N_STEPS
 
     # ---- synthetic inputs: each rank owns its own contiguous shard of the global theta batch (weak scaling)
     pr = workload(B, seed=rank)
@@ -262,19 +262,20 @@ def run_ours(args):
                                             ctypes.c_void_p(h_out.data_ptr()))
         _lib.check(rc, "dalton_host")
 
-    for _ in range(3):
+    n_e2e = 0 if args.skip_e2e else args.steps
+    for _ in range(0 if args.skip_e2e else 3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         e2e_step()                      # returns after the D2H copy has completed (stream synchronised inside)
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * N * args.steps / float(t_e2e.item())
+    e2e_value = world * B * N * n_e2e / float(t_e2e.item()) if n_e2e else None
     h2d = int(h_x0.numel() * 8 + h_th.numel() * 8 + h_ind.nbytes + h_y.nbytes + h_D.nbytes + h_Om.nbytes)
     d2h = int(h_out.numel() * 8)
-    same = bool(np.allclose(h_out.numpy(), out.cpu().numpy(), rtol=0, atol=0, equal_nan=True))
+    same = bool(np.array_equal(h_out.numpy(), out.cpu().numpy(), equal_nan=True)) if n_e2e else None
 
     if rank != 0:
         if world > 1:
@@ -308,7 +309,7 @@ def run_ours(args):
                      "hbm_gbs_measured": peaks.get("hbm_gbs")},
     }
 
-    cpu = cpu_baseline() if world == 1 else None
+    cpu = cpu_baseline() if (world == 1 and not args.skip_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -334,6 +335,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--thetas", type=int, default=B_PER_GPU,
+                    help="thetas per GPU (tuning experiments only; the benchmark configuration is the default)")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

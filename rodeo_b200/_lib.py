@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librodeo_b200.so")
+LIB_PATH = os.environ.get("RODEO_B200_LIB") or os.path.join(_HERE, "librodeo_b200.so")   # env: tuning builds
 
 c_double_p = ctypes.c_void_p
 c_int32_p = ctypes.c_void_p

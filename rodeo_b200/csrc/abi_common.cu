@@ -135,7 +135,7 @@ int rodeo_b200_ode_init_pad_f64(const RodeoProblem* p, double t, const double* t
   if (p->n_bstate < 2) { set_error("first_order_pad needs n_deriv >= 2"); return RODEO_ERR_INVALID; }
   RodeoProblem q = *p;
   q.interrogate = RODEO_INTERROGATE_KRAMER;
-  return dispatch_model<InitPadRun>(q, QK_DENSE, q, t, theta, x0, X0, (cudaStream_t)stream);
+  return dispatch_model<InitPadRun>(q, (const double*)nullptr, (const double*)nullptr, q, t, theta, x0, X0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -15,7 +15,7 @@ struct DaltonRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    dalton_kernel<double, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32, 0, s>>>(C, a, o, out);
+    dalton_kernel<double, Model, INTERR, QK, 1><<<grid_for(2 * p.B, 32), 32, 0, s>>>(C, a, o, out);
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;
@@ -36,9 +36,8 @@ extern "C" int rodeo_b200_dalton_f64(const RodeoProblem* p, const double* ode_we
   (void)workspace; (void)workspace_bytes;
   if (int rc = check_common(p)) return rc;
   if (p->n_obs < 1) { set_error("dalton needs n_obs >= 1"); return RODEO_ERR_INVALID; }
-  const int qk = detect_qkind<double>(prior_weight, p->n_block, p->n_bstate);
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
   ObsArgs<double> o{p->n_obs, obs_ind, obs_data, obs_weight, obs_var};
-  return dispatch_model<DaltonRun>(*p, qk, *p, ode_weight, prior_weight, prior_var, a, o, loglik_out,
+  return dispatch_model<DaltonRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, o, loglik_out,
                                    (cudaStream_t)stream);
 }

@@ -40,9 +40,8 @@ extern "C" int rodeo_b200_fenrir_f64(const RodeoProblem* p, const double* ode_we
     set_error("workspace too small: need %zu bytes, got %zu", need, workspace ? workspace_bytes : (size_t)0);
     return RODEO_ERR_WORKSPACE;
   }
-  const int qk = detect_qkind<double>(prior_weight, p->n_block, p->n_bstate);
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
   ObsArgs<double> o{p->n_obs, obs_ind, obs_data, obs_weight, obs_var};
-  return dispatch_model<FenrirRun>(*p, qk, *p, ode_weight, prior_weight, prior_var, a, o, (double*)workspace,
+  return dispatch_model<FenrirRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, o, (double*)workspace,
                                    loglik_out, (cudaStream_t)stream);
 }

@@ -56,9 +56,8 @@ extern "C" int rodeo_b200_solve_mv_f64(const RodeoProblem* p, const double* ode_
                                        size_t workspace_bytes, void* stream) {
   if (int rc = check_common(p)) return rc;
   if (int rc = check_ws(RODEO_OP_SOLVE_MV, p, workspace, workspace_bytes)) return rc;
-  const int qk = detect_qkind<double>(prior_weight, p->n_block, p->n_bstate);
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
-  return dispatch_model<SolveMvRun>(*p, qk, *p, ode_weight, prior_weight, prior_var, a, (double*)workspace,
+  return dispatch_model<SolveMvRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, (double*)workspace,
                                     mean_out, var_out, (cudaStream_t)stream);
 }
 
@@ -68,8 +67,7 @@ extern "C" int rodeo_b200_solve_sim_f64(const RodeoProblem* p, const double* ode
                                         void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_common(p)) return rc;
   if (int rc = check_ws(RODEO_OP_SOLVE_SIM, p, workspace, workspace_bytes)) return rc;
-  const int qk = detect_qkind<double>(prior_weight, p->n_block, p->n_bstate);
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
-  return dispatch_model<SolveSimRun>(*p, qk, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
+  return dispatch_model<SolveSimRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
                                      (double*)workspace, x_out, (cudaStream_t)stream);
 }

@@ -47,6 +47,21 @@ template <> struct Lim<float> {
   RD_DEV static float nan() { return __int_as_float(0x7fc00000); }
 };
 
+// ---- reciprocal ---------------------------------------------------------------------------------------------------
+// 1/x to <= 1 ulp without the branchy slow path of the IEEE division sequence: MUFU.RCP64H seed (>= 20 bits) and two
+// Newton steps.  Zero, infinite, NaN and subnormal arguments yield inf/NaN garbage, exactly where the reference's
+// LAPACK solve would have produced inf/NaN as well (a singular innovation variance).
+RD_DEV double rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+RD_DEV float rcp(float x) { return __frcp_rn(x); }
+
 // ---- constants that live in the kernel-parameter constant bank ------------------------------------------
 // Q, R, W are shared by every theta of a launch (reference layouts (nb,p,p), (nb,p,p), (nb,m,p)); passing them
 // by value as a __grid_constant__ kernel parameter lets every DFMA take them as c[0][..] operands: they cost
@@ -183,7 +198,7 @@ struct LogPdfAcc {
 template <typename T, int MM, int P>
 RD_DEV void solve_small(const T (&Ss)[MM * (MM + 1) / 2], T (&Bm)[MM][P]) {
   if (MM == 1) {
-    T r = T(1) / Ss[0];
+    T r = rcp(Ss[0]);
     RD_UNROLL for (int i = 0; i < P; ++i) Bm[0][i] *= r;
     return;
   }
@@ -203,7 +218,7 @@ RD_DEV void solve_small(const T (&Ss)[MM * (MM + 1) / 2], T (&Bm)[MM][P]) {
         Bm[k][c] = sw ? b : a; Bm[r][c] = sw ? a : b;
       }
     }
-    T rp = T(1) / A[k][k];
+    T rp = rcp(A[k][k]);
     RD_UNROLL for (int r = k + 1; r < MM; ++r) {
       T l = A[r][k] * rp;
       RD_UNROLL for (int c = k + 1; c < MM; ++c) A[r][c] = rd_fma(-l, A[k][c], A[r][c]);
@@ -211,7 +226,7 @@ RD_DEV void solve_small(const T (&Ss)[MM * (MM + 1) / 2], T (&Bm)[MM][P]) {
     }
   }
   RD_UNROLL for (int k = MM - 1; k >= 0; --k) {
-    T rp = T(1) / A[k][k];
+    T rp = rcp(A[k][k]);
     RD_UNROLL for (int c = 0; c < P; ++c) {
       T s = Bm[k][c];
       RD_UNROLL for (int j = k + 1; j < MM; ++j) s = rd_fma(-A[k][j], Bm[j][c], s);
@@ -282,13 +297,13 @@ RD_DEV void eig_jacobi(T (&A)[MM][MM], T (&V)[MM][MM]) {
 template <typename T, int MM>
 RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], LogPdfAcc<T>& acc) {
   if (MM == 1) {
-    acc.term(Ss[0], res[0], T(1) / Ss[0]);
+    acc.term(Ss[0], res[0], rcp(Ss[0]));
   } else if (MM == 2) {
     T w1, w2, c, s;
     eig2<T>(Ss[0], Ss[1], Ss[2], w1, w2, c, s);
     T z1 = c * res[0] + s * res[1], z2 = -s * res[0] + c * res[1];
-    acc.term(w1, z1, T(1) / w1);
-    acc.term(w2, z2, T(1) / w2);
+    acc.term(w1, z1, rcp(w1));
+    acc.term(w2, z2, rcp(w2));
   } else {
     T A[MM][MM], V[MM][MM];
     RD_UNROLL for (int r = 0; r < MM; ++r)
@@ -297,7 +312,7 @@ RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], L
     RD_UNROLL for (int k = 0; k < MM; ++k) {
       T z = T(0);
       RD_UNROLL for (int r = 0; r < MM; ++r) z = rd_fma(V[r][k], res[r], z);
-      acc.term(A[k][k], z, T(1) / A[k][k]);
+      acc.term(A[k][k], z, rcp(A[k][k]));
     }
   }
 }
@@ -342,6 +357,30 @@ RD_DEV void update(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], co
     }
 }
 
+// Scalar-measurement update for a row of the form  wm = e_WK - [jl_0 .. jl_{JC-1}, 0, ...]  (what interrogate_kramer
+// produces for W = e_WK and a right-hand side that reads the leading JC state columns; jl == 0 for the other
+// interrogations).  Same arithmetic as update<T,P,1,...> with the multiplications by the structural 0 / 1 entries
+// removed (those are exact, so the results are bitwise those of the general row).
+template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J>
+RD_DEV void update_unit_row(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[JC], T res, T V, LogPdfAcc<T>& acc) {
+  T v[P];
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T a = S[sym<P>(i, WK)];
+    if (HAS_J) { RD_UNROLL for (int j = 0; j < JC; ++j) a = rd_fma(-jl[j], S[sym<P>(i, j)], a); }
+    v[i] = a;
+  }
+  T Sm = V + v[WK];
+  if (HAS_J) { RD_UNROLL for (int j = 0; j < JC; ++j) Sm = rd_fma(-jl[j], v[j], Sm); }
+  const T rS = rcp(Sm);
+  if (WITH_LOGPDF) acc.term(Sm, res, rS);
+  const T g = res * rS;
+  RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = rd_fma(v[i], g, mu[i]);
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    const T k = v[i] * rS;
+    RD_UNROLL for (int j = i; j < P; ++j) S[sidx<P>(i, j)] = rd_fma(-k, v[j], S[sidx<P>(i, j)]);
+  }
+}
+
 // ---- SPD factorisations ---------------------------------------------------------------------------------------
 // L D L^T of a symmetric positive definite matrix (unit lower L packed into Lo[i][j], j<i; reciprocals of D).
 template <typename T, int P>
@@ -350,7 +389,7 @@ RD_DEV void ldlt(const T (&S)[P * (P + 1) / 2], T (&L)[P][P], T (&rD)[P]) {
   RD_UNROLL for (int j = 0; j < P; ++j) {
     T dj = S[sidx<P>(j, j)];
     RD_UNROLL for (int k = 0; k < j; ++k) dj = rd_fma(-L[j][k] * L[j][k], D[k], dj);
-    D[j] = dj; rD[j] = T(1) / dj;
+    D[j] = dj; rD[j] = rcp(dj);
     RD_UNROLL for (int i = j + 1; i < P; ++i) {
       T s = S[sidx<P>(j, i)];
       RD_UNROLL for (int k = 0; k < j; ++k) s = rd_fma(-L[i][k] * L[j][k], D[k], s);
@@ -380,7 +419,7 @@ RD_DEV void psd_factor(const T (&C)[P * (P + 1) / 2], T (&A)[P][P]) {
     RD_UNROLL for (int k = 0; k < j; ++k) d = rd_fma(-A[j][k], A[j][k], d);
     bool pos = d > T(0);
     T dj = sqrt(pos ? d : T(1));
-    T rdj = T(1) / dj;
+    T rdj = rcp(dj);
     A[j][j] = pos ? dj : T(0);
     RD_UNROLL for (int i = j + 1; i < P; ++i) {
       T s = C[sidx<P>(j, i)];

@@ -29,16 +29,22 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return ::rodeo::host::cuda_fail(e__, #call); \
   } while (0)
 
-// Q is "unit upper triangular" (every IBM prior is: src/rodeo/prior/ibm.py:55-57) iff, exactly,
-// diag == 1 and the strict lower triangle == 0 for every block.
+// The structured instantiation (QK_UNIT_UPPER) needs, exactly:
+//   Q unit upper triangular for every block (every IBM prior is: src/rodeo/prior/ibm.py:55-57), and
+//   W = e_wcol (one row, a single 1) for every block (what first_order_pad builds: src/rodeo/utils.py:100-101).
+// Anything else runs the dense instantiation.
 template <typename T>
-inline int detect_qkind(const T* Q, int nb, int p) {
+inline int detect_structure(const T* Q, const T* W, int nb, int p, int m, int wcol) {
   for (int b = 0; b < nb; ++b)
     for (int i = 0; i < p; ++i)
       for (int j = 0; j <= i; ++j) {
         T v = Q[(b * p + i) * p + j];
         if (i == j ? (v != T(1)) : (v != T(0))) return QK_DENSE;
       }
+  if (m != 1) return QK_DENSE;
+  for (int b = 0; b < nb; ++b)
+    for (int j = 0; j < p; ++j)
+      if (W[b * p + j] != (j == wcol ? T(1) : T(0))) return QK_DENSE;
   return QK_UNIT_UPPER;
 }
 
@@ -114,8 +120,9 @@ inline int dispatch_interr(int interr, int qk, A&&... args) {
   set_error("unknown interrogate id %d", interr);
   return RODEO_ERR_UNSUPPORTED;
 }
+// W and Q are the host arrays of the call; the structure test needs the model's WCOL, so it happens here.
 template <template <class, int, int> class FN, typename... A>
-inline int dispatch_model(const RodeoProblem& p, int qk, A&&... args) {
+inline int dispatch_model(const RodeoProblem& p, const double* W, const double* Q, A&&... args) {
   switch (p.model_id) {
 #define RODEO_CASE(MODEL, ID)                                                                                 \
   case ID:                                                                                                    \
@@ -124,7 +131,10 @@ inline int dispatch_model(const RodeoProblem& p, int qk, A&&... args) {
                 MODEL::NB, MODEL::P, MODEL::M, MODEL::NTHETA, p.n_block, p.n_bstate, p.n_bmeas, p.n_theta);   \
       return RODEO_ERR_INVALID;                                                                               \
     }                                                                                                         \
-    return dispatch_interr<FN, MODEL>(p.interrogate, qk, static_cast<A&&>(args)...);
+    return dispatch_interr<FN, MODEL>(p.interrogate,                                                          \
+                                      (W && Q) ? detect_structure<double>(Q, W, MODEL::NB, MODEL::P, MODEL::M, \
+                                                                          MODEL::WCOL) : QK_DENSE,             \
+                                      static_cast<A&&>(args)...);
     RODEO_AOT_MODELS(RODEO_CASE)
 #undef RODEO_CASE
   }

@@ -17,11 +17,6 @@
 #include "rodeo_core.cuh"
 #include "rodeo_models.cuh"
 
-// Register cap of the dalton kernel (two filters per thread).  144 registers = 14 one-warp CTAs per SM, so the
-// headline batch of 65,536 thetas (2,048 warps) is resident in a single wave on 148 SMs.
-#ifndef RODEO_DALTON_MAXNREG
-#define RODEO_DALTON_MAXNREG 144
-#endif
 
 namespace rodeo {
 
@@ -78,6 +73,12 @@ template <typename T, class Model, int INTERR, int QK>
 struct Fwd {
   static constexpr int NB = Model::NB, P = Model::P, M = Model::M, JC = Model::JCOLS;
   static constexpr int NS = P * (P + 1) / 2, MS = M * (M + 1) / 2;
+  // QK_UNIT_UPPER is the "structured" instantiation: Q unit upper triangular (every IBM prior) AND, for scalar
+  // measurements, W = e_WCOL in every block (what first_order_pad / the docs' higher-order example build).  The host
+  // checks both exactly and otherwise dispatches the dense instantiation (rodeo_host.h: detect_structure).
+  static constexpr bool UNITW = (QK == QK_UNIT_UPPER) && (M == 1);
+  static constexpr int WK = Model::WCOL;
+  static constexpr bool HAS_J = (INTERR == INTERR_KRAMER);
   typedef FilterConsts<T, NB, P, M> Consts;
   typedef typename Model::template Par<T> Par;
 
@@ -101,17 +102,23 @@ struct Fwd {
     }
   }
 
+  RD_DEV static T Wc(const Consts& C, int b, int r, int j) {
+    if (UNITW) return j == WK ? T(1) : T(0);
+    return C.W[b][r][j];
+  }
+
   // Interrogation at the predicted moments (reference src/rodeo/interrogate.py:13-115) combined with
   // W_meas = ode_weight + wgt_meas (src/rodeo/solve.py:79).  zc[b][j] are the standard normals consumed by
   // interrogate_chkrebtii; only the JC columns the right-hand side can see are ever needed.
   //
-  // Output: the measurement rows wm, their noise V, and the update residual res = x_meas - (wm mu_p + mean_meas)
-  // with x_meas == 0.  For every interrogation this is  f - W mu_p  with f evaluated at mu_p (kramer, schober,
-  // rodeo) or at the draw (chkrebtii): in interrogate_kramer, mean_meas = -f + J mu_p and wm = W - J, so the two
-  // J mu_p terms cancel identically.  Forming the cancelled expression directly drops an O(|J mu_p|) rounding
-  // term from a residual of size sqrt(S) ~ 1e-3 and is strictly more accurate than evaluating both terms.
+  // Output: jl = the block-diagonal Jacobian (kramer; zero otherwise) so that the measurement rows are
+  // wm = W - [jl, 0..]; their noise V; and the update residual res = x_meas - (wm mu_p + mean_meas), x_meas == 0.
+  // For every interrogation this is  f - W mu_p  with f evaluated at mu_p (kramer, schober, rodeo) or at the draw
+  // (chkrebtii): in interrogate_kramer, mean_meas = -f + J mu_p and wm = W - J, so the two J mu_p terms cancel
+  // identically.  Forming the cancelled expression directly drops an O(|J mu_p|) rounding term from a residual of
+  // size sqrt(S) ~ 1e-3 and is strictly more accurate than evaluating both terms.
   RD_DEV void interrogate(const Consts& C, const Par& q, T t, const T (&zc)[NB][JC],
-                          T (&wm)[NB][M][P], T (&res)[NB][M], T (&V)[NB][MS]) const {
+                          T (&jl)[NB][M][JC], T (&res)[NB][M], T (&V)[NB][MS]) const {
     T x[NB][JC];
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       if constexpr (INTERR == INTERR_CHKREBTII) {
@@ -129,45 +136,57 @@ struct Fwd {
       }
     }
     T f[NB][M];
-    if constexpr (INTERR == INTERR_KRAMER) {
-      T J[NB][M][JC];
-      eval_f_jac<Model, T>(q, t, x, f, J);
-      RD_UNROLL for (int b = 0; b < NB; ++b)
-        RD_UNROLL for (int r = 0; r < M; ++r)
-          RD_UNROLL for (int j = 0; j < P; ++j)
-            wm[b][r][j] = (j < JC) ? C.W[b][r][j] - J[b][r][j] : C.W[b][r][j];
+    if constexpr (HAS_J) {
+      eval_f_jac<Model, T>(q, t, x, f, jl);
     } else {
       Model::template rhs<T, T>(q, t, x, f);
       RD_UNROLL for (int b = 0; b < NB; ++b)
         RD_UNROLL for (int r = 0; r < M; ++r)
-          RD_UNROLL for (int j = 0; j < P; ++j) wm[b][r][j] = C.W[b][r][j];
+          RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][r][j] = T(0);
     }
     RD_UNROLL for (int b = 0; b < NB; ++b)
       RD_UNROLL for (int r = 0; r < M; ++r) {
-        T a = f[b][r];
-        RD_UNROLL for (int j = 0; j < P; ++j) a = rd_fma(-C.W[b][r][j], mu[b][j], a);
-        res[b][r] = a;
+        if (UNITW) {
+          res[b][r] = f[b][r] - mu[b][WK];
+        } else {
+          T a = f[b][r];
+          RD_UNROLL for (int j = 0; j < P; ++j) a = rd_fma(-C.W[b][r][j], mu[b][j], a);
+          res[b][r] = a;
+        }
       }
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       if constexpr (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) {
         // var_meas = W S_p W^T  (interrogate.py:25-29, 109-112)
-        T u[M][P];
-        RD_UNROLL for (int r = 0; r < M; ++r)
-          RD_UNROLL for (int i = 0; i < P; ++i) {
-            T a = S[b][sym<P>(i, 0)] * C.W[b][r][0];
-            RD_UNROLL for (int j = 1; j < P; ++j) a = rd_fma(S[b][sym<P>(i, j)], C.W[b][r][j], a);
-            u[r][i] = a;
-          }
-        RD_UNROLL for (int r = 0; r < M; ++r)
-          RD_UNROLL for (int s = r; s < M; ++s) {
-            T a = C.W[b][r][0] * u[s][0];
-            RD_UNROLL for (int i = 1; i < P; ++i) a = rd_fma(C.W[b][r][i], u[s][i], a);
-            V[b][sidx<M>(r, s)] = a;
-          }
+        if (UNITW) {
+          V[b][0] = S[b][sidx<P>(WK, WK)];
+        } else {
+          T u[M][P];
+          RD_UNROLL for (int r = 0; r < M; ++r)
+            RD_UNROLL for (int i = 0; i < P; ++i) {
+              T a = S[b][sym<P>(i, 0)] * C.W[b][r][0];
+              RD_UNROLL for (int j = 1; j < P; ++j) a = rd_fma(S[b][sym<P>(i, j)], C.W[b][r][j], a);
+              u[r][i] = a;
+            }
+          RD_UNROLL for (int r = 0; r < M; ++r)
+            RD_UNROLL for (int s = r; s < M; ++s) {
+              T a = C.W[b][r][0] * u[s][0];
+              RD_UNROLL for (int i = 1; i < P; ++i) a = rd_fma(C.W[b][r][i], u[s][i], a);
+              V[b][sidx<M>(r, s)] = a;
+            }
+        }
       } else {
         RD_UNROLL for (int k = 0; k < MS; ++k) V[b][k] = T(0);
       }
     }
+  }
+
+  // measurement rows wm = W - [jl, 0..] of block b
+  RD_DEV static void rows(const Consts& C, int b, const T (&jl)[M][JC], T (&wm)[M][P]) {
+    RD_UNROLL for (int r = 0; r < M; ++r)
+      RD_UNROLL for (int j = 0; j < P; ++j) {
+        T w = Wc(C, b, r, j);
+        wm[r][j] = (HAS_J && j < JC) ? w - jl[r][j] : w;
+      }
   }
 
   // normals for this step's chkrebtii interrogation: injected array or Philox
@@ -193,21 +212,31 @@ struct Fwd {
 
   // plain ODE-measurement update of every block, x_meas == 0 (solve.py:51, 81-88)
   template <bool WITH_LOGPDF>
-  RD_DEV void update_z(const T (&wm)[NB][M][P], const T (&res)[NB][M], const T (&V)[NB][MS], LogPdfAcc<T>& acc) {
-    RD_UNROLL for (int b = 0; b < NB; ++b) update<T, P, M, WITH_LOGPDF>(mu[b], S[b], wm[b], res[b], V[b], acc);
+  RD_DEV void update_z(const Consts& C, const T (&jl)[NB][M][JC], const T (&res)[NB][M], const T (&V)[NB][MS],
+                       LogPdfAcc<T>& acc) {
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      if constexpr (UNITW) {
+        update_unit_row<T, P, JC, WK, WITH_LOGPDF, HAS_J>(mu[b], S[b], jl[b][0], res[b][0], V[b][0], acc);
+      } else {
+        T wm[M][P];
+        rows(C, b, jl[b], wm);
+        update<T, P, M, WITH_LOGPDF>(mu[b], S[b], wm, res[b], V[b], acc);
+      }
+    }
   }
 
   // observation-augmented update (dalton zy_update, dalton.py:136-149): rows [W~; D_i], offsets [d; 0],
   // noise blockdiag(V, Omega_i), observed value [0; y_i]  ->  residual [res; y_i - D_i mu_p]
   template <int NOBS, bool WITH_LOGPDF>
-  RD_DEV void update_zy(const T (&wm)[NB][M][P], const T (&res)[NB][M], const T (&V)[NB][MS],
+  RD_DEV void update_zy(const Consts& C, const T (&jl)[NB][M][JC], const T (&res)[NB][M], const T (&V)[NB][MS],
                         const ObsArgs<T>& o, int i, LogPdfAcc<T>& acc) {
     constexpr int MA = M + NOBS, MAS = MA * (MA + 1) / 2;
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T wa[MA][P], ra[MA], Va[MAS];
+      T wa[MA][P], ra[MA], Va[MAS], wm[M][P];
+      rows(C, b, jl[b], wm);
       RD_UNROLL for (int k = 0; k < MAS; ++k) Va[k] = T(0);
       RD_UNROLL for (int r = 0; r < M; ++r) {
-        RD_UNROLL for (int j = 0; j < P; ++j) wa[r][j] = wm[b][r][j];
+        RD_UNROLL for (int j = 0; j < P; ++j) wa[r][j] = wm[r][j];
         ra[r] = res[b][r];
         RD_UNROLL for (int s = r; s < M; ++s) Va[sidx<MA>(r, s)] = V[b][sidx<M>(r, s)];
       }
@@ -249,34 +278,45 @@ struct Fwd {
 // ------------------------------------------------------------------------------------------------------------------
 // dalton: log p(Y | Z) = log p(Z, Y) - log p(Z), two forward filters, scalar output, no history
 // ------------------------------------------------------------------------------------------------------------------
+// Thread mapping: one thread per (theta, filter); lanes 2k / 2k+1 of a warp run the joint (Z,Y) and the marginal (Z)
+// filter of the same theta and meet in a single shuffle at the end.  The two filters execute identical code except
+// on the n_obs observation steps, where the joint lanes take the augmented update.  Why not one thread per theta:
+// the kernel is FP64-pipe bound per SM sub-partition, so its time is ceil(warps per sub-partition) x (cost of one
+// warp); 65,536 thetas are 2,048 two-filter warps = 3.46 per sub-partition (rounds up to 4, 13.5% idle) but 4,096
+// one-filter warps of half the cost = 6.92 (rounds up to 7, 1.2% idle).  It also halves the live state per thread,
+// so the kernel fits 128 registers (4 resident warps per sub-partition) without spilling.
 template <typename T, class Model, int INTERR, int QK, int NOBS>
-__global__ void __maxnreg__(RODEO_DALTON_MAXNREG)
+__global__ void __launch_bounds__(32, 16)
 dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ loglik) {
   typedef Fwd<T, Model, INTERR, QK> F;
   constexpr int NB = F::NB, P = F::P, M = F::M, JC = F::JC, MS = F::MS;
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.B) return;
+  const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool joint = (tid & 1) == 0;
+  i64 idx = tid >> 1;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;                 // keep the whole warp in the loop for the final shuffle
   const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
-  F zy, z;
-  zy.init(a.ode_init + idx * NB * P);
-  z.init(a.ode_init + idx * NB * P);
-  LogPdfAcc<T> acc_zy, acc_z;
-  acc_zy.init(); acc_z.init();
+  F f;
+  f.init(a.ode_init + idx * NB * P);
+  LogPdfAcc<T> acc;
+  acc.init();
 
-  // log p(Y_0 | X_0) when the first observation sits on t_min (dalton.py:207-215)
+  // log p(Y_0 | X_0) when the first observation sits on t_min (dalton.py:207-215); joint filter only
   int i = 0;
   if (__ldg(o.obs_ind) == 0) {
-    constexpr int OS = NOBS * (NOBS + 1) / 2;
-    RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T res[NOBS], Om[OS];
-      RD_UNROLL for (int r = 0; r < NOBS; ++r) {
-        T m = T(0);
-        RD_UNROLL for (int j = 0; j < P; ++j) m = rd_fma(__ldg(o.obs_weight + (b * NOBS + r) * P + j), zy.mu[b][j], m);
-        res[r] = __ldg(o.obs_data + b * NOBS + r) - m;
-        RD_UNROLL for (int s = r; s < NOBS; ++s) Om[sidx<NOBS>(r, s)] = __ldg(o.obs_var + (b * NOBS + r) * NOBS + s);
+    if (joint) {
+      constexpr int OS = NOBS * (NOBS + 1) / 2;
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        T res[NOBS], Om[OS];
+        RD_UNROLL for (int r = 0; r < NOBS; ++r) {
+          T m = T(0);
+          RD_UNROLL for (int j = 0; j < P; ++j) m = rd_fma(__ldg(o.obs_weight + (b * NOBS + r) * P + j), f.mu[b][j], m);
+          res[r] = __ldg(o.obs_data + b * NOBS + r) - m;
+          RD_UNROLL for (int s = r; s < NOBS; ++s) Om[sidx<NOBS>(r, s)] = __ldg(o.obs_var + (b * NOBS + r) * NOBS + s);
+        }
+        logpdf_terms<T, NOBS>(Om, res, acc);
       }
-      logpdf_terms<T, NOBS>(Om, res, acc_zy);
     }
     i = 1;
   }
@@ -285,27 +325,25 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 
   for (int n = 0; n < a.n_steps; ++n) {
     const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
-    T wm[NB][M][P], res[NB][M], V[NB][MS], zc[NB][JC];
-    // joint filter (Z, Y)
-    zy.predict_all(C);
-    zy.template interr_normals<2>(a, idx, n, 0, zc);
-    zy.interrogate(C, q, t, zc, wm, res, V);
+    T jl[NB][M][JC], res[NB][M], V[NB][MS], zc[NB][JC];
+    // each filter is linearised at its own prediction (dalton.py:116-132, 168-184)
+    f.predict_all(C);
+    f.template interr_normals<2>(a, idx, n, joint ? 0 : 1, zc);
+    f.interrogate(C, q, t, zc, jl, res, V);
     if (n + 1 == next_obs) {
       const int ic = i < o.n_obs ? i : o.n_obs - 1;
-      zy.template update_zy<NOBS, true>(wm, res, V, o, ic, acc_zy);
+      if (joint) f.template update_zy<NOBS, true>(C, jl, res, V, o, ic, acc);
+      else f.template update_z<true>(C, jl, res, V, acc);
       ++i;
       next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
     } else {
-      zy.template update_z<true>(wm, res, V, acc_zy);
+      f.template update_z<true>(C, jl, res, V, acc);
     }
-    // marginal filter (Z), linearised at its own prediction (dalton.py:168-195)
-    z.predict_all(C);
-    z.template interr_normals<2>(a, idx, n, 1, zc);
-    z.interrogate(C, q, t, zc, wm, res, V);
-    z.template update_z<true>(wm, res, V, acc_z);
-    if ((n & 7) == 7) { acc_zy.ld.renorm(); acc_z.ld.renorm(); }
+    if ((n & 7) == 7) acc.ld.renorm();
   }
-  loglik[idx] = acc_zy.value() - acc_z.value();
+  const T mine = acc.value();
+  const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  if (joint && live) loglik[idx] = mine - other;          // logdens_joint - logdens_marg (dalton.py:235)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -343,11 +381,11 @@ RD_DEV void forward_and_stash(const FilterConsts<T, Model::NB, Model::P, Model::
   dummy.init();
   for (int n = 0; n < a.n_steps; ++n) {
     const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
-    T wm[NB][M][P], res[NB][M], V[NB][MS], zc[NB][JC];
+    T jl[NB][M][JC], res[NB][M], V[NB][MS], zc[NB][JC];
     f.predict_all(C);
     f.template interr_normals<1>(a, idx, n, 0, zc);
-    f.interrogate(C, q, t, zc, wm, res, V);
-    f.template update_z<false>(wm, res, V, dummy);
+    f.interrogate(C, q, t, zc, jl, res, V);
+    f.template update_z<false>(C, jl, res, V, dummy);
     if (n + 1 < a.n_steps) stash_store<T, F>(stash, ldb, idx, n + 1, f);
   }
 }

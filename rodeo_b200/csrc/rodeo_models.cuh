@@ -6,6 +6,7 @@
 //
 //   static constexpr int NB, P, M, NTHETA;      // n_block, n_bstate, n_bmeas, len(theta)
 //   static constexpr int JCOLS;                 // f only reads X[:, 0:JCOLS]  (1 for first_order_pad systems)
+//   static constexpr int WCOL;                  // the ODE is X[:, WCOL] = f(X, t): W = e_WCOL (1 for first order)
 //   static constexpr bool USES_TIME, HAS_JAC;
 //   template <class T> struct Par;              // per-theta constants kept in registers for the whole solve
 //   template <class T> static Par<T> load(const T* theta);
@@ -94,7 +95,7 @@ RD_DEV void eval_f_jac(const typename Model::template Par<T>& q, T t, const T (&
 
 // ---- FitzHugh-Nagumo  (reference README.md:92-99; theta = (a, b, c)) -------------------------------------------
 struct FitzHughNagumo {
-  static constexpr int NB = 2, P = 3, M = 1, NTHETA = 3, JCOLS = 1;
+  static constexpr int NB = 2, P = 3, M = 1, NTHETA = 3, JCOLS = 1, WCOL = 1;
   static constexpr bool USES_TIME = false, HAS_JAC = true;
   template <class T> struct Par { T a, b, c, mrc; };
   template <class T> RD_DEV static Par<T> load(const T* th) {
@@ -103,7 +104,7 @@ struct FitzHughNagumo {
   template <class T, class X>
   RD_DEV static void rhs(const Par<T>& q, T, const X (&x)[NB][JCOLS], X (&f)[NB][M]) {
     X V = x[0][0], R = x[1][0];
-    f[0][0] = q.c * (V - V * V * V / T(3) + R);
+    f[0][0] = q.c * (V - V * V * V * T(1.0 / 3.0) + R);
     f[1][0] = q.mrc * (V - q.a + q.b * R);
   }
   template <class T>
@@ -116,7 +117,7 @@ struct FitzHughNagumo {
 
 // ---- Lorenz63  (reference docs/examples/lorenz.md:95-101; theta = (rho, sigma, beta)) -------------------------
 struct Lorenz63 {
-  static constexpr int NB = 3, P = 3, M = 1, NTHETA = 3, JCOLS = 1;
+  static constexpr int NB = 3, P = 3, M = 1, NTHETA = 3, JCOLS = 1, WCOL = 1;
   static constexpr bool USES_TIME = false, HAS_JAC = true;
   template <class T> struct Par { T rho, sig, beta; };
   template <class T> RD_DEV static Par<T> load(const T* th) {
@@ -138,7 +139,7 @@ struct Lorenz63 {
 // ---- second-order ODE  x'' = sin(omega t) - k x   (reference docs/examples/higher_order.md:47-58 with
 //      theta = (omega, k) = (2, 1); n_deriv = 4) ------------------------------------------------------------------
 struct SecondOrderSin {
-  static constexpr int NB = 1, P = 4, M = 1, NTHETA = 2, JCOLS = 1;
+  static constexpr int NB = 1, P = 4, M = 1, NTHETA = 2, JCOLS = 1, WCOL = 2;
   static constexpr bool USES_TIME = true, HAS_JAC = true;
   template <class T> struct Par { T om, k; };
   template <class T> RD_DEV static Par<T> load(const T* th) { Par<T> q; q.om = th[0]; q.k = th[1]; return q; }
@@ -152,7 +153,7 @@ struct SecondOrderSin {
 
 // ---- Hes1 on the log scale  (reference examples/timings.py:253-262; theta = (a..g)) ----------------------------
 struct Hes1 {
-  static constexpr int NB = 3, P = 3, M = 1, NTHETA = 7, JCOLS = 1;
+  static constexpr int NB = 3, P = 3, M = 1, NTHETA = 7, JCOLS = 1, WCOL = 1;
   static constexpr bool USES_TIME = false, HAS_JAC = false;   // Jacobian by dual numbers
   template <class T> struct Par { T a, b, c, d, e, f, g; };
   template <class T> RD_DEV static Par<T> load(const T* th) {
@@ -172,7 +173,7 @@ struct Hes1 {
 
 // ---- SEIRAH  (reference examples/timings.py:339-351; theta = (b, r, alpha, D_e, D_I, D_q)) ---------------------
 struct Seirah {
-  static constexpr int NB = 6, P = 3, M = 1, NTHETA = 6, JCOLS = 1;
+  static constexpr int NB = 6, P = 3, M = 1, NTHETA = 6, JCOLS = 1, WCOL = 1;
   static constexpr bool USES_TIME = false, HAS_JAC = false;
   template <class T> struct Par { T b, r, alpha, De, DI, Dq; };
   template <class T> RD_DEV static Par<T> load(const T* th) {

@@ -188,3 +188,199 @@ def test_first_order_pad_on_device(rb):
     X0 = init(pr["x0"], 0.0, theta=pr["theta"])
     assert np.array_equal(W, pr["W"])
     assert P.maxnorm_rel(_np(X0), pr["X0"]) < 1e-15
+
+
+# ---- other models / code paths -------------------------------------------------------------------------------------
+def _mv_pair(rb, name, pr, interr="kramer"):
+    m, v = rb.solve_mv(None, getattr(rb.models, name), pr["W"], pr["X0"], 0.0, pr["t_max"], pr["n_steps"],
+                       _interr(rb, interr), prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"])
+    om, ov = orc.solve_mv(orc.MODELS[name], pr["W"], pr["X0"], 0.0, pr["t_max"], pr["n_steps"], ORC_INTERR[interr],
+                          (pr["Q"], pr["R"]), pr["theta"])
+    return _np(m), _np(v), om, ov
+
+
+def test_solve_mv_lorenz63(rb):
+    # chaotic: keep the horizon short enough that rounding differences are not amplified past the gate
+    pr = P.lorenz_problem(24, n_steps=400, t_max=2.0, seed=4)
+    m, v, om, ov = _mv_pair(rb, "lorenz63", pr)
+    assert P.maxnorm_rel(m, om) < 1e-9 and P.maxnorm_rel(v, ov) < 1e-9
+
+
+def test_solve_mv_second_order_p4(rb):
+    pr = P.second_order_problem(24, n_steps=400, sigma=0.01, seed=4)
+    m, v, om, ov = _mv_pair(rb, "second_order_sin", pr)
+    assert P.maxnorm_rel(m, om) < TOL and P.maxnorm_rel(v, ov) < TOL
+
+
+def _generic_first_order(name, B, n_steps, t_max, x0, theta0, sigma, seed):
+    mdl = orc.MODELS[name]
+    rng = np.random.default_rng(seed)
+    theta = np.asarray(theta0) * np.exp(0.02 * rng.standard_normal((B, len(theta0))))
+    W, init = orc.first_order_pad(mdl, mdl.n_block, 3)
+    X0 = init(np.tile(np.asarray(x0, dtype=float), (B, 1)), 0.0, theta)
+    Q, R = orc.ibm_init(t_max / n_steps, 3, np.array([sigma] * mdl.n_block))
+    return dict(model=name, W=W, X0=X0, theta=theta, Q=Q, R=R, t_max=t_max, n_steps=n_steps)
+
+
+def test_solve_mv_hes1_dual_number_jacobian(rb):
+    # reference examples/timings.py:288-300: x0 = log(1.439, 2.037, 17.904), theta below
+    pr = _generic_first_order("hes1", 16, 240, 240.0, np.log([1.439, 2.037, 17.904]),
+                              [0.022, 0.3, 0.031, 0.028, 0.5, 20, 0.3], 0.1, 5)
+    m, v, om, ov = _mv_pair(rb, "hes1", pr)
+    assert P.maxnorm_rel(m, om) < TOL and P.maxnorm_rel(v, ov) < TOL
+
+
+def test_solve_mv_seirah_six_blocks(rb):
+    # reference examples/timings.py:405-420
+    pr = _generic_first_order("seirah", 16, 80, 60.0, [63804435., 15492., 21752., 0., 618013., 93583.],
+                              [2.23, 0.034, 0.55, 5.1, 2.3, 1.13], 0.1, 6)
+    m, v, om, ov = _mv_pair(rb, "seirah", pr)
+    assert P.maxnorm_rel(m, om) < TOL and P.maxnorm_rel(v, ov) < 1e-9
+
+
+def test_dense_prior_and_general_weight_path(rb):
+    # a non-IBM prior (dense Q) and a W that is not a unit row force the general instantiation
+    pr = P.fitz_problem(32, n_steps=150, t_max=7.5, seed=8)
+    rng = np.random.default_rng(1)
+    Q = pr["Q"] + 0.01 * rng.standard_normal(pr["Q"].shape)
+    W = pr["W"].copy(); W[:, 0, 2] = 0.05; W[:, 0, 0] = -0.02
+    pr2 = dict(pr, Q=Q, W=W)
+    m, v, om, ov = _mv_pair(rb, "fitzhugh_nagumo", pr2)
+    assert P.maxnorm_rel(m, om) < TOL and P.maxnorm_rel(v, ov) < TOL
+    ob = P.fitz_obs(pr2, None, n_obs=6)
+    got = rb.inference.dalton(None, rb.models.fitzhugh_nagumo, W, pr["X0"], 0.0, 7.5, 150,
+                              rb.interrogate.interrogate_kramer, prior_pars=(Q, pr["R"]), theta=pr["theta"], **ob)
+    want = orc.dalton(orc.MODELS["fitzhugh_nagumo"], W, pr["X0"], 0.0, 7.5, 150, orc.interrogate_kramer,
+                      (Q, pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    assert ll_err(_np(got), want) < 2e-9
+
+
+def test_fenrir_observations_on_both_ends(rb):
+    # obs at t_min (scan reaches t = 0) and at t_max (terminal-point update, fenrir.py:196-220)
+    pr = P.fitz_problem(24, n_steps=100, t_max=5.0, seed=12)
+    ob = P.fitz_obs(pr, None, n_obs=6)
+    assert ob["obs_times"][0] == 0.0 and ob["obs_times"][-1] == 5.0
+    got = rb.inference.fenrir(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 5.0, 100,
+                              rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"],
+                              **ob)
+    want = orc.fenrir(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 5.0, 100, orc.interrogate_kramer,
+                      (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"],
+                      ob["obs_var"])
+    assert ll_err(_np(got), want) < TOL
+    # interior-only observations
+    ob["obs_times"] = np.array([0.7, 1.3, 2.0, 2.9, 3.3, 4.1])
+    got = rb.inference.fenrir(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 5.0, 100,
+                              rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"],
+                              **ob)
+    want = orc.fenrir(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 5.0, 100, orc.interrogate_kramer,
+                      (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"],
+                      ob["obs_var"])
+    assert ll_err(_np(got), want) < TOL
+
+
+def test_basic_returns_loglik_and_trajectory(rb):
+    import torch
+    pr = P.fitz_problem(20, n_steps=100, t_max=5.0, seed=14)
+    ob = P.fitz_obs(pr, None, n_obs=6)
+    Y = ob["obs_data"][:, :, 0]
+
+    def loglik_t(obs_data, ode_data, **params):      # user function on torch tensors (reference README.md:186-200)
+        y = torch.as_tensor(Y, device=ode_data.device)
+        return (-0.5 * ((y - ode_data[..., 0]) / 0.07) ** 2).sum(dim=(-1, -2))
+
+    ll, Xt = rb.inference.basic(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 5.0, 100,
+                                rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]),
+                                obs_data=ob["obs_data"], obs_times=ob["obs_times"], obs_loglik=loglik_t,
+                                theta=pr["theta"])
+    oll, oXt = orc.basic(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 5.0, 100, orc.interrogate_kramer,
+                         (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"],
+                         lambda od, xd, th: (-0.5 * ((Y - xd[..., 0]) / 0.07) ** 2).sum(axis=(-1, -2)))
+    assert P.maxnorm_rel(_np(Xt), oXt) < TOL and P.maxnorm_rel(_np(ll), oll) < 1e-9
+
+
+# ---- sampling paths: distribution-level and determinism ------------------------------------------------------------------
+def test_solve_sim_draws_have_solve_mv_moments_for_a_linear_ode(rb):
+    """For a linear ODE with interrogate_kramer the model is linear-Gaussian, so solve_sim draws are exactly
+    N(solve_mv mean, solve_mv var) marginally.  16,384 draws of one theta."""
+    n = 16384
+    pr = P.second_order_problem(1, n_steps=60, t_max=3.0, sigma=0.5, seed=0)
+    X0 = np.repeat(pr["X0"], n, axis=0); th = np.repeat(pr["theta"], n, axis=0)
+    x = _np(rb.solve_sim(np.array([3, 4], dtype=np.uint32), rb.models.second_order_sin, pr["W"], X0, 0.0, 3.0, 60,
+                         rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]), theta=th))
+    om, ov = orc.solve_mv(orc.MODELS["second_order_sin"], pr["W"], pr["X0"], 0.0, 3.0, 60, orc.interrogate_kramer,
+                          (pr["Q"], pr["R"]), pr["theta"])
+    assert np.array_equal(x[:, 0], X0)                      # row 0 is ode_init verbatim
+    for t in (10, 30, 59, 60):
+        sd = np.sqrt(np.maximum(np.diagonal(ov[0, t, 0]), 0))
+        zmean = (x[:, t, 0].mean(axis=0) - om[0, t, 0]) / np.maximum(sd / np.sqrt(n), 1e-300)
+        keep = sd > 1e-9 * np.abs(om[0, t, 0]).max()
+        assert np.all(np.abs(zmean[keep]) < 5.0), (t, zmean)
+        cov = np.cov(x[:, t, 0].T)
+        scale = np.outer(sd, sd)[np.ix_(keep, keep)]
+        assert np.max(np.abs(cov[np.ix_(keep, keep)] - ov[0, t, 0][np.ix_(keep, keep)]) / scale) < 0.06, t
+
+
+def test_solve_sim_is_deterministic_and_sharding_invariant(rb):
+    pr = P.fitz_problem(64, n_steps=80, t_max=4.0, seed=15)
+    chk = _interr(rb, "chkrebtii")
+    kw = dict(prior_pars=(pr["Q"], pr["R"]))
+    key = np.array([11, 22], dtype=np.uint32)
+    a = _np(rb.solve_sim(key, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 4.0, 80, chk, theta=pr["theta"], **kw))
+    b = _np(rb.solve_sim(key, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 4.0, 80, chk, theta=pr["theta"], **kw))
+    assert np.array_equal(a, b) and np.isfinite(a).all()
+    # second half computed as its own shard with the global particle offset
+    c = _np(rb.solve_sim(key, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"][32:], 0.0, 4.0, 80, chk,
+                         theta=pr["theta"][32:], _particle_offset=32, **kw))
+    assert np.array_equal(a[32:], c)
+    d = _np(rb.solve_sim(np.array([11, 23], dtype=np.uint32), rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 4.0,
+                         80, chk, theta=pr["theta"], **kw))
+    assert not np.array_equal(a, d)
+
+
+def test_philox_normals_are_standard(rb):
+    # terminal draw of a problem whose filter variance is known: x_N - mu_N = A z with A A^T = S_f[N]
+    n = 32768
+    pr = P.second_order_problem(1, n_steps=1, t_max=0.5, sigma=2.0, seed=0)
+    X0 = np.repeat(pr["X0"], n, axis=0); th = np.repeat(pr["theta"], n, axis=0)
+    x = _np(rb.solve_sim(7, rb.models.second_order_sin, pr["W"], X0, 0.0, 0.5, 1, rb.interrogate.interrogate_kramer,
+                         prior_pars=(pr["Q"], pr["R"]), theta=th))
+    om, ov = orc.solve_mv(orc.MODELS["second_order_sin"], pr["W"], pr["X0"], 0.0, 0.5, 1, orc.interrogate_kramer,
+                          (pr["Q"], pr["R"]), pr["theta"])
+    r = x[:, 1, 0] - om[0, 1, 0]
+    sd = np.sqrt(np.diagonal(ov[0, 1, 0]))
+    for j in (0, 1, 3):
+        z = r[:, j] / sd[j]
+        assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 0.05
+        assert abs(np.mean(z ** 3)) < 0.1 and abs(np.mean(z ** 4) - 3) < 0.25
+
+
+# ---- full-size properties --------------------------------------------------------------------------------------------
+def test_dalton_full_size_matches_c_oracle_on_a_subset(rb):
+    from oracle import c_port
+    B = 65536
+    pr = P.fitz_problem(B, seed=0)
+    pr0 = P.fitz_problem(1, jitter=False)
+    truth, _ = c_port.solve_mv("fitzhugh_nagumo", "kramer", pr0["W"], pr0["X0"], 0.0, 40.0, 800, pr0["Q"], pr0["R"],
+                               pr0["theta"])
+    ob = P.fitz_obs(pr, truth[0])
+    got = _np(rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 40.0, 800,
+                                  rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]),
+                                  theta=pr["theta"], **ob))
+    assert got.shape == (B,) and np.isfinite(got).all()
+    sub = np.random.default_rng(0).choice(B, 1024, replace=False)
+    ind = orc.obs_index(0.0, 40.0, 800, ob["obs_times"])
+    want = c_port.dalton("fitzhugh_nagumo", "kramer", pr["W"], pr["X0"][sub], 0.0, 40.0, 800, pr["Q"], pr["R"],
+                         pr["theta"][sub], ob["obs_data"], ind, ob["obs_weight"], ob["obs_var"])
+    # float64 noise floor at N = 800: judge both against the extended-precision value (see the test above)
+    import ld_reference as L
+    exact = L.dalton_ld(L.fitz_fun_ld, L.fitz_jac_ld, pr["W"], pr["X0"][sub], 0.0, 40.0, 800, pr["Q"], pr["R"],
+                        pr["theta"][sub], ob["obs_data"], ind, ob["obs_weight"], ob["obs_var"]).astype(np.float64)
+    e_oracle, e_kernel = ll_err(want, exact), ll_err(got[sub], exact)
+    print(f"full size: |C oracle-exact|={e_oracle:.2e} |kernel-exact|={e_kernel:.2e}")
+    assert e_kernel <= max(TOL, 3 * e_oracle)
+    assert ll_err(got[sub], want) <= max(TOL, 4 * e_oracle)
+    # batch-composition invariance: a theta's result does not depend on its neighbours
+    again = _np(rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"][sub], 0.0, 40.0, 800,
+                                    rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]),
+                                    theta=pr["theta"][sub], **ob))
+    assert np.array_equal(again, got[sub])
