@@ -74,10 +74,13 @@ size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes)
     case RODEO_OP_SOLVE_MV:
     case RODEO_OP_SOLVE_SIM:
     case RODEO_OP_FENRIR: {
-      // stash of filt[1..N-1]: (N-1) * n_block * (p + p(p+1)/2) * ldb elements
-      const size_t nstate = (size_t)p->n_block * (p->n_bstate + p->n_bstate * (p->n_bstate + 1) / 2);
-      const size_t steps = p->n_steps > 1 ? (size_t)(p->n_steps - 1) : 0;
-      return steps * nstate * (size_t)stash_ldb(p->B) * (size_t)elem_bytes;
+      // history of filtered states, theta-innermost: entries filt[KC], filt[2 KC], ... < N.  solve_mv keeps one
+      // checkpoint per shared-memory segment (KC = seg_len(nstate)) and recomputes; solve_sim / fenrir keep every
+      // state (KC = 1).  See rodeo_kernels.cuh.
+      const int nstate = nstate_of(p->n_block, p->n_bstate);
+      const int KC = (op == RODEO_OP_SOLVE_MV) ? seg_len(nstate) : 1;
+      const size_t J = ((size_t)p->n_steps + KC - 1) / KC;
+      return (J > 0 ? J - 1 : 0) * (size_t)nstate * (size_t)stash_ldb(p->B) * (size_t)elem_bytes;
     }
     default:
       return 0;

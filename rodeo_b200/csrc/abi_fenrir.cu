@@ -15,7 +15,10 @@ struct FenrirRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    fenrir_kernel<double, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32, 0, s>>>(C, a, o, stash, stash_ldb(p.B), out);
+    constexpr int SMEM = SegBuf<double, Fwd<double, Model, INTERR, QK>>::BYTES;
+    RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_kernel<double, Model, INTERR, QK, 1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    fenrir_kernel<double, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, o, stash, stash_ldb(p.B), out);
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;

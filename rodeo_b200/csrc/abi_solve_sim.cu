@@ -1,4 +1,4 @@
-// rodeo_b200_solve_mv_f64: batched rodeo.solve_mv
+// rodeo_b200_solve_sim_f64: batched rodeo.solve_sim
 // (reference src/rodeo/solve.py:125-302).
 #include "rodeo_host.h"
 
@@ -6,17 +6,17 @@ namespace rodeo {
 namespace host {
 
 template <class Model, int INTERR, int QK>
-struct SolveMvRun {
+struct SolveSimRun {
   static int run(const RodeoProblem& p, const double* W, const double* Q, const double* R,
-                 const CommonArgs<double>& a, double* stash, double* mean_out, double* var_out, cudaStream_t s) {
+                 const CommonArgs<double>& a, const double* z_smooth, double* stash, double* x_out, cudaStream_t s) {
     FilterConsts<double, Model::NB, Model::P, Model::M> C;
     pack_consts<double, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
     constexpr int SMEM = SegBuf<double, Fwd<double, Model, INTERR, QK>>::BYTES;
-    RODEO_CUDA_OK(cudaFuncSetAttribute(solve_mv_kernel<double, Model, INTERR, QK>,
+    RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<double, Model, INTERR, QK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    solve_mv_kernel<double, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, stash, stash_ldb(p.B),
-                                                                               mean_out, var_out);
+    solve_sim_kernel<double, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, z_smooth, stash,
+                                                                                stash_ldb(p.B), x_out);
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;
@@ -38,14 +38,13 @@ static int check_ws(int op, const RodeoProblem* p, void* ws, size_t ws_bytes) {
   return RODEO_OK;
 }
 
-extern "C" int rodeo_b200_solve_mv_f64(const RodeoProblem* p, const double* ode_weight, const double* prior_weight,
-                                       const double* prior_var, const double* ode_init, const double* theta,
-                                       const double* z_interr, double* mean_out, double* var_out, void* workspace,
-                                       size_t workspace_bytes, void* stream) {
+extern "C" int rodeo_b200_solve_sim_f64(const RodeoProblem* p, const double* ode_weight, const double* prior_weight,
+                                        const double* prior_var, const double* ode_init, const double* theta,
+                                        const double* z_interr, const double* z_smooth, double* x_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_common(p)) return rc;
-  if (int rc = check_ws(RODEO_OP_SOLVE_MV, p, workspace, workspace_bytes)) return rc;
+  if (int rc = check_ws(RODEO_OP_SOLVE_SIM, p, workspace, workspace_bytes)) return rc;
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
-  return dispatch_model<SolveMvRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, (double*)workspace,
-                                    mean_out, var_out, (cudaStream_t)stream);
+  return dispatch_model<SolveSimRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
+                                     (double*)workspace, x_out, (cudaStream_t)stream);
 }
-

@@ -18,6 +18,7 @@
 
 #define RD_DEV __device__ __forceinline__
 #define RD_UNROLL _Pragma("unroll")
+#define RD_UNROLL4 _Pragma("unroll 4")
 
 namespace rodeo {
 

@@ -347,50 +347,188 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward filter + stash of the filtered moments, shared by solve_mv / solve_sim / fenrir
+// History for the backward sweeps (solve_mv / solve_sim / fenrir): checkpoints in HBM, segments in shared memory
 // ------------------------------------------------------------------------------------------------------------------
-// Stash layout: stash[((n-1) * NSTATE + k) * ldb + idx], n = 1..N-1, k over [mu (NB*P) | S packed (NB*NS)];
-// theta innermost, so a warp writes/reads 32 consecutive elements per (n, k).  pred[n+1] is not stored: it is
-// recomputed from filt[n] in the backward sweep (one predict), which halves the history traffic.
+// The smoothers need filt[n] for n = N-1 .. 0 (pred[n+1] is one predict away from filt[n] and is never stored).
+// Writing every filt[n] to HBM and reading it back costs 2 x NSTATE x 8 B per theta*step (288 B for FitzHugh-Nagumo,
+// against 192 B of compulsory solve_mv output), so instead
+//   * the forward sweep stores only every K-th filtered state ("checkpoint", theta-innermost => coalesced), and
+//   * the backward sweep works segment by segment: reload checkpoint jK, re-run the K-1 forward steps of the
+//     segment into a per-warp shared-memory buffer, then smooth the segment backwards out of shared memory.
+// History traffic drops to 2 x NSTATE x 8 / K bytes per theta*step for (K-1)/K of an extra forward step.
+// The same buffer then stages the segment's outputs so that a warp writes them to HBM as contiguous runs of
+// K time rows per theta (the reference layout is theta-outermost: a thread-per-theta store would scatter 8-byte
+// writes 38 KB apart).
+//
+// Buffer layout, per warp:  buf[slot s][state k][lane] with a lane pitch of 33 doubles: conflict-free both for the
+// per-thread accesses (fixed (s,k), lane varies) and for the copy-out (fixed lane, k varies).
+constexpr int SEG_PITCH = 33;
+
+// checkpoint interval: the largest K <= 8 whose buffer fits 18 KB per warp (12 one-warp CTAs per SM)
+__host__ __device__ constexpr int seg_len(int nstate) {
+  return (69 / nstate) < 1 ? 1 : ((69 / nstate) > 8 ? 8 : (69 / nstate));
+}
+__host__ __device__ constexpr int nstate_of(int nb, int p) { return nb * (p + p * (p + 1) / 2); }
+
+// KC: checkpoint interval of the HBM history.  KC == K: one checkpoint per segment, the rest is recomputed (solve_mv,
+// which is HBM-bound on its 192 B/theta*step of compulsory output).  KC == 1: every filtered state is stored and a
+// segment is simply loaded back (solve_sim / fenrir: FP64-bound -- the draws or the backward filter dominate -- with
+// little or no output, so re-running forward steps, and the chkrebtii random draws in them, would cost more than the
+// history traffic).
 template <typename T, class F>
-RD_DEV void stash_store(T* __restrict__ stash, i64 ldb, i64 idx, int n, const F& f) {
+struct SegBuf {
+  static constexpr int NB = F::NB, P = F::P, NS = F::NS, NSTATE = NB * (P + NS);
+  static constexpr int K = seg_len(NSTATE);
+  static constexpr int BYTES = K * NSTATE * SEG_PITCH * (int)sizeof(T);
+  T* base;
+  int lane;
+  RD_DEV T& at(int s, int k) { return base[(s * NSTATE + k) * SEG_PITCH + lane]; }
+  RD_DEV void put(int s, const T (&mu)[NB][P], const T (&S)[NB][NS]) {
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      RD_UNROLL for (int i = 0; i < P; ++i) at(s, b * P + i) = mu[b][i];
+      RD_UNROLL for (int k = 0; k < NS; ++k) at(s, NB * P + b * NS + k) = S[b][k];
+    }
+  }
+  RD_DEV void get(int s, T (&mu)[NB][P], T (&S)[NB][NS]) {
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = at(s, b * P + i);
+      RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = at(s, NB * P + b * NS + k);
+    }
+  }
+  // Copy `rows` staged time rows starting at time n0 to a (B, N+1, ROW) output, ROW = NB*P (means / draws) or
+  // NB*P*P (full covariances expanded from the packed slots).  Per theta the rows form ONE contiguous run of
+  // rows*ROW elements, so the warp walks the 32 thetas and, for each, consecutive lanes store consecutive elements
+  // of the run.  A lane's position r in the run -- hence its source slot/state -- is the same for every theta:
+  // the (s, k) decode is done once per call, and the loop body is one LDS, one STG and two pointer bumps.
+  template <bool VAR>
+  RD_DEV void copy_out(T* __restrict__ out, i64 theta0, i64 B, int n_rows_total, int n0, int rows) {
+    constexpr int ROW = VAR ? NB * P * P : NB * P;
+    constexpr int NIT = (K * ROW + 31) / 32;
+    const int run = rows * ROW;
+    int src[NIT];
+    RD_UNROLL for (int it = 0; it < NIT; ++it) {
+      const int r = lane + 32 * it;
+      const int s = r / ROW, e = r - s * ROW;
+      int k = e;
+      if (VAR) {
+        const int b = e / (P * P), ij = e - b * (P * P), i = ij / P, j = ij - i * P;
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        k = NB * P + b * NS + lo * P - (lo * (lo - 1)) / 2 + (hi - lo);
+      }
+      src[it] = r < run ? (s * NSTATE + k) * SEG_PITCH : -1;
+    }
+    const i64 stride = (i64)n_rows_total * ROW;
+    T* dst = out + (theta0 * (i64)n_rows_total + n0) * ROW + lane;
+    const int nth = (B - theta0) < 32 ? (int)(B - theta0) : 32;
+    RD_UNROLL4 for (int th = 0; th < nth; ++th) {
+      RD_UNROLL for (int it = 0; it < NIT; ++it)
+        if (src[it] >= 0) dst[32 * it] = base[src[it] + th];
+      dst += stride;
+    }
+  }
+};
+
+// checkpoint j (= filt[j*K], j >= 1) of theta idx:  stash[((j-1) * NSTATE + k) * ldb + idx]
+template <typename T, class F>
+RD_DEV void ckpt_store(T* __restrict__ stash, i64 ldb, i64 idx, int j, const F& f) {
   constexpr int NB = F::NB, P = F::P, NS = F::NS, NSTATE = NB * (P + NS);
-  T* s = stash + (i64)(n - 1) * NSTATE * ldb + idx;
+  T* s = stash + (i64)(j - 1) * NSTATE * ldb + idx;
   RD_UNROLL for (int b = 0; b < NB; ++b) {
     RD_UNROLL for (int i = 0; i < P; ++i) s[(i64)(b * P + i) * ldb] = f.mu[b][i];
     RD_UNROLL for (int k = 0; k < NS; ++k) s[(i64)(NB * P + b * NS + k) * ldb] = f.S[b][k];
   }
 }
 template <typename T, class F>
-RD_DEV void stash_load(const T* __restrict__ stash, i64 ldb, i64 idx, int n, F& f) {
+RD_DEV void ckpt_load(const T* __restrict__ stash, i64 ldb, i64 idx, int j, F& f) {
   constexpr int NB = F::NB, P = F::P, NS = F::NS, NSTATE = NB * (P + NS);
-  const T* s = stash + (i64)(n - 1) * NSTATE * ldb + idx;
+  const T* s = stash + (i64)(j - 1) * NSTATE * ldb + idx;
   RD_UNROLL for (int b = 0; b < NB; ++b) {
     RD_UNROLL for (int i = 0; i < P; ++i) f.mu[b][i] = s[(i64)(b * P + i) * ldb];
     RD_UNROLL for (int k = 0; k < NS; ++k) f.S[b][k] = s[(i64)(NB * P + b * NS + k) * ldb];
   }
 }
 
+// L2 prefetch of history entry j (no registers held while the lines travel from HBM)
+template <typename T, class F>
+RD_DEV void ckpt_prefetch(const T* __restrict__ stash, i64 ldb, i64 idx, int j) {
+  constexpr int NSTATE = F::NB * (F::P + F::NS);
+  const T* s = stash + (i64)(j - 1) * NSTATE * ldb + idx;
+  RD_UNROLL for (int k = 0; k < NSTATE; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(s + (i64)k * ldb));
+}
+
+// one forward step n -> n+1 of a plain (no log-density) filter
 template <typename T, class Model, int INTERR, int QK>
-RD_DEV void forward_and_stash(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
-                              const typename Model::template Par<T>& q, i64 idx,
-                              Fwd<T, Model, INTERR, QK>& f, T* __restrict__ stash, i64 ldb) {
+RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
+                         const typename Model::template Par<T>& q, i64 idx, int n, Fwd<T, Model, INTERR, QK>& f) {
   typedef Fwd<T, Model, INTERR, QK> F;
-  constexpr int NB = F::NB, P = F::P, M = F::M, JC = F::JC, MS = F::MS;
+  constexpr int NB = F::NB, M = F::M, JC = F::JC, MS = F::MS;
   LogPdfAcc<T> dummy;
-  dummy.init();
+  const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
+  T jl[NB][M][JC], res[NB][M], V[NB][MS], zc[NB][JC];
+  f.predict_all(C);
+  f.template interr_normals<1>(a, idx, n, 0, zc);
+  f.interrogate(C, q, t, zc, jl, res, V);
+  f.template update_z<false>(C, jl, res, V, dummy);
+}
+
+// forward sweep 0 -> N storing filt[n] for every n that is a multiple of KC (history entry n / KC); on exit f holds
+// filt[N]
+template <typename T, class Model, int INTERR, int QK, int KC>
+RD_DEV void forward_with_checkpoints(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
+                                     const typename Model::template Par<T>& q, i64 idx, bool live,
+                                     Fwd<T, Model, INTERR, QK>& f, T* __restrict__ stash, i64 ldb) {
+  typedef Fwd<T, Model, INTERR, QK> F;
+  int to_ckpt = KC, j = 0;
   for (int n = 0; n < a.n_steps; ++n) {
-    const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
-    T jl[NB][M][JC], res[NB][M], V[NB][MS], zc[NB][JC];
-    f.predict_all(C);
-    f.template interr_normals<1>(a, idx, n, 0, zc);
-    f.interrogate(C, q, t, zc, jl, res, V);
-    f.template update_z<false>(C, jl, res, V, dummy);
-    if (n + 1 < a.n_steps) stash_store<T, F>(stash, ldb, idx, n + 1, f);
+    forward_step<T, Model, INTERR, QK>(C, a, q, idx, n, f);
+    if (--to_ckpt == 0) {
+      to_ckpt = KC;
+      ++j;
+      if (live && n + 1 < a.n_steps) ckpt_store<T, F>(stash, ldb, idx, j, f);
+    }
   }
 }
 
-// full-matrix / vector stores of one time row of the outputs (reference layouts (N+1, nb, p) and (N+1, nb, p, p))
+// Rebuild filt[j*K .. j*K + cnt - 1] of segment j into the buffer slots 0 .. cnt-1.
+//   KC == K: load checkpoint j (filt[0] = (ode_init, 0) for j == 0) and re-run the cnt-1 forward steps;
+//   KC == 1: load every state of the segment from the history.
+template <typename T, class Model, int INTERR, int QK, int KC>
+RD_DEV void rebuild_segment(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
+                            const typename Model::template Par<T>& q, i64 idx, int j, int cnt,
+                            Fwd<T, Model, INTERR, QK>& f, const T* __restrict__ stash, i64 ldb,
+                            SegBuf<T, Fwd<T, Model, INTERR, QK>>& buf) {
+  typedef Fwd<T, Model, INTERR, QK> F;
+  constexpr int NB = F::NB, P = F::P, K = SegBuf<T, F>::K;
+  if constexpr (KC == 1) {
+    for (int s = 0; s < cnt; ++s) {
+      const int n = j * K + s;
+      if (n == 0) f.init(a.ode_init + idx * NB * P);
+      else ckpt_load<T, F>(stash, ldb, idx, n, f);
+      buf.put(s, f.mu, f.S);
+    }
+  } else {
+    if (j == 0) f.init(a.ode_init + idx * NB * P);            // filt[0] = (ode_init, 0)
+    else ckpt_load<T, F>(stash, ldb, idx, j, f);
+    buf.put(0, f.mu, f.S);
+    for (int s = 1; s < cnt; ++s) {
+      forward_step<T, Model, INTERR, QK>(C, a, q, idx, j * K + s - 1, f);
+      buf.put(s, f.mu, f.S);
+    }
+  }
+}
+
+// prefetch what rebuild_segment(j) will load (called one segment ahead, before the copy-out of segment j+1)
+template <typename T, class F, int KC>
+RD_DEV void prefetch_segment(const T* __restrict__ stash, i64 ldb, i64 idx, int j, int K) {
+  if (KC == 1) {
+    for (int s = 0; s < K; ++s)
+      if (j * K + s >= 1) ckpt_prefetch<T, F>(stash, ldb, idx, j * K + s);
+  } else if (j >= 1) {
+    ckpt_prefetch<T, F>(stash, ldb, idx, j);
+  }
+}
+
+// full-matrix / vector stores of one time row (used for the single row N; everything else is staged)
 template <typename T, int NB, int P>
 RD_DEV void store_mean_row(T* __restrict__ out, const T (&mu)[NB][P]) {
   RD_UNROLL for (int b = 0; b < NB; ++b)
@@ -403,6 +541,8 @@ RD_DEV void store_var_row(T* __restrict__ out, const T (&S)[NB][P * (P + 1) / 2]
       RD_UNROLL for (int j = 0; j < P; ++j) out[(b * P + i) * P + j] = S[b][sym<P>(i, j)];
 }
 
+extern __shared__ double rodeo_dyn_smem[];
+
 // ------------------------------------------------------------------------------------------------------------------
 // solve_mv: forward filter, then the mean/variance smoother  (reference src/rodeo/solve.py:208-302)
 // ------------------------------------------------------------------------------------------------------------------
@@ -412,50 +552,59 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
                 const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
                 T* __restrict__ mean_out, T* __restrict__ var_out) {
   typedef Fwd<T, Model, INTERR, QK> F;
-  constexpr int NB = F::NB, P = F::P, NS = F::NS;
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.B) return;
+  typedef SegBuf<T, F> Buf;
+  constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
+  const i64 theta0 = (i64)blockIdx.x * 32;
+  i64 idx = theta0 + threadIdx.x;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;                 // the whole warp takes part in the cooperative copy-out
   const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
+  Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
   f.init(a.ode_init + idx * NB * P);
-  T* mrow = mean_out + idx * (i64)(N + 1) * (NB * P);
-  T* vrow = var_out + idx * (i64)(N + 1) * (NB * P * P);
-  // row 0 is (ode_init, 0) verbatim: x0 is known and never smoothed (solve.py:295-301)
-  store_mean_row<T, NB, P>(mrow, f.mu);
-  store_var_row<T, NB, P>(vrow, f.S);
+  forward_with_checkpoints<T, Model, INTERR, QK, K>(C, a, q, idx, live, f, stash, ldb);
 
-  forward_and_stash<T, Model, INTERR, QK>(C, a, q, idx, f, stash, ldb);
-
-  // smoothed[N] = filt[N]
+  // smoothed[N] = filt[N]   (solve.py:279-282)
   T ms[NB][P], Ss[NB][NS];
   RD_UNROLL for (int b = 0; b < NB; ++b) {
     RD_UNROLL for (int i = 0; i < P; ++i) ms[b][i] = f.mu[b][i];
     RD_UNROLL for (int k = 0; k < NS; ++k) Ss[b][k] = f.S[b][k];
   }
-  store_mean_row<T, NB, P>(mrow + (i64)N * (NB * P), ms);
-  store_var_row<T, NB, P>(vrow + (i64)N * (NB * P * P), Ss);
+  if (live && mean_out != nullptr) store_mean_row<T, NB, P>(mean_out + (idx * (i64)(N + 1) + N) * (NB * P), ms);
+  if (live && var_out != nullptr) store_var_row<T, NB, P>(var_out + (idx * (i64)(N + 1) + N) * (NB * P * P), Ss);
 
-  for (int n = N - 1; n >= 1; --n) {
-    stash_load<T, F>(stash, ldb, idx, n, f);     // filt[n]
-    RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T mp[P], Sp[NS], G[P][P], Ct[P][P];
-      predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
-      smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
-      // mu_s = mu_f + G (mu_s' - mu_p) ;  S_s = S_f + G (S_s' - S_p) G^T    (standard.py:213-216)
-      T dm[P], D[NS];
-      RD_UNROLL for (int i = 0; i < P; ++i) dm[i] = ms[b][i] - mp[i];
-      RD_UNROLL for (int k = 0; k < NS; ++k) D[k] = Ss[b][k] - Sp[k];
-      RD_UNROLL for (int i = 0; i < P; ++i) {
-        T m = f.mu[b][i];
-        RD_UNROLL for (int j = 0; j < P; ++j) m = rd_fma(G[i][j], dm[j], m);
-        ms[b][i] = m;
+  // rows N-1 .. 0, segment by segment
+  for (int j = (N - 1) / K; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;          // rows n0 .. n0+cnt-1  (all <= N-1)
+    rebuild_segment<T, Model, INTERR, QK, K>(C, a, q, idx, j, cnt, f, stash, ldb, buf);
+    for (int s = cnt - 1; s >= 0; --s) {
+      if (n0 + s == 0) break;                              // row 0 stays (ode_init, 0): never smoothed (solve.py:295-301)
+      buf.get(s, f.mu, f.S);                               // filt[n]
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        T mp[P], Sp[NS], G[P][P], Ct[P][P];
+        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
+        smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
+        // mu_s = mu_f + G (mu_s' - mu_p) ;  S_s = S_f + G (S_s' - S_p) G^T    (standard.py:213-216)
+        T dm[P], D[NS];
+        RD_UNROLL for (int i = 0; i < P; ++i) dm[i] = ms[b][i] - mp[i];
+        RD_UNROLL for (int k = 0; k < NS; ++k) D[k] = Ss[b][k] - Sp[k];
+        RD_UNROLL for (int i = 0; i < P; ++i) {
+          T m = f.mu[b][i];
+          RD_UNROLL for (int jj = 0; jj < P; ++jj) m = rd_fma(G[i][jj], dm[jj], m);
+          ms[b][i] = m;
+        }
+        RD_UNROLL for (int k = 0; k < NS; ++k) Ss[b][k] = f.S[b][k];
+        add_GDGt<T, P>(G, D, Ss[b]);
       }
-      RD_UNROLL for (int k = 0; k < NS; ++k) Ss[b][k] = f.S[b][k];
-      add_GDGt<T, P>(G, D, Ss[b]);
+      buf.put(s, ms, Ss);                                  // stage the output row in place of filt[n]
     }
-    store_mean_row<T, NB, P>(mrow + (i64)n * (NB * P), ms);
-    store_var_row<T, NB, P>(vrow + (i64)n * (NB * P * P), Ss);
+    if (j > 0) prefetch_segment<T, F, K>(stash, ldb, idx, j - 1, K);     // travels during the copy-out
+    __syncwarp();
+    if (mean_out != nullptr) buf.template copy_out<false>(mean_out, theta0, a.B, N + 1, n0, cnt);
+    if (var_out != nullptr) buf.template copy_out<true>(var_out, theta0, a.B, N + 1, n0, cnt);
+    __syncwarp();
   }
 }
 
@@ -470,55 +619,79 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
                  const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
                  T* __restrict__ x_out) {
   typedef Fwd<T, Model, INTERR, QK> F;
-  constexpr int NB = F::NB, P = F::P, NS = F::NS;
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.B) return;
+  typedef SegBuf<T, F> Buf;
+  constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
+  const i64 theta0 = (i64)blockIdx.x * 32;
+  i64 idx = theta0 + threadIdx.x;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;
   const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
+  Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
   f.init(a.ode_init + idx * NB * P);
-  T* xrow = x_out + idx * (i64)(N + 1) * (NB * P);
-  store_mean_row<T, NB, P>(xrow, f.mu);
+  forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
 
-  forward_and_stash<T, Model, INTERR, QK>(C, a, q, idx, f, stash, ldb);
-
-  T x[NB][P];
-  for (int n = N; n >= 1; --n) {
-    T z[NB * P];
+  auto normals = [&](int n, T (&z)[NB * P]) {
     if (z_smooth != nullptr) {
       const T* zp = z_smooth + (idx * (i64)(N + 1) + n) * (NB * P);
       RD_UNROLL for (int k = 0; k < NB * P; ++k) z[k] = zp[k];
     } else {
       philox_normals<T, NB * P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, z);
     }
-    if (n < N) stash_load<T, F>(stash, ldb, idx, n, f);     // filt[n]
-    RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T m[P], Cv[NS];
-      if (n == N) {
-        // terminal draw from N(mu_f[N], S_f[N])  (solve.py:182-186)
-        RD_UNROLL for (int i = 0; i < P; ++i) m[i] = f.mu[b][i];
-        RD_UNROLL for (int k = 0; k < NS; ++k) Cv[k] = f.S[b][k];
-      } else {
-        T mp[P], Sp[NS], G[P][P], Ct[P][P];
-        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);        // pred[n+1]
+  };
+  auto draw = [&](int b, const T (&m)[P], const T (&Cv)[NS], const T (&z)[NB * P], T (&x)[NB][P]) {
+    T A[P][P];
+    psd_factor<T, P>(Cv, A);
+    RD_UNROLL for (int i = 0; i < P; ++i) {
+      T acc = m[i];
+      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma(A[i][k], z[b * P + k], acc);
+      x[b][i] = acc;
+    }
+  };
+
+  // terminal draw from N(mu_f[N], S_f[N])  (solve.py:182-186)
+  T x[NB][P];
+  {
+    T z[NB * P];
+    normals(N, z);
+    T xn[NB][P];
+    RD_UNROLL for (int b = 0; b < NB; ++b) draw(b, f.mu[b], f.S[b], z, xn);
+    RD_UNROLL for (int b = 0; b < NB; ++b)
+      RD_UNROLL for (int i = 0; i < P; ++i) x[b][i] = xn[b][i];
+    if (live) store_mean_row<T, NB, P>(x_out + (idx * (i64)(N + 1) + N) * (NB * P), x);
+  }
+
+  for (int j = (N - 1) / K; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;
+    rebuild_segment<T, Model, INTERR, QK, 1>(C, a, q, idx, j, cnt, f, stash, ldb, buf);
+    for (int s = cnt - 1; s >= 0; --s) {
+      if (n0 + s == 0) break;                              // row 0 = ode_init: x0 is known, not sampled (solve.py:202-204)
+      buf.get(s, f.mu, f.S);                               // filt[n]
+      T z[NB * P];
+      normals(n0 + s, z);
+      T xn[NB][P];
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        T mp[P], Sp[NS], G[P][P], Ct[P][P], m[P], Cv[NS];
+        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         // m = mu_f + G (x' - mu_p) ;  C = S_f - G (S_f Q^T)^T      (standard.py:251-254)
         RD_UNROLL for (int i = 0; i < P; ++i) {
           T acc = f.mu[b][i];
-          RD_UNROLL for (int j = 0; j < P; ++j) acc = rd_fma(G[i][j], x[b][j] - mp[j], acc);
+          RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma(G[i][jj], x[b][jj] - mp[jj], acc);
           m[i] = acc;
         }
         cond_var<T, P>(f.S[b], G, Ct, Cv);
+        draw(b, m, Cv, z, xn);
       }
-      T A[P][P];
-      psd_factor<T, P>(Cv, A);
-      RD_UNROLL for (int i = 0; i < P; ++i) {
-        T acc = m[i];
-        RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma(A[i][k], z[b * P + k], acc);
-        x[b][i] = acc;
-      }
+      RD_UNROLL for (int b = 0; b < NB; ++b)
+        RD_UNROLL for (int i = 0; i < P; ++i) { x[b][i] = xn[b][i]; buf.at(s, b * P + i) = xn[b][i]; }
     }
-    store_mean_row<T, NB, P>(xrow + (i64)n * (NB * P), x);
+    if (j > 0) prefetch_segment<T, F, 1>(stash, ldb, idx, j - 1, K);
+    __syncwarp();
+    buf.template copy_out<false>(x_out, theta0, a.B, N + 1, n0, cnt);
+    __syncwarp();
   }
 }
 
@@ -532,14 +705,17 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ stash, i64 ldb,
               T* __restrict__ loglik) {
   typedef Fwd<T, Model, INTERR, QK> F;
-  constexpr int NB = F::NB, P = F::P, NS = F::NS;
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.B) return;
+  typedef SegBuf<T, F> Buf;
+  constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
+  i64 idx = (i64)blockIdx.x * 32 + threadIdx.x;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;
   const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
+  Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
   f.init(a.ode_init + idx * NB * P);
-  forward_and_stash<T, Model, INTERR, QK>(C, a, q, idx, f, stash, ldb);
+  forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
 
   // backward-filter state starts at filt[N]
   F bk;
@@ -557,35 +733,42 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     --i;
   }
   int next_obs = obs_at(i);
-  int cnt = 0;
-  for (int t = N - 1; t >= 0; --t) {
-    if (t >= 1) stash_load<T, F>(stash, ldb, idx, t, f);  // filt[t]
-    else f.init(a.ode_init + idx * NB * P);               // filt[0] = (ode_init, 0)
-    RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T mp[P], Sp[NS], G[P][P], Ct[P][P], Cv[NS];
-      predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[t+1]
-      smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
-      cond_var<T, P>(f.S[b], G, Ct, Cv);
-      // backward chain X_t = A X_{t+1} + bvec + N(0, Cv), A = G, bvec = mu_f - G mu_p   (standard.py:366-370)
-      // predict the backward filter through it (fenrir.py:151-157)
-      T nm[P];
-      RD_UNROLL for (int r = 0; r < P; ++r) {
-        T acc2 = f.mu[b][r];
-        RD_UNROLL for (int j = 0; j < P; ++j) acc2 = rd_fma(G[r][j], bk.mu[b][j] - mp[j], acc2);
-        nm[r] = acc2;
+  int cnt8 = 0;
+  for (int j = (N - 1) / K; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;
+    if (j > 0) prefetch_segment<T, F, 1>(stash, ldb, idx, j - 1, K);
+    rebuild_segment<T, Model, INTERR, QK, 1>(C, a, q, idx, j, cnt, f, stash, ldb, buf);
+    for (int s = cnt - 1; s >= 0; --s) {
+      const int t = n0 + s;
+      buf.get(s, f.mu, f.S);                              // filt[t]  (t = 0: (ode_init, 0))
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        T mp[P], Sp[NS], G[P][P], Ct[P][P], Cv[NS];
+        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[t+1]
+        smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
+        cond_var<T, P>(f.S[b], G, Ct, Cv);
+        // backward chain X_t = A X_{t+1} + bvec + N(0, Cv), A = G, bvec = mu_f - G mu_p   (standard.py:366-370)
+        // predict the backward filter through it (fenrir.py:151-157)
+        T nm[P];
+        RD_UNROLL for (int r = 0; r < P; ++r) {
+          T acc2 = f.mu[b][r];
+          RD_UNROLL for (int jj = 0; jj < P; ++jj) acc2 = rd_fma(G[r][jj], bk.mu[b][jj] - mp[jj], acc2);
+          nm[r] = acc2;
+        }
+        add_GDGt<T, P>(G, bk.S[b], Cv);
+        RD_UNROLL for (int r = 0; r < P; ++r) bk.mu[b][r] = nm[r];
+        RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = Cv[k];
       }
-      add_GDGt<T, P>(G, bk.S[b], Cv);
-      RD_UNROLL for (int r = 0; r < P; ++r) bk.mu[b][r] = nm[r];
-      RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = Cv[k];
+      if (next_obs == t) {
+        bk.template update_y<NOBS>(o, i < 0 ? i + o.n_obs : i, acc);
+        --i;
+        next_obs = obs_at(i);
+      }
+      if ((++cnt8 & 7) == 0) acc.ld.renorm();
     }
-    if (next_obs == t) {
-      bk.template update_y<NOBS>(o, i < 0 ? i + o.n_obs : i, acc);
-      --i;
-      next_obs = obs_at(i);
-    }
-    if ((++cnt & 7) == 0) acc.ld.renorm();
+    __syncwarp();
   }
-  loglik[idx] = acc.value();
+  if (live) loglik[idx] = acc.value();
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -1,11 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -q -m gpu 2>&1 | tail -4
-for b in 32768 65536 75776; do
-  echo "== B=$b"
-  python bench.py --steps 20 --warmup 3 --skip-cpu --thetas $b 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('ms/step',d['ms_per_step'],'value G',d['value']/1e9, 'e2e G', d['e2e']['value']/1e9, 'frac', d['roofline']['frac'])
-    else: print(l.rstrip())
-"
+for v in "" build/variants/st3_4000.so build/variants/st6_2000.so build/variants/st4_8000.so; do
+  echo "== ${v:-default}"; RODEO_B200_LIB=$v python tools/exp_solve_mv.py > /tmp/o.txt 2>&1; head -1 /tmp/o.txt
 done
