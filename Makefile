@@ -9,7 +9,7 @@ NVCCFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -X
 CSRC      := rodeo_b200/csrc
 OBJDIR    := build/obj$(if $(FAST),_fast,)$(if $(VARIANT),_$(VARIANT),)
 OUT       ?= rodeo_b200/librodeo_b200.so
-TUS       := abi_common abi_dalton abi_solve abi_solve_sim abi_fenrir abi_hostbuf
+TUS       := abi_common abi_dalton abi_solve abi_solve_sim abi_fenrir abi_hostbuf abi_nvrtc embedded_headers
 OBJS      := $(TUS:%=$(OBJDIR)/%.o)
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(CSRC)/rodeo_host.h include/rodeo_b200.h
 
@@ -19,9 +19,17 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ > $(OBJDIR)/$*.ptxas.log 2>&1 || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 
+# the three device headers as string literals, for NVRTC (abi_nvrtc.cu)
+$(OBJDIR)/embedded_headers.cu: $(wildcard $(CSRC)/*.cuh) tools/embed_headers.py
+	@mkdir -p $(OBJDIR)
+	python tools/embed_headers.py $(CSRC) $@
+
+$(OBJDIR)/embedded_headers.o: $(OBJDIR)/embedded_headers.cu
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ > $(OBJDIR)/embedded_headers.ptxas.log 2>&1 || (cat $(OBJDIR)/embedded_headers.ptxas.log; exit 1)
+
 $(OUT): $(OBJS)
 	@mkdir -p $(dir $(OUT))
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS)
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -ldl
 
 oracle:
 	$(MAKE) -C oracle

@@ -69,6 +69,8 @@ typedef struct RodeoProblem {
   int32_t n_bobs;          /* obs_weight.shape[2]                                                          */
   uint32_t key[2];         /* the jax PRNG key (uint32[2]); only sampling paths read it                    */
   double t_min, t_max;
+  int32_t user_wcol;       /* user (NVRTC) models only: the ODE is X[:, user_wcol] = f(X, t), i.e. W = e_user_wcol  */
+  int32_t reserved;
 } RodeoProblem;
 
 /* Bytes of device workspace the op needs for this problem (0 on unsupported input). */
@@ -146,6 +148,15 @@ int rodeo_b200_solve_mv_f64_host(const RodeoProblem* prob, const double* ode_wei
                                  double* mean_out, double* var_out);
 /* release the cached arena of the *_host wrappers */
 void rodeo_b200_host_arena_release(void);
+
+/*
+ * Register a user ODE right-hand side given as CUDA source defining `struct UserModel` with the functor interface
+ * documented in rodeo_b200/csrc/rodeo_models.cuh (rodeo_b200.models.CudaOde generates it from a one-line rhs).  The
+ * kernels are compiled for sm_100a with NVRTC on first use.  Replaces: an arbitrary `ode_fun` callable passed to
+ * rodeo.solve_mv & co. (src/rodeo/solve.py:219).  Returns the model id to put in RodeoProblem.model_id.
+ */
+int rodeo_b200_register_model_nvrtc(const char* name, const char* src, int n_block, int n_bstate, int n_bmeas,
+                                    int n_theta, int* model_id);
 
 /* measured FP64 FMA throughput (TFLOP/s) of the current device: the roofline denominator bench.py reports against */
 int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out);

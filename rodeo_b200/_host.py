@@ -130,6 +130,7 @@ class Problem:
         c.n_obs, c.n_bobs = 0, 0
         c.key[0], c.key[1] = k0, k1
         c.t_min, c.t_max = self.t_min, self.t_max
+        c.user_wcol = self.model.wcol
         self.c = c
         self.lib = _lib.load()
 

@@ -32,6 +32,8 @@ class RodeoProblem(ctypes.Structure):
         ("key", ctypes.c_uint32 * 2),
         ("t_min", ctypes.c_double),
         ("t_max", ctypes.c_double),
+        ("user_wcol", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -60,6 +62,7 @@ SIGNATURES = {
     "rodeo_b200_solve_mv_f64_host": (_i, [_P] + [_vp] * 7),
     "rodeo_b200_host_arena_release": (None, []),
     "rodeo_b200_fp64_peak_probe": (_i, [_i, _vp]),
+    "rodeo_b200_register_model_nvrtc": (_i, [ctypes.c_char_p, ctypes.c_char_p, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -136,6 +136,11 @@ int rodeo_b200_ode_init_pad_f64(const RodeoProblem* p, double t, const double* t
                                 void* stream) {
   if (int rc = check_common(p)) return rc;
   if (p->n_bstate < 2) { set_error("first_order_pad needs n_deriv >= 2"); return RODEO_ERR_INVALID; }
+  if (p->model_id >= RODEO_MODEL_USER_BASE) {
+    long long B = p->B;
+    return user_launch_raw(p->model_id, "rodeo::ode_init_pad_kernel<double, UserModel>", B, 128,
+                           {&B, &t, &theta, &x0, &X0}, (cudaStream_t)stream);
+  }
   RodeoProblem q = *p;
   q.interrogate = RODEO_INTERROGATE_KRAMER;
   return dispatch_model<InitPadRun>(q, (const double*)nullptr, (const double*)nullptr, q, t, theta, x0, X0, (cudaStream_t)stream);

@@ -38,6 +38,11 @@ extern "C" int rodeo_b200_dalton_f64(const RodeoProblem* p, const double* ode_we
   if (p->n_obs < 1) { set_error("dalton needs n_obs >= 1"); return RODEO_ERR_INVALID; }
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
   ObsArgs<double> o{p->n_obs, obs_ind, obs_data, obs_weight, obs_var};
+  if (p->model_id >= RODEO_MODEL_USER_BASE) {
+    if (p->n_bobs != 1) { set_error("dalton: n_bobs=%d is not supported for user models (only 1)", p->n_bobs); return RODEO_ERR_UNSUPPORTED; }
+    return user_launch(*p, "dalton_kernel", ", 1", ode_weight, prior_weight, prior_var, p->user_wcol, 2 * p->B, 0,
+                       {&a, &o, &loglik_out}, (cudaStream_t)stream);
+  }
   return dispatch_model<DaltonRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, o, loglik_out,
                                    (cudaStream_t)stream);
 }

@@ -45,6 +45,14 @@ extern "C" int rodeo_b200_fenrir_f64(const RodeoProblem* p, const double* ode_we
   }
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
   ObsArgs<double> o{p->n_obs, obs_ind, obs_data, obs_weight, obs_var};
+  if (p->model_id >= RODEO_MODEL_USER_BASE) {
+    if (p->n_bobs != 1) { set_error("fenrir: n_bobs=%d is not supported for user models (only 1)", p->n_bobs); return RODEO_ERR_UNSUPPORTED; }
+    double* stash = (double*)workspace;
+    long long ldb = stash_ldb(p->B);
+    const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * 8;
+    return user_launch(*p, "fenrir_kernel", ", 1", ode_weight, prior_weight, prior_var, p->user_wcol, p->B, smem,
+                       {&a, &o, &stash, &ldb, &loglik_out}, (cudaStream_t)stream);
+  }
   return dispatch_model<FenrirRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, o, (double*)workspace,
                                    loglik_out, (cudaStream_t)stream);
 }

@@ -45,6 +45,13 @@ extern "C" int rodeo_b200_solve_sim_f64(const RodeoProblem* p, const double* ode
   if (int rc = check_common(p)) return rc;
   if (int rc = check_ws(RODEO_OP_SOLVE_SIM, p, workspace, workspace_bytes)) return rc;
   CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
+  if (p->model_id >= RODEO_MODEL_USER_BASE) {
+    double* stash = (double*)workspace;
+    long long ldb = stash_ldb(p->B);
+    const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * 8;
+    return user_launch(*p, "solve_sim_kernel", "", ode_weight, prior_weight, prior_var, p->user_wcol, p->B, smem,
+                       {&a, &z_smooth, &stash, &ldb, &x_out}, (cudaStream_t)stream);
+  }
   return dispatch_model<SolveSimRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
                                      (double*)workspace, x_out, (cudaStream_t)stream);
 }

@@ -146,3 +146,17 @@ inline unsigned grid_for(long long B, int block) { return (unsigned)((B + block 
 
 }  // namespace host
 }  // namespace rodeo
+
+#include <vector>
+namespace rodeo {
+namespace host {
+// NVRTC path for user models (abi_nvrtc.cu): compile-on-first-use of the same kernel templates, driver-API launch.
+// `args` point at the kernel parameters after the leading FilterConsts; `extra_targs` are trailing template arguments
+// (", 1" for the NOBS of dalton / fenrir).
+int user_launch(const RodeoProblem& p, const char* kernel, const char* extra_targs, const double* W, const double* Q,
+                const double* R, int wcol, long long threads, int smem, std::vector<void*> args, cudaStream_t s);
+int user_launch_raw(int model_id, const char* expr, long long threads, int block, std::vector<void*> args,
+                    cudaStream_t s);
+
+}  // namespace host
+}  // namespace rodeo

@@ -42,6 +42,10 @@ _IDS = {
 }
 
 
+for _fn, _id in _IDS.items():
+    _fn.rodeo_id = _id          # the kernel enum, also reachable from a jax.ffi binding
+
+
 def resolve(interrogate, kalman_type="standard"):
     """Map an interrogation callable to its kernel enum."""
     fn, kw = interrogate, {}

@@ -29,7 +29,7 @@ def first_order_pad(ode_fun, n_vars, n_deriv):
         x0d = x0d.expand(B, n_vars).contiguous()
         c = _lib.RodeoProblem()
         c.B, c.n_steps, c.n_block, c.n_bstate, c.n_bmeas = B, 1, n_vars, n_deriv, model.n_bmeas
-        c.n_theta, c.model_id = theta.shape[1], model.model_id
+        c.n_theta, c.model_id, c.user_wcol = theta.shape[1], model.model_id, model.wcol
         X0 = torch.empty((B, n_vars, n_deriv), dtype=torch.float64, device=_host.device())
         lib = _lib.load()
         rc = lib.rodeo_b200_ode_init_pad_f64(ctypes.byref(c), float(t), _host.ptr(theta), _host.ptr(x0d),

@@ -384,3 +384,43 @@ def test_dalton_full_size_matches_c_oracle_on_a_subset(rb):
                                     rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]),
                                     theta=pr["theta"][sub], **ob))
     assert np.array_equal(again, got[sub])
+
+
+# ---- NVRTC user models ------------------------------------------------------------------------------------------------
+def test_nvrtc_user_model_matches_builtin_and_oracle(rb):
+    """A user right-hand side given as a CUDA string (the device-side analogue of passing any Python `ode_fun`) runs
+    the same kernel templates: with the FitzHugh-Nagumo formula it must reproduce the built-in functor (whose
+    Jacobian is analytic; the user model's comes from dual numbers, like jax.jacfwd) and the oracle."""
+    user = rb.models.CudaOde("fitz_user", n_block=2, n_bstate=3, n_theta=3, rhs="""
+        X V = x[0][0], R = x[1][0];
+        f[0][0] = th[2] * (V - V * V * V / T(3) + R);
+        f[1][0] = T(-1) / th[2] * (V - th[0] + th[1] * R);""")
+    pr = P.fitz_problem(48, n_steps=200, t_max=10.0, seed=21)
+    kr = rb.interrogate.interrogate_kramer
+    m, v = rb.solve_mv(None, user, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(pr["Q"], pr["R"]),
+                       theta=pr["theta"])
+    om, ov = orc.solve_mv(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                          (pr["Q"], pr["R"]), pr["theta"])
+    assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(v), ov) < TOL
+    ob = P.fitz_obs(pr, None, n_obs=11)
+    a = rb.inference.dalton(None, user, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(pr["Q"], pr["R"]),
+                            theta=pr["theta"], **ob)
+    b = rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr,
+                            prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"], **ob)
+    assert ll_err(_np(a), _np(b)) < 2e-9
+    f = rb.inference.fenrir(None, user, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(pr["Q"], pr["R"]),
+                            theta=pr["theta"], **ob)
+    fo = orc.fenrir(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                    (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    assert ll_err(_np(f), fo) < TOL
+    # first_order_pad evaluates the user functor on the device as well
+    W, init = rb.utils.first_order_pad(user, 2, 3)
+    assert P.maxnorm_rel(_np(init(pr["x0"], 0.0, theta=pr["theta"])), pr["X0"]) < 1e-15
+
+
+def test_nvrtc_reports_compile_errors(rb):
+    bad = rb.models.CudaOde("broken", n_block=1, n_bstate=3, n_theta=1, rhs="f[0][0] = undefined_symbol;")
+    with pytest.raises(Exception) as e:
+        rb.solve_mv(None, bad, np.array([[[0.0, 1.0, 0.0]]]), np.zeros((1, 3)), 0.0, 1.0, 4,
+                    rb.interrogate.interrogate_kramer, prior_pars=rb.prior.ibm_init(0.25, 3, [1.0]), theta=np.ones(1))
+    assert "undefined_symbol" in str(e.value)
