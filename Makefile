@@ -9,9 +9,10 @@ NVCCFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -X
 CSRC      := rodeo_b200/csrc
 OBJDIR    := build/obj$(if $(FAST),_fast,)$(if $(VARIANT),_$(VARIANT),)
 OUT       ?= rodeo_b200/librodeo_b200.so
-TUS       := abi_common abi_dalton abi_solve abi_solve_sim abi_fenrir abi_hostbuf abi_nvrtc embedded_headers
+TUS       := abi_common abi_dalton abi_solve abi_solve_sim abi_fenrir abi_hostbuf abi_nvrtc embedded_headers \
+             abi_dalton_f32 abi_solve_f32 abi_solve_sim_f32 abi_fenrir_f32
 OBJS      := $(TUS:%=$(OBJDIR)/%.o)
-HDRS      := $(wildcard $(CSRC)/*.cuh) $(CSRC)/rodeo_host.h include/rodeo_b200.h
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(CSRC)/rodeo_host.h include/rodeo_b200.h $(wildcard $(CSRC)/abi_*.cu)
 
 all: $(OUT) oracle
 

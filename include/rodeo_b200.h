@@ -135,6 +135,30 @@ int rodeo_b200_ode_init_pad_f64(const RodeoProblem* prob, double t, const double
                                 double* X0, void* stream);
 
 /*
+ * float32 instantiations: identical argument lists with `float` buffers (and a `float` time in ode_init_pad).
+ * The reference's float width follows jax_enable_x64; its own unit tests run in float32 when tox is not used.
+ */
+int rodeo_b200_solve_mv_f32(const RodeoProblem* prob, const float* ode_weight, const float* prior_weight,
+                            const float* prior_var, const float* ode_init, const float* theta, const float* z_interr,
+                            float* mean_out, float* var_out, void* workspace, size_t workspace_bytes, void* stream);
+int rodeo_b200_solve_sim_f32(const RodeoProblem* prob, const float* ode_weight, const float* prior_weight,
+                             const float* prior_var, const float* ode_init, const float* theta, const float* z_interr,
+                             const float* z_smooth, float* x_out, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int rodeo_b200_dalton_f32(const RodeoProblem* prob, const float* ode_weight, const float* prior_weight,
+                          const float* prior_var, const float* ode_init, const float* theta, const float* z_interr,
+                          const int32_t* obs_ind, const float* obs_data, const float* obs_weight, const float* obs_var,
+                          float* loglik_out, void* workspace, size_t workspace_bytes, void* stream);
+int rodeo_b200_fenrir_f32(const RodeoProblem* prob, const float* ode_weight, const float* prior_weight,
+                          const float* prior_var, const float* ode_init, const float* theta, const float* z_interr,
+                          const int32_t* obs_ind, const float* obs_data, const float* obs_weight, const float* obs_var,
+                          float* loglik_out, void* workspace, size_t workspace_bytes, void* stream);
+int rodeo_b200_basic_gather_f32(const RodeoProblem* prob, const float* Xt, const int32_t* obs_ind, float* ode_data,
+                                void* stream);
+int rodeo_b200_ode_init_pad_f32(const RodeoProblem* prob, float t, const float* theta, const float* x0, float* X0,
+                                void* stream);
+
+/*
  * Host-buffer convenience wrapper for the headline op: every pointer is HOST memory (pinned or pageable).
  * Copies inputs to an internal cached device arena, runs rodeo_b200_dalton_f64, copies loglik back and
  * synchronises the stream.  This is the call a ctypes / cffi / jax CPU-callback binding makes.

@@ -29,11 +29,21 @@ def to_dev(x, dtype=_DT):
     return t.to(device=device(), dtype=dtype, non_blocking=True).contiguous()
 
 
-def to_host(x):
-    """array-like / torch -> float64 C-contiguous numpy (for the tiny W, Q, R that go in the parameter bank)"""
+def to_host(x, dtype=np.float64):
+    """array-like / torch -> C-contiguous numpy (for the tiny W, Q, R that go in the parameter bank)"""
     if isinstance(x, torch.Tensor):
         x = x.detach().cpu().numpy()
-    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
+def real_dtype(*xs):
+    """float32 iff the ODE parameters / initial values are given in float32 (the reference's width follows
+    jax_enable_x64, i.e. the dtype of the user's arrays); float64 otherwise."""
+    for x in xs:
+        dt = getattr(x, "dtype", None)
+        if dt in (torch.float32, np.dtype(np.float32), np.float32):
+            return torch.float32
+    return torch.float64
 
 
 def ptr(t):
@@ -69,7 +79,7 @@ def prior_from(prior_pars, prior_weight, prior_var):
         prior_weight, prior_var = prior_pars
     if prior_weight is None or prior_var is None:
         raise TypeError("missing prior: pass prior_pars=(prior_weight, prior_var)")
-    return to_host(prior_weight), to_host(prior_var)
+    return prior_weight, prior_var
 
 
 def kalman_id(kalman_type):
@@ -87,11 +97,17 @@ class Problem:
     def __init__(self, key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                  prior_weight, prior_var, kalman_type, params, particle_offset=0):
         self.model = _models.resolve(ode_fun)
-        self.W = to_host(ode_weight)
+        self.dtype = real_dtype(params.get("theta"), ode_init)
+        self.sfx = "f32" if self.dtype == torch.float32 else "f64"
+        self.esize = 4 if self.dtype == torch.float32 else 8
+        npdt = np.float32 if self.dtype == torch.float32 else np.float64
+        self.W = to_host(ode_weight, npdt)
         if self.W.ndim != 3:
             raise ValueError("ode_weight must have shape (n_block, n_bmeas, n_bstate)")
         self.nb, self.m, self.p = self.W.shape
-        self.Q, self.R = prior_from(prior_pars, prior_weight, prior_var)
+        Qh, Rh = prior_from(prior_pars, prior_weight, prior_var)
+        # the prior is built in float64 on the host (ibm_init) and rounded once to the compute type
+        self.Q, self.R = to_host(Qh, npdt), to_host(Rh, npdt)
         if self.Q.shape != (self.nb, self.p, self.p) or self.R.shape != (self.nb, self.p, self.p):
             raise ValueError(f"prior matrices must have shape {(self.nb, self.p, self.p)}; per-theta priors are "
                              f"not supported yet (got {self.Q.shape}, {self.R.shape})")
@@ -103,8 +119,8 @@ class Problem:
             if self.model.n_theta:
                 raise TypeError(f"model {self.model.name} needs theta=({self.model.n_theta},)")
             theta = np.zeros((1, 0))
-        theta = to_dev(theta)
-        x0 = to_dev(ode_init)
+        theta = to_dev(theta, self.dtype)
+        x0 = to_dev(ode_init, self.dtype)
         self.batched = theta.ndim == 2 or x0.ndim == 3
         if theta.ndim == 1:
             theta = theta[None]
@@ -138,8 +154,18 @@ class Problem:
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def fn(self, name):
+        """C-ABI entry point of this problem's arithmetic type, e.g. fn("solve_mv") -> rodeo_b200_solve_mv_f64"""
+        return getattr(self.lib, f"rodeo_b200_{name}_{self.sfx}")
+
+    def dev(self, x):
+        return to_dev(x, self.dtype)
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=self.dtype, device=device())
+
     def workspace(self, op):
-        n = self.lib.rodeo_b200_workspace_bytes(op, ctypes.byref(self.c), 8)
+        n = self.lib.rodeo_b200_workspace_bytes(op, ctypes.byref(self.c), self.esize)
         ws = torch.empty(max(n, 1), dtype=torch.uint8, device=device())
         return ws, n
 
@@ -152,9 +178,9 @@ class Problem:
         self.obs_ind_host = ind
         self.obs_ind = torch.from_numpy(ind).to(device())
         self.c.n_obs = len(ind)
-        self.obs_data = to_dev(obs_data)
+        self.obs_data = self.dev(obs_data)
         if obs_weight is not None:
-            self.obs_weight, self.obs_var = to_dev(obs_weight), to_dev(obs_var)
+            self.obs_weight, self.obs_var = self.dev(obs_weight), self.dev(obs_var)
             n_obs, nb, n_bobs, p = self.obs_weight.shape
             if (n_obs, nb, p) != (len(ind), self.nb, self.p) or self.obs_var.shape != (n_obs, nb, n_bobs, n_bobs) \
                     or self.obs_data.shape != (n_obs, nb, n_bobs):

@@ -58,6 +58,12 @@ SIGNATURES = {
     "rodeo_b200_fenrir_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
     "rodeo_b200_basic_gather_f64": (_i, [_P, _vp, _vp, _vp, _vp]),
     "rodeo_b200_ode_init_pad_f64": (_i, [_P, _d, _vp, _vp, _vp, _vp]),
+    "rodeo_b200_solve_mv_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "rodeo_b200_solve_sim_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "rodeo_b200_dalton_f32": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
+    "rodeo_b200_fenrir_f32": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
+    "rodeo_b200_basic_gather_f32": (_i, [_P, _vp, _vp, _vp, _vp]),
+    "rodeo_b200_ode_init_pad_f32": (_i, [_P, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "rodeo_b200_dalton_f64_host": (_i, [_P] + [_vp] * 10),
     "rodeo_b200_solve_mv_f64_host": (_i, [_P] + [_vp] * 7),
     "rodeo_b200_host_arena_release": (None, []),

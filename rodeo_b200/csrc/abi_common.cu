@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters,
 
 template <class Model, int INTERR, int QK>
 struct InitPadRun {
-  static int run(const RodeoProblem& p, double t, const double* theta, const double* x0, double* X0, cudaStream_t s) {
+  template <typename T>
+  static int run(const RodeoProblem& p, T t, const T* theta, const T* x0, T* X0, cudaStream_t s) {
     if (p.B == 0) return RODEO_OK;
-    ode_init_pad_kernel<double, Model><<<grid_for(p.B, 128), 128, 0, s>>>(p.B, t, theta, x0, X0);
+    ode_init_pad_kernel<T, Model><<<grid_for(p.B, 128), 128, 0, s>>>(p.B, t, theta, x0, X0);
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;
@@ -61,6 +62,37 @@ struct InitPadRun {
 
 using namespace rodeo;
 using namespace rodeo::host;
+
+template <typename T>
+static int basic_gather_impl(const RodeoProblem* p, const T* Xt, const int32_t* obs_ind, T* ode_data, void* stream) {
+  if (int rc = check_common(p)) return rc;
+  if (p->n_obs < 0) { set_error("n_obs < 0"); return RODEO_ERR_INVALID; }
+  const long long total = p->B * (long long)p->n_obs * p->n_block * p->n_bstate;
+  if (total == 0) return RODEO_OK;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  gather_rows_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(p->B, p->n_steps + 1, p->n_obs, p->n_block * p->n_bstate,
+                                                               obs_ind, Xt, ode_data);
+  g_launches++;
+  RODEO_CUDA_OK(cudaGetLastError());
+  return RODEO_OK;
+}
+
+template <typename T>
+static int ode_init_pad_impl(const RodeoProblem* p, T t, const T* theta, const T* x0, T* X0, void* stream) {
+  if (int rc = check_common(p)) return rc;
+  if (p->n_bstate < 2) { set_error("first_order_pad needs n_deriv >= 2"); return RODEO_ERR_INVALID; }
+  if (p->model_id >= RODEO_MODEL_USER_BASE) {
+    if (sizeof(T) != 8) { set_error("user (NVRTC) models are float64 only"); return RODEO_ERR_UNSUPPORTED; }
+    long long B = p->B;
+    return user_launch_raw(p->model_id, "rodeo::ode_init_pad_kernel<double, UserModel>", B, 128,
+                           {&B, &t, &theta, &x0, &X0}, (cudaStream_t)stream);
+  }
+  RodeoProblem q = *p;
+  q.interrogate = RODEO_INTERROGATE_KRAMER;
+  return dispatch_model<InitPadRun>(q, (const T*)nullptr, (const T*)nullptr, q, t, theta, x0, X0, (cudaStream_t)stream);
+}
+
 
 extern "C" {
 
@@ -118,32 +150,12 @@ int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out) {
 }
 
 int rodeo_b200_basic_gather_f64(const RodeoProblem* p, const double* Xt, const int32_t* obs_ind, double* ode_data,
-                                void* stream) {
-  if (int rc = check_common(p)) return rc;
-  if (p->n_obs < 0) { set_error("n_obs < 0"); return RODEO_ERR_INVALID; }
-  const long long total = p->B * (long long)p->n_obs * p->n_block * p->n_bstate;
-  if (total == 0) return RODEO_OK;
-  unsigned grid = (unsigned)((total + 255) / 256);
-  if (grid > 148u * 16u) grid = 148u * 16u;
-  gather_rows_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(p->B, p->n_steps + 1, p->n_obs,
-                                                                    p->n_block * p->n_bstate, obs_ind, Xt, ode_data);
-  g_launches++;
-  RODEO_CUDA_OK(cudaGetLastError());
-  return RODEO_OK;
-}
-
+                                void* stream) { return basic_gather_impl<double>(p, Xt, obs_ind, ode_data, stream); }
+int rodeo_b200_basic_gather_f32(const RodeoProblem* p, const float* Xt, const int32_t* obs_ind, float* ode_data,
+                                void* stream) { return basic_gather_impl<float>(p, Xt, obs_ind, ode_data, stream); }
 int rodeo_b200_ode_init_pad_f64(const RodeoProblem* p, double t, const double* theta, const double* x0, double* X0,
-                                void* stream) {
-  if (int rc = check_common(p)) return rc;
-  if (p->n_bstate < 2) { set_error("first_order_pad needs n_deriv >= 2"); return RODEO_ERR_INVALID; }
-  if (p->model_id >= RODEO_MODEL_USER_BASE) {
-    long long B = p->B;
-    return user_launch_raw(p->model_id, "rodeo::ode_init_pad_kernel<double, UserModel>", B, 128,
-                           {&B, &t, &theta, &x0, &X0}, (cudaStream_t)stream);
-  }
-  RodeoProblem q = *p;
-  q.interrogate = RODEO_INTERROGATE_KRAMER;
-  return dispatch_model<InitPadRun>(q, (const double*)nullptr, (const double*)nullptr, q, t, theta, x0, X0, (cudaStream_t)stream);
-}
+                                void* stream) { return ode_init_pad_impl<double>(p, t, theta, x0, X0, stream); }
+int rodeo_b200_ode_init_pad_f32(const RodeoProblem* p, float t, const float* theta, const float* x0, float* X0,
+                                void* stream) { return ode_init_pad_impl<float>(p, t, theta, x0, X0, stream); }
 
 }  // extern "C"

@@ -2,20 +2,29 @@
 // (reference src/rodeo/solve.py:125-302).
 #include "rodeo_host.h"
 
+#ifndef RODEO_REAL
+#define RODEO_REAL double
+#define RODEO_SUFFIX _f64
+#endif
+#define RODEO_CAT2(a, b) a##b
+#define RODEO_CAT(a, b) RODEO_CAT2(a, b)
+#define RODEO_FN(name) RODEO_CAT(name, RODEO_SUFFIX)
+typedef RODEO_REAL real_t;
+
 namespace rodeo {
 namespace host {
 
 template <class Model, int INTERR, int QK>
 struct SolveSimRun {
-  static int run(const RodeoProblem& p, const double* W, const double* Q, const double* R,
-                 const CommonArgs<double>& a, const double* z_smooth, double* stash, double* x_out, cudaStream_t s) {
-    FilterConsts<double, Model::NB, Model::P, Model::M> C;
-    pack_consts<double, Model::NB, Model::P, Model::M>(W, Q, R, C);
+  static int run(const RodeoProblem& p, const real_t* W, const real_t* Q, const real_t* R,
+                 const CommonArgs<real_t>& a, const real_t* z_smooth, real_t* stash, real_t* x_out, cudaStream_t s) {
+    FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
+    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
-    constexpr int SMEM = SegBuf<double, Fwd<double, Model, INTERR, QK>>::BYTES;
-    RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<double, Model, INTERR, QK>,
+    constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
+    RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<real_t, Model, INTERR, QK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    solve_sim_kernel<double, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, z_smooth, stash,
+    solve_sim_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, z_smooth, stash,
                                                                                 stash_ldb(p.B), x_out);
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
@@ -30,7 +39,7 @@ using namespace rodeo;
 using namespace rodeo::host;
 
 static int check_ws(int op, const RodeoProblem* p, void* ws, size_t ws_bytes) {
-  const size_t need = rodeo_b200_workspace_bytes(op, p, 8);
+  const size_t need = rodeo_b200_workspace_bytes(op, p, (int)sizeof(real_t));
   if (need > 0 && (ws == nullptr || ws_bytes < need)) {
     set_error("workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);
     return RODEO_ERR_WORKSPACE;
@@ -38,20 +47,21 @@ static int check_ws(int op, const RodeoProblem* p, void* ws, size_t ws_bytes) {
   return RODEO_OK;
 }
 
-extern "C" int rodeo_b200_solve_sim_f64(const RodeoProblem* p, const double* ode_weight, const double* prior_weight,
-                                        const double* prior_var, const double* ode_init, const double* theta,
-                                        const double* z_interr, const double* z_smooth, double* x_out,
+extern "C" int RODEO_FN(rodeo_b200_solve_sim)(const RodeoProblem* p, const real_t* ode_weight, const real_t* prior_weight,
+                                        const real_t* prior_var, const real_t* ode_init, const real_t* theta,
+                                        const real_t* z_interr, const real_t* z_smooth, real_t* x_out,
                                         void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_common(p)) return rc;
   if (int rc = check_ws(RODEO_OP_SOLVE_SIM, p, workspace, workspace_bytes)) return rc;
-  CommonArgs<double> a = make_common<double>(*p, ode_init, theta, z_interr);
+  CommonArgs<real_t> a = make_common<real_t>(*p, ode_init, theta, z_interr);
   if (p->model_id >= RODEO_MODEL_USER_BASE) {
-    double* stash = (double*)workspace;
+    if (sizeof(real_t) != 8) { set_error("user (NVRTC) models are float64 only"); return RODEO_ERR_UNSUPPORTED; }
+    real_t* stash = (real_t*)workspace;
     long long ldb = stash_ldb(p->B);
-    const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * 8;
-    return user_launch(*p, "solve_sim_kernel", "", ode_weight, prior_weight, prior_var, p->user_wcol, p->B, smem,
+    const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * (int)sizeof(real_t);
+    return user_launch(*p, "solve_sim_kernel", "", (const double*)ode_weight, (const double*)prior_weight, (const double*)prior_var, p->user_wcol, p->B, smem,
                        {&a, &z_smooth, &stash, &ldb, &x_out}, (cudaStream_t)stream);
   }
   return dispatch_model<SolveSimRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
-                                     (double*)workspace, x_out, (cudaStream_t)stream);
+                                     (real_t*)workspace, x_out, (cudaStream_t)stream);
 }

@@ -121,8 +121,8 @@ inline int dispatch_interr(int interr, int qk, A&&... args) {
   return RODEO_ERR_UNSUPPORTED;
 }
 // W and Q are the host arrays of the call; the structure test needs the model's WCOL, so it happens here.
-template <template <class, int, int> class FN, typename... A>
-inline int dispatch_model(const RodeoProblem& p, const double* W, const double* Q, A&&... args) {
+template <template <class, int, int> class FN, typename R, typename... A>
+inline int dispatch_model(const RodeoProblem& p, const R* W, const R* Q, A&&... args) {
   switch (p.model_id) {
 #define RODEO_CASE(MODEL, ID)                                                                                 \
   case ID:                                                                                                    \
@@ -132,7 +132,7 @@ inline int dispatch_model(const RodeoProblem& p, const double* W, const double* 
       return RODEO_ERR_INVALID;                                                                               \
     }                                                                                                         \
     return dispatch_interr<FN, MODEL>(p.interrogate,                                                          \
-                                      (W && Q) ? detect_structure<double>(Q, W, MODEL::NB, MODEL::P, MODEL::M, \
+                                      (W && Q) ? detect_structure<R>(Q, W, MODEL::NB, MODEL::P, MODEL::M, \
                                                                           MODEL::WCOL) : QK_DENSE,             \
                                       static_cast<A&&>(args)...);
     RODEO_AOT_MODELS(RODEO_CASE)

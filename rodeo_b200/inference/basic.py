@@ -22,8 +22,8 @@ def basic(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate
     Xt, _ = solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate,
                      prior_pars=(pb.Q, pb.R), kalman_type=kalman_type, **params)
     Xb = Xt if pb.batched else Xt[None]
-    ode_data = torch.empty((pb.B, pb.c.n_obs, pb.nb, pb.p), dtype=torch.float64, device=_host.device())
-    rc = pb.lib.rodeo_b200_basic_gather_f64(ctypes.byref(pb.c), _host.ptr(Xb), _host.ptr(pb.obs_ind),
+    ode_data = pb.empty(pb.B, pb.c.n_obs, pb.nb, pb.p)
+    rc = pb.fn("basic_gather")(ctypes.byref(pb.c), _host.ptr(Xb), _host.ptr(pb.obs_ind),
                                             _host.ptr(ode_data), pb.stream())
     _lib.check(rc, "basic_gather")
     return obs_loglik(obs_data, pb.unbatch(ode_data), **params), Xt

@@ -17,9 +17,9 @@ def dalton(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogat
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
     pb.set_obs(obs_data, obs_times, obs_weight, obs_var)
-    out = torch.empty((pb.B,), dtype=torch.float64, device=_host.device())
-    zi = None if _z_interr is None else _host.to_dev(_z_interr)
-    rc = pb.lib.rodeo_b200_dalton_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
+    out = pb.empty(pb.B)
+    zi = None if _z_interr is None else pb.dev(_z_interr)
+    rc = pb.fn("dalton")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
                                       _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(pb.obs_ind),
                                       _host.ptr(pb.obs_data), _host.ptr(pb.obs_weight), _host.ptr(pb.obs_var),
                                       _host.ptr(out), None, 0, pb.stream())

@@ -14,16 +14,16 @@ def solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrog
 
     Returns:
         mean (``[B,] n_steps+1, n_block, n_bstate``), var (``[B,] n_steps+1, n_block, n_bstate, n_bstate``)
-        as float64 CUDA tensors.
+        as CUDA tensors (float64, or float32 when ``theta`` / ``ode_init`` are float32).
     """
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params)
     N, dev = pb.n_steps, _host.device()
-    mean = torch.empty((pb.B, N + 1, pb.nb, pb.p), dtype=torch.float64, device=dev)
-    var = torch.empty((pb.B, N + 1, pb.nb, pb.p, pb.p), dtype=torch.float64, device=dev)
+    mean = pb.empty(pb.B, N + 1, pb.nb, pb.p)
+    var = pb.empty(pb.B, N + 1, pb.nb, pb.p, pb.p)
     ws, n = pb.workspace(_lib.OP_SOLVE_MV)
-    zi = None if _z_interr is None else _host.to_dev(_z_interr)
-    rc = pb.lib.rodeo_b200_solve_mv_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
+    zi = None if _z_interr is None else pb.dev(_z_interr)
+    rc = pb.fn("solve_mv")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
                                         _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(mean),
                                         _host.ptr(var), _host.ptr(ws), n, pb.stream())
     _lib.check(rc, "solve_mv")
@@ -47,11 +47,11 @@ def solve_sim(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interro
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
     N, dev = pb.n_steps, _host.device()
-    x = torch.empty((pb.B, N + 1, pb.nb, pb.p), dtype=torch.float64, device=dev)
+    x = pb.empty(pb.B, N + 1, pb.nb, pb.p)
     ws, n = pb.workspace(_lib.OP_SOLVE_SIM)
-    zi = None if _z_interr is None else _host.to_dev(_z_interr)
-    zs = None if _z_smooth is None else _host.to_dev(_z_smooth)
-    rc = pb.lib.rodeo_b200_solve_sim_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
+    zi = None if _z_interr is None else pb.dev(_z_interr)
+    zs = None if _z_smooth is None else pb.dev(_z_smooth)
+    rc = pb.fn("solve_sim")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
                                          _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(zs),
                                          _host.ptr(x), _host.ptr(ws), n, pb.stream())
     _lib.check(rc, "solve_sim")

@@ -19,8 +19,9 @@ def first_order_pad(ode_fun, n_vars, n_deriv):
         raise ValueError(f"{model.name} is compiled for n_vars={model.n_block}, n_deriv={model.n_bstate}")
 
     def ode_init(x0, t, **params):
-        theta = _host.to_dev(params["theta"])
-        x0d = _host.to_dev(x0)
+        dt = _host.real_dtype(params["theta"], x0)
+        theta = _host.to_dev(params["theta"], dt)
+        x0d = _host.to_dev(x0, dt)
         batched = theta.ndim == 2 or x0d.ndim == 2
         theta = theta[None] if theta.ndim == 1 else theta
         x0d = x0d[None] if x0d.ndim == 1 else x0d
@@ -30,9 +31,10 @@ def first_order_pad(ode_fun, n_vars, n_deriv):
         c = _lib.RodeoProblem()
         c.B, c.n_steps, c.n_block, c.n_bstate, c.n_bmeas = B, 1, n_vars, n_deriv, model.n_bmeas
         c.n_theta, c.model_id, c.user_wcol = theta.shape[1], model.model_id, model.wcol
-        X0 = torch.empty((B, n_vars, n_deriv), dtype=torch.float64, device=_host.device())
+        X0 = torch.empty((B, n_vars, n_deriv), dtype=dt, device=_host.device())
         lib = _lib.load()
-        rc = lib.rodeo_b200_ode_init_pad_f64(ctypes.byref(c), float(t), _host.ptr(theta), _host.ptr(x0d),
+        fn = lib.rodeo_b200_ode_init_pad_f32 if dt == torch.float32 else lib.rodeo_b200_ode_init_pad_f64
+        rc = fn(ctypes.byref(c), float(t), _host.ptr(theta), _host.ptr(x0d),
                                              _host.ptr(X0), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "ode_init")
         return X0 if batched else X0[0]
