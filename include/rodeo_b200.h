@@ -71,6 +71,10 @@ typedef struct RodeoProblem {
   double t_min, t_max;
   int32_t user_wcol;       /* user (NVRTC) models only: the ODE is X[:, user_wcol] = f(X, t), i.e. W = e_user_wcol  */
   int32_t reserved;
+  /* optional DEVICE pointer (B, n_block), same arithmetic type as the call, or NULL: per-theta scale of the prior
+   * variance, R(theta, b) = prior_var_scale[theta, b] * prior_var[b].  Covers an IBM prior whose sigma is part of
+   * theta (sigma^2 R_1, src/rodeo/prior/ibm.py:84-86) without a (B, n_block, p, p) array. */
+  const void* prior_var_scale;
 } RodeoProblem;
 
 /* Bytes of device workspace the op needs for this problem (0 on unsupported input). */

@@ -106,6 +106,21 @@ class Problem:
             raise ValueError("ode_weight must have shape (n_block, n_bmeas, n_bstate)")
         self.nb, self.m, self.p = self.W.shape
         Qh, Rh = prior_from(prior_pars, prior_weight, prior_var)
+        Qh, Rh = to_host(Qh), to_host(Rh)
+        self.r_scale = None
+        if Rh.ndim == 4:
+            # per-theta prior variance (B, n_block, p, p): supported when it is a per-(theta, block) multiple of a
+            # shared matrix, which is what ibm_init gives when sigma is part of theta (R = sigma^2 R_1)
+            if Qh.ndim == 4:
+                if not np.all(Qh == Qh[:1]):
+                    raise NotImplementedError("per-theta prior_weight (Q) is not supported")
+                Qh = Qh[0]
+            ref = Rh[0]
+            scale = Rh[:, :, -1, -1] / ref[None, :, -1, -1]
+            if not np.allclose(Rh, scale[:, :, None, None] * ref[None], rtol=1e-13, atol=0.0):
+                raise NotImplementedError("per-theta prior_var must be a per-(theta, block) multiple of one matrix "
+                                          "(e.g. ibm_init with a theta-dependent sigma)")
+            self.r_scale_host, Rh = scale, ref
         # the prior is built in float64 on the host (ibm_init) and rounded once to the compute type
         self.Q, self.R = to_host(Qh, npdt), to_host(Rh, npdt)
         if self.Q.shape != (self.nb, self.p, self.p) or self.R.shape != (self.nb, self.p, self.p):
@@ -147,6 +162,12 @@ class Problem:
         c.key[0], c.key[1] = k0, k1
         c.t_min, c.t_max = self.t_min, self.t_max
         c.user_wcol = self.model.wcol
+        if getattr(self, "r_scale_host", None) is not None:
+            if self.r_scale_host.shape[0] not in (1, B):
+                raise ValueError("per-theta prior_var disagrees with the batch size")
+            self.r_scale = to_dev(np.broadcast_to(self.r_scale_host, (B, self.nb)).copy(), self.dtype)
+            c.prior_var_scale = self.r_scale.data_ptr()
+            self.batched = True
         self.c = c
         self.lib = _lib.load()
 

@@ -75,9 +75,12 @@ struct FilterConsts {
 };
 
 // ---- predict ----------------------------------------------------------------------------------------------
-// mu_p = Q mu ;  S_p = Q S Q^T + R        (mean_state == 0 in the solver, reference src/rodeo/solve.py:52)
+// mu_p = Q mu ;  S_p = Q S Q^T + rs R      (mean_state == 0 in the solver, reference src/rodeo/solve.py:52)
+// rs is a per-theta scale of the shared prior variance (1 when the prior is not batched): an IBM prior whose sigma
+// is part of theta is R(theta) = sigma^2 R_1 (src/rodeo/prior/ibm.py:84-86), so the per-theta prior costs one
+// register per block instead of p(p+1)/2.
 template <typename T, int P, int QK>
-RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], const T (&mu)[P],
+RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], T rs, const T (&mu)[P],
                     const T (&S)[P * (P + 1) / 2], T (&mup)[P], T (&Sp)[P * (P + 1) / 2]) {
   T A[P][P];  // A = Q S
   RD_UNROLL for (int i = 0; i < P; ++i) {
@@ -111,7 +114,7 @@ RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], const T (
         s = A[i][0] * Q[j][0];
         RD_UNROLL for (int k = 1; k < P; ++k) s = rd_fma(A[i][k], Q[j][k], s);
       }
-      Sp[sidx<P>(i, j)] = s + R[sidx<P>(i, j)];
+      Sp[sidx<P>(i, j)] = rd_fma(rs, R[sidx<P>(i, j)], s);
     }
   }
 }

@@ -33,6 +33,7 @@ struct CommonArgs {
   const T* ode_init;      // (B, NB, P)
   unsigned key0, key1;    // PRNG key (the reference's uint32[2] jax key)
   const T* z_interr;      // optional injected normals for interrogate_chkrebtii, (B, n_steps, NSTREAM, NB, P)
+  const T* r_scale;       // optional per-theta scale of the prior variance, (B, NB): R(theta, b) = r_scale * R[b]
 };
 
 template <typename T>
@@ -84,6 +85,11 @@ struct Fwd {
 
   T mu[NB][P];
   T S[NB][NS];
+  T rs[NB];               // per-theta prior-variance scale (1 unless the prior is batched)
+
+  RD_DEV void load_scale(const CommonArgs<T>& a, i64 idx) {
+    RD_UNROLL for (int b = 0; b < NB; ++b) rs[b] = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
+  }
 
   RD_DEV void init(const T* x0) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
@@ -96,7 +102,7 @@ struct Fwd {
   RD_DEV void predict_all(const Consts& C) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       T mp[P], Sp[NS];
-      predict<T, P, QK>(C.Q[b], C.R[b], mu[b], S[b], mp, Sp);
+      predict<T, P, QK>(C.Q[b], C.R[b], rs[b], mu[b], S[b], mp, Sp);
       RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = mp[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = Sp[k];
     }
@@ -299,6 +305,7 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
   F f;
   f.init(a.ode_init + idx * NB * P);
+  f.load_scale(a, idx);
   LogPdfAcc<T> acc;
   acc.init();
 
@@ -563,6 +570,7 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
   f.init(a.ode_init + idx * NB * P);
+  f.load_scale(a, idx);
   forward_with_checkpoints<T, Model, INTERR, QK, K>(C, a, q, idx, live, f, stash, ldb);
 
   // smoothed[N] = filt[N]   (solve.py:279-282)
@@ -584,7 +592,7 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
       buf.get(s, f.mu, f.S);                               // filt[n]
       RD_UNROLL for (int b = 0; b < NB; ++b) {
         T mp[P], Sp[NS], G[P][P], Ct[P][P];
-        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
+        predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         // mu_s = mu_f + G (mu_s' - mu_p) ;  S_s = S_f + G (S_s' - S_p) G^T    (standard.py:213-216)
         T dm[P], D[NS];
@@ -630,6 +638,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
   f.init(a.ode_init + idx * NB * P);
+  f.load_scale(a, idx);
   forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
 
   auto normals = [&](int n, T (&z)[NB * P]) {
@@ -674,7 +683,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
       T xn[NB][P];
       RD_UNROLL for (int b = 0; b < NB; ++b) {
         T mp[P], Sp[NS], G[P][P], Ct[P][P], m[P], Cv[NS];
-        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
+        predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         // m = mu_f + G (x' - mu_p) ;  C = S_f - G (S_f Q^T)^T      (standard.py:251-254)
         RD_UNROLL for (int i = 0; i < P; ++i) {
@@ -715,6 +724,7 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
   f.init(a.ode_init + idx * NB * P);
+  f.load_scale(a, idx);
   forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
 
   // backward-filter state starts at filt[N]
@@ -744,7 +754,7 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
       buf.get(s, f.mu, f.S);                              // filt[t]  (t = 0: (ode_init, 0))
       RD_UNROLL for (int b = 0; b < NB; ++b) {
         T mp[P], Sp[NS], G[P][P], Ct[P][P], Cv[NS];
-        predict<T, P, QK>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Sp);          // pred[t+1]
+        predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[t+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         cond_var<T, P>(f.S[b], G, Ct, Cv);
         // backward chain X_t = A X_{t+1} + bvec + N(0, Cv), A = G, bvec = mu_f - G mu_p   (standard.py:366-370)

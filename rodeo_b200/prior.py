@@ -29,9 +29,18 @@ def ibm_state(dt, q, sigma):
 
 
 def ibm_init(dt, n_deriv, sigma):
-    """(wgt_state, var_state) of shapes (n_block, p, p) -- reference src/rodeo/prior/ibm.py:65-88."""
+    """(wgt_state, var_state) of shapes (n_block, p, p) -- reference src/rodeo/prior/ibm.py:65-88.
+
+    ``sigma`` of shape (B, n_block) (a theta-dependent prior scale, as in the reference's
+    docs/examples/parameter.md:218-222 under vmap) gives var_state of shape (B, n_block, p, p).
+    """
+    if hasattr(sigma, "detach"):
+        sigma = sigma.detach().cpu().numpy()
     sigma = np.asarray(sigma, dtype=np.float64)
     Q1, R1 = ibm_state(dt, n_deriv - 1, 1)
+    if sigma.ndim == 2:
+        Q = np.repeat(Q1[None], sigma.shape[1], axis=0)
+        return Q, sigma[:, :, None, None] ** 2 * R1[None, None]
     Q = np.repeat(Q1[None], len(sigma), axis=0)
     R = np.stack([sigma[b] ** 2 * R1 for b in range(len(sigma))])
     return Q, R

@@ -458,3 +458,33 @@ def test_float32_solve_mv_and_dalton(rb):
     e = ll_err(_np(ll).astype(np.float64), want)
     print(f"float32 dalton: {e:.2e}")
     assert ll.dtype == torch.float32 and e < 1e-3
+
+
+# ---- per-theta prior ---------------------------------------------------------------------------------------------------
+def test_theta_dependent_prior_scale(rb):
+    """sigma as part of theta (reference docs/examples/parameter.md:218-222: prior_pars rebuilt per theta under vmap):
+    ibm_init with a (B, n_block) sigma gives R of shape (B, n_block, p, p)."""
+    B = 48
+    pr = P.fitz_problem(B, n_steps=200, t_max=10.0, seed=41)
+    sig = 0.1 * np.exp(0.3 * np.random.default_rng(3).standard_normal((B, 2)))
+    Q, Rb = rb.prior.ibm_init(10.0 / 200, 3, sig)
+    assert Rb.shape == (B, 2, 3, 3)
+    Qo = Q
+    Ro = np.stack([orc.ibm_init(10.0 / 200, 3, sig[k])[1] for k in range(B)])
+    assert np.allclose(Rb, Ro, rtol=1e-15)
+    kr = rb.interrogate.interrogate_kramer
+    m, v = rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(Q, Rb),
+                       theta=pr["theta"])
+    om, ov = orc.solve_mv(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                          (Qo, Ro), pr["theta"])
+    assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(v), ov) < TOL
+    ob = P.fitz_obs(pr, None, n_obs=11)
+    ll = rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr,
+                             prior_pars=(Q, Rb), theta=pr["theta"], **ob)
+    want = orc.dalton(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                      (Qo, Ro), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    assert ll_err(_np(ll), want) < 2e-9
+    with pytest.raises(NotImplementedError):
+        bad = Rb.copy(); bad[3, 0, 0, 1] *= 1.5
+        rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(Q, bad),
+                    theta=pr["theta"])
