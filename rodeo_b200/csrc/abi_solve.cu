@@ -21,11 +21,20 @@ struct SolveMvRun {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
-    constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
-    RODEO_CUDA_OK(cudaFuncSetAttribute(solve_mv_kernel<real_t, Model, INTERR, QK>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    solve_mv_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, stash, stash_ldb(p.B),
-                                                                               mean_out, var_out);
+    if constexpr (Model::NB >= 2) {
+      // one lane per (theta, block): fewer thetas per warp => longer contiguous output runs (rodeo_kernels.cuh)
+      typedef BlockLane<real_t, Model, INTERR, QK> L;
+      RODEO_CUDA_OK(cudaFuncSetAttribute(solve_mv_bl_kernel<real_t, Model, INTERR, QK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+      solve_mv_bl_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, L::TW), 32, L::BYTES, s>>>(
+          C, a, stash, stash_ldb(p.B), mean_out, var_out);
+    } else {
+      constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
+      RODEO_CUDA_OK(cudaFuncSetAttribute(solve_mv_kernel<real_t, Model, INTERR, QK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      solve_mv_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, stash, stash_ldb(p.B),
+                                                                                 mean_out, var_out);
+    }
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;

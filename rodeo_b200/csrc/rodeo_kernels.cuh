@@ -616,6 +616,291 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   }
 }
 
+
+// ==================================================================================================================
+// solve_mv with one lane per (theta, block)
+// ==================================================================================================================
+// solve_mv is bound by the write-back of its 192 B/theta*step of output, and the reference layout is theta-outermost:
+// a warp can only write, per theta, the K time rows it has staged (K * 144 B of covariances).  A store-only
+// micro-benchmark of that pattern (tools/micro/copyout_pattern.cu) reaches 3.2 TB/s at K = 3 but 4.3 TB/s at K = 6:
+// the longer the per-theta run, the better HBM takes it.  K is capped by shared memory per warp, i.e. by the number
+// of thetas a warp carries -- so for n_block >= 2 the blocks of a theta are spread over adjacent lanes: a warp then
+// carries 32 / n_block thetas and stages n_block times more rows in the same buffer.  The block Kalman recursions are
+// independent between blocks (reference: jax.vmap over n_block, src/rodeo/solve.py:62,81,263); only the ODE
+// right-hand side couples them, through the JCOLS leading entries of each block's predicted mean, which the lanes of a
+// theta exchange by shuffle once per forward step.  It also halves the work quantum per warp (finer load balance over
+// the SM sub-partitions) and the registers per lane.
+#ifndef RODEO_BL_SMEM
+#define RODEO_BL_SMEM 18432      // staging bytes per warp
+#endif
+__host__ __device__ constexpr int seg_len_bl(int nstate, int nb) {
+  return (RODEO_BL_SMEM / (nstate * (32 / nb + 1) * 8)) < 1 ? 1
+       : ((RODEO_BL_SMEM / (nstate * (32 / nb + 1) * 8)) > 12 ? 12 : (RODEO_BL_SMEM / (nstate * (32 / nb + 1) * 8)));
+}
+
+template <typename T, class Model, int INTERR, int QK>
+struct BlockLane {
+  static constexpr int NB = Model::NB, P = Model::P, M = Model::M, JC = Model::JCOLS;
+  static constexpr int NS = P * (P + 1) / 2, MS = M * (M + 1) / 2, NSTATE = NB * (P + NS);
+  static constexpr bool UNITW = (QK == QK_UNIT_UPPER) && (M == 1);
+  static constexpr int WK = Model::WCOL;
+  static constexpr bool HAS_J = (INTERR == INTERR_KRAMER);
+  static constexpr int TW = 32 / NB;                 // thetas per warp
+  static constexpr int PITCH = TW + 1;
+  static constexpr int K = seg_len_bl(NSTATE, NB);
+  static constexpr int BYTES = K * NSTATE * PITCH * (int)sizeof(T);
+  typedef FilterConsts<T, NB, P, M> Consts;
+  typedef typename Model::template Par<T> Par;
+
+  T mu[P], S[NS], rs;
+  T Q[P][P], R[NS], W[M][P];     // this lane's block of the shared constants, in registers
+  int b, gb;                     // block index, first lane of this theta's lane group
+
+  RD_DEV void load_consts(const Consts& C) {
+    RD_UNROLL for (int c = 0; c < NB; ++c)
+      if (c == b) {
+        RD_UNROLL for (int i = 0; i < P; ++i)
+          RD_UNROLL for (int j = 0; j < P; ++j) Q[i][j] = C.Q[c][i][j];
+        RD_UNROLL for (int k = 0; k < NS; ++k) R[k] = C.R[c][k];
+        RD_UNROLL for (int r = 0; r < M; ++r)
+          RD_UNROLL for (int j = 0; j < P; ++j) W[r][j] = C.W[c][r][j];
+      }
+  }
+  RD_DEV void init(const T* x0) {
+    RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = x0[b * P + i];
+    RD_UNROLL for (int k = 0; k < NS; ++k) S[k] = T(0);
+  }
+  RD_DEV static int km(int bb, int i) { return bb * P + i; }
+  RD_DEV static int kv(int bb, int k) { return NB * P + bb * NS + k; }
+
+  // one forward step n -> n+1 of this lane's block (predict, interrogate, update); all 32 lanes must call it
+  RD_DEV void step(const CommonArgs<T>& a, const Par& q, i64 idx, int n) {
+    {
+      T mp[P], Sp[NS];
+      predict<T, P, QK>(Q, R, rs, mu, S, mp, Sp);
+      RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = mp[i];
+      RD_UNROLL for (int k = 0; k < NS; ++k) S[k] = Sp[k];
+    }
+    const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
+    T xo[JC];
+    if constexpr (INTERR == INTERR_CHKREBTII) {
+      T zc[JC];
+      if (a.z_interr != nullptr) {
+        const T* z = a.z_interr + (idx * a.n_steps + n) * (NB * P) + b * P;
+        RD_UNROLL for (int j = 0; j < JC; ++j) zc[j] = z[j];
+      } else {
+        // the same stream layout as the thread-per-theta kernels: normal k = b*JC + j of the step's vector
+        T z[NB * JC];
+        philox_normals<T, NB * JC>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, z);
+        RD_UNROLL for (int j = 0; j < JC; ++j) {
+          T v = z[j];
+          RD_UNROLL for (int c = 1; c < NB; ++c) v = (b == c) ? z[c * JC + j] : v;
+          zc[j] = v;
+        }
+      }
+      T A[P][P];
+      psd_factor<T, P>(S, A);
+      RD_UNROLL for (int j = 0; j < JC; ++j) {
+        T acc = mu[j];
+        RD_UNROLL for (int k = 0; k <= j; ++k) acc = rd_fma(A[j][k], zc[k], acc);
+        xo[j] = acc;
+      }
+    } else {
+      RD_UNROLL for (int j = 0; j < JC; ++j) xo[j] = mu[j];
+    }
+    // the right-hand side couples the blocks: gather every block's visible columns from the theta's lane group
+    T x[NB][JC];
+    RD_UNROLL for (int c = 0; c < NB; ++c)
+      RD_UNROLL for (int j = 0; j < JC; ++j) x[c][j] = __shfl_sync(0xffffffffu, xo[j], gb + c);
+    T f[NB][M], jl[NB][M][JC];
+    if constexpr (HAS_J) {
+      eval_f_jac<Model, T>(q, t, x, f, jl);
+    } else {
+      Model::template rhs<T, T>(q, t, x, f);
+      RD_UNROLL for (int c = 0; c < NB; ++c)
+        RD_UNROLL for (int r = 0; r < M; ++r)
+          RD_UNROLL for (int j = 0; j < JC; ++j) jl[c][r][j] = T(0);
+    }
+    T fo[M], jo[M][JC];
+    RD_UNROLL for (int r = 0; r < M; ++r) {
+      fo[r] = f[0][r];
+      RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = jl[0][r][j];
+      RD_UNROLL for (int c = 1; c < NB; ++c) {
+        fo[r] = (b == c) ? f[c][r] : fo[r];
+        RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = (b == c) ? jl[c][r][j] : jo[r][j];
+      }
+    }
+    LogPdfAcc<T> dummy;
+    if constexpr (UNITW) {
+      const T res = fo[0] - mu[WK];
+      const T V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) ? S[sidx<P>(WK, WK)] : T(0);
+      update_unit_row<T, P, JC, WK, false, HAS_J>(mu, S, jo[0], res, V, dummy);
+    } else {
+      T wm[M][P], res[M], V[MS];
+      RD_UNROLL for (int r = 0; r < M; ++r) {
+        T acc = fo[r];
+        RD_UNROLL for (int j = 0; j < P; ++j) {
+          wm[r][j] = (HAS_J && j < JC) ? W[r][j] - jo[r][j] : W[r][j];
+          acc = rd_fma(-W[r][j], mu[j], acc);
+        }
+        res[r] = acc;
+      }
+      if constexpr (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) {
+        T u[M][P];
+        RD_UNROLL for (int r = 0; r < M; ++r)
+          RD_UNROLL for (int i = 0; i < P; ++i) {
+            T acc = S[sym<P>(i, 0)] * W[r][0];
+            RD_UNROLL for (int j = 1; j < P; ++j) acc = rd_fma(S[sym<P>(i, j)], W[r][j], acc);
+            u[r][i] = acc;
+          }
+        RD_UNROLL for (int r = 0; r < M; ++r)
+          RD_UNROLL for (int s = r; s < M; ++s) {
+            T acc = W[r][0] * u[s][0];
+            RD_UNROLL for (int i = 1; i < P; ++i) acc = rd_fma(W[r][i], u[s][i], acc);
+            V[sidx<M>(r, s)] = acc;
+          }
+      } else {
+        RD_UNROLL for (int k = 0; k < MS; ++k) V[k] = T(0);
+      }
+      update<T, P, M, false>(mu, S, wm, res, V, dummy);
+    }
+  }
+};
+
+// copy `rows` staged time rows of `nth` thetas (buffer [slot][state][theta], pitch PITCH) to a (B, N+1, ROW) output;
+// same scheme as SegBuf::copy_out
+template <typename T, int NB, int P, int K, int PITCH, bool VAR>
+RD_DEV void seg_copy_out(const T* __restrict__ base, int lane, T* __restrict__ out, i64 theta0, int nth,
+                         int n_rows_total, int n0, int rows) {
+  constexpr int NS = P * (P + 1) / 2, NSTATE = NB * (P + NS);
+  constexpr int ROW = VAR ? NB * P * P : NB * P;
+  constexpr int NIT = (K * ROW + 31) / 32;
+  const int run = rows * ROW;
+  int src[NIT];
+  RD_UNROLL for (int it = 0; it < NIT; ++it) {
+    const int r = lane + 32 * it;
+    const int s = r / ROW, e = r - s * ROW;
+    int k = e;
+    if (VAR) {
+      const int bb = e / (P * P), ij = e - bb * (P * P), i = ij / P, j = ij - i * P;
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      k = NB * P + bb * NS + lo * P - (lo * (lo - 1)) / 2 + (hi - lo);
+    }
+    src[it] = r < run ? (s * NSTATE + k) * PITCH : -1;
+  }
+  const i64 stride = (i64)n_rows_total * ROW;
+  T* dst = out + (theta0 * (i64)n_rows_total + n0) * ROW + lane;
+  RD_UNROLL4 for (int th = 0; th < nth; ++th) {
+    RD_UNROLL for (int it = 0; it < NIT; ++it)
+      if (src[it] >= 0) dst[32 * it] = base[src[it] + th];
+    dst += stride;
+  }
+}
+
+template <typename T, class Model, int INTERR, int QK>
+__global__ void __launch_bounds__(32)
+solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                   const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
+                   T* __restrict__ mean_out, T* __restrict__ var_out) {
+  typedef BlockLane<T, Model, INTERR, QK> L;
+  constexpr int NB = L::NB, P = L::P, NS = L::NS, K = L::K, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
+  const int lane = threadIdx.x;
+  int tl = lane / NB, b = lane - tl * NB;
+  const bool lane_ok = tl < TW;            // 32 % NB trailing lanes shadow the last group; their stores are masked
+  if (!lane_ok) { tl = TW - 1; b = NB - 1; }
+  const i64 theta0 = (i64)blockIdx.x * TW;
+  i64 idx = theta0 + tl;
+  const bool live = lane_ok && idx < a.B;
+  if (idx >= a.B) idx = a.B - 1;
+  const typename L::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const int N = a.n_steps;
+  T* buf = reinterpret_cast<T*>(rodeo_dyn_smem);
+  L f;
+  f.b = b; f.gb = tl * NB;
+  f.load_consts(C);
+  f.rs = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
+  const T* x0 = a.ode_init + idx * NB * P;
+  f.init(x0);
+  auto put = [&](int s, const T (&m)[P], const T (&Sv)[NS]) {
+    RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * NSTATE + L::km(b, i)) * PITCH + tl] = m[i];
+    RD_UNROLL for (int k = 0; k < NS; ++k) buf[(s * NSTATE + L::kv(b, k)) * PITCH + tl] = Sv[k];
+  };
+  auto get = [&](int s, T (&m)[P], T (&Sv)[NS]) {
+    RD_UNROLL for (int i = 0; i < P; ++i) m[i] = buf[(s * NSTATE + L::km(b, i)) * PITCH + tl];
+    RD_UNROLL for (int k = 0; k < NS; ++k) Sv[k] = buf[(s * NSTATE + L::kv(b, k)) * PITCH + tl];
+  };
+  // history entry j (= filt[j*K]) of this lane's block
+  auto ck = [&](int j, int k) -> i64 { return ((i64)(j - 1) * NSTATE + k) * ldb + idx; };
+
+  // forward sweep with one checkpoint per segment
+  {
+    int to_ckpt = K, j = 0;
+    for (int n = 0; n < N; ++n) {
+      f.step(a, q, idx, n);
+      if (--to_ckpt == 0) {
+        to_ckpt = K; ++j;
+        if (live && n + 1 < N) {
+          RD_UNROLL for (int i = 0; i < P; ++i) stash[ck(j, L::km(b, i))] = f.mu[i];
+          RD_UNROLL for (int k = 0; k < NS; ++k) stash[ck(j, L::kv(b, k))] = f.S[k];
+        }
+      }
+    }
+  }
+  // smoothed[N] = filt[N]   (solve.py:279-282)
+  T ms[P], Ss[NS];
+  RD_UNROLL for (int i = 0; i < P; ++i) ms[i] = f.mu[i];
+  RD_UNROLL for (int k = 0; k < NS; ++k) Ss[k] = f.S[k];
+  if (live && mean_out != nullptr)
+    RD_UNROLL for (int i = 0; i < P; ++i) mean_out[(idx * (i64)(N + 1) + N) * (NB * P) + b * P + i] = ms[i];
+  if (live && var_out != nullptr)
+    RD_UNROLL for (int i = 0; i < P; ++i)
+      RD_UNROLL for (int jj = 0; jj < P; ++jj)
+        var_out[(idx * (i64)(N + 1) + N) * (NB * P * P) + (b * P + i) * P + jj] = Ss[sym<P>(i, jj)];
+
+  const int nth = (a.B - theta0) < TW ? (int)(a.B - theta0) : TW;
+  for (int j = (N - 1) / K; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;          // rows n0 .. n0+cnt-1  (all <= N-1)
+    if (j == 0) {
+      f.init(x0);                                           // filt[0] = (ode_init, 0)
+    } else {
+      RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = stash[ck(j, L::km(b, i))];
+      RD_UNROLL for (int k = 0; k < NS; ++k) f.S[k] = stash[ck(j, L::kv(b, k))];
+    }
+    put(0, f.mu, f.S);
+    for (int s = 1; s < cnt; ++s) {
+      f.step(a, q, idx, n0 + s - 1);
+      put(s, f.mu, f.S);
+    }
+    for (int s = cnt - 1; s >= 0; --s) {
+      if (n0 + s == 0) break;                              // row 0 stays (ode_init, 0): never smoothed
+      get(s, f.mu, f.S);                                   // filt[n]
+      T mp[P], Sp[NS], G[P][P], Ct[P][P];
+      predict<T, P, QK>(f.Q, f.R, f.rs, f.mu, f.S, mp, Sp);               // pred[n+1]
+      smooth_gain<T, P, QK>(f.Q, f.S, Sp, G, Ct);
+      T dm[P], D[NS];
+      RD_UNROLL for (int i = 0; i < P; ++i) dm[i] = ms[i] - mp[i];
+      RD_UNROLL for (int k = 0; k < NS; ++k) D[k] = Ss[k] - Sp[k];
+      RD_UNROLL for (int i = 0; i < P; ++i) {
+        T m = f.mu[i];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) m = rd_fma(G[i][jj], dm[jj], m);
+        ms[i] = m;
+      }
+      RD_UNROLL for (int k = 0; k < NS; ++k) Ss[k] = f.S[k];
+      add_GDGt<T, P>(G, D, Ss);
+      put(s, ms, Ss);                                      // stage the output row in place of filt[n]
+    }
+    if (j > 1) {                                           // next segment's checkpoint travels during the copy-out
+      RD_UNROLL for (int i = 0; i < P; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(stash + ck(j - 1, L::km(b, i))));
+      RD_UNROLL for (int k = 0; k < NS; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(stash + ck(j - 1, L::kv(b, k))));
+    }
+    __syncwarp();
+    if (mean_out != nullptr) seg_copy_out<T, NB, P, K, PITCH, false>(buf, lane, mean_out, theta0, nth, N + 1, n0, cnt);
+    if (var_out != nullptr) seg_copy_out<T, NB, P, K, PITCH, true>(buf, lane, var_out, theta0, nth, N + 1, n0, cnt);
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // solve_sim: forward filter, then the sampling smoother  (reference src/rodeo/solve.py:125-205)
 // ------------------------------------------------------------------------------------------------------------------
