@@ -21,11 +21,20 @@ struct SolveSimRun {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
-    constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
-    RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<real_t, Model, INTERR, QK>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    solve_sim_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, z_smooth, stash,
-                                                                                stash_ldb(p.B), x_out);
+    if constexpr (Model::NB >= 2) {
+      typedef BlockLane<real_t, Model, INTERR, QK> L;
+      constexpr int SMEM = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
+      RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_bl_kernel<real_t, Model, INTERR, QK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      solve_sim_bl_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, L::TW), 32, SMEM, s>>>(
+          C, a, z_smooth, stash, stash_ldb(p.B), x_out);
+    } else {
+      constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
+      RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<real_t, Model, INTERR, QK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      solve_sim_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, z_smooth, stash,
+                                                                                  stash_ldb(p.B), x_out);
+    }
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;

@@ -901,6 +901,153 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// solve_sim with one lane per (theta, block)
+// ------------------------------------------------------------------------------------------------------------------
+// Same lane mapping as solve_mv_bl_kernel.  The sampling smoother is FP64-bound (three reciprocals, a 3x3 factor and
+// the Box-Muller normals per block-step) and its batches are smaller (C5: 32,768 particles per GPU = 1.7 one-theta
+// warps per SM sub-partition), so spreading the blocks over lanes is mainly about parallelism.  Every filtered state
+// is kept in HBM (per-lane loads are 9 doubles, prefetched one step ahead in registers); shared memory only stages
+// the draws so that they leave as runs of K time rows per theta.
+
+// normals first .. first+COUNT-1 of the (theta, step, tag) stream (pairs g/2, component g&1), `first` a run-time value
+template <typename T, int COUNT>
+RD_DEV void philox_normal_range(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, int first,
+                                T (&z)[COUNT]) {
+  constexpr int NPAIR = COUNT / 2 + 1;
+  Philox ph{key0, key1};
+  T pr[2 * NPAIR];
+  const int p0 = first >> 1;
+  RD_UNROLL for (int k = 0; k < NPAIR; ++k) {
+    unsigned r[4];
+    ph((unsigned)particle, (unsigned)((unsigned long long)particle >> 32), (unsigned)step, tag + (unsigned)(p0 + k), r);
+    normal_pair(r, pr[2 * k], pr[2 * k + 1]);
+  }
+  const bool odd = (first & 1) != 0;
+  RD_UNROLL for (int k = 0; k < COUNT; ++k) z[k] = odd ? pr[k + 1] : pr[k];
+}
+
+template <typename T, class Model, int INTERR, int QK>
+__global__ void __launch_bounds__(32)
+solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                    const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
+                    T* __restrict__ x_out) {
+  typedef BlockLane<T, Model, INTERR, QK> L;
+  constexpr int NB = L::NB, P = L::P, NS = L::NS, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
+  constexpr int K = 16, ROW = NB * P;                    // staged time rows: K * ROW * PITCH elements per warp
+  const int lane = threadIdx.x;
+  int tl = lane / NB, b = lane - tl * NB;
+  const bool lane_ok = tl < TW;
+  if (!lane_ok) { tl = TW - 1; b = NB - 1; }
+  const i64 theta0 = (i64)blockIdx.x * TW;
+  i64 idx = theta0 + tl;
+  const bool live = lane_ok && idx < a.B;
+  if (idx >= a.B) idx = a.B - 1;
+  const typename L::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const int N = a.n_steps;
+  T* buf = reinterpret_cast<T*>(rodeo_dyn_smem);
+  L f;
+  f.b = b; f.gb = tl * NB;
+  f.load_consts(C);
+  f.rs = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
+  const T* x0 = a.ode_init + idx * NB * P;
+  f.init(x0);
+  // history entry n (= filt[n], 1 <= n <= N-1) of this lane's block
+  auto hs = [&](int n, int k) -> i64 { return ((i64)(n - 1) * NSTATE + k) * ldb + idx; };
+
+  for (int n = 0; n < N; ++n) {
+    f.step(a, q, idx, n);
+    if (live && n + 1 < N) {
+      RD_UNROLL for (int i = 0; i < P; ++i) stash[hs(n + 1, L::km(b, i))] = f.mu[i];
+      RD_UNROLL for (int k = 0; k < NS; ++k) stash[hs(n + 1, L::kv(b, k))] = f.S[k];
+    }
+  }
+
+  auto normals = [&](int n, T (&z)[P]) {
+    if (z_smooth != nullptr) {
+      const T* zp = z_smooth + (idx * (i64)(N + 1) + n) * (NB * P) + b * P;
+      RD_UNROLL for (int k = 0; k < P; ++k) z[k] = zp[k];
+    } else {
+      philox_normal_range<T, P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, b * P, z);
+    }
+  };
+  auto draw = [&](const T (&m)[P], const T (&Cv)[NS], const T (&z)[P], T (&xo)[P]) {
+    T A[P][P];
+    psd_factor<T, P>(Cv, A);
+    RD_UNROLL for (int i = 0; i < P; ++i) {
+      T acc = m[i];
+      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma(A[i][k], z[k], acc);
+      xo[i] = acc;
+    }
+  };
+
+  // terminal draw from N(mu_f[N], S_f[N])  (solve.py:182-186)
+  T x[P];
+  {
+    T z[P], xn[P];
+    normals(N, z);
+    draw(f.mu, f.S, z, xn);
+    RD_UNROLL for (int i = 0; i < P; ++i) x[i] = xn[i];
+    if (live) RD_UNROLL for (int i = 0; i < P; ++i) x_out[(idx * (i64)(N + 1) + N) * ROW + b * P + i] = x[i];
+  }
+
+  const int nth = (a.B - theta0) < TW ? (int)(a.B - theta0) : TW;
+  // software pipeline: filt[n-1] is loaded into registers while row n is being processed
+  T nmu[P], nS[NS];
+  auto load = [&](int n) {
+    if (n >= 1) {
+      RD_UNROLL for (int i = 0; i < P; ++i) nmu[i] = stash[hs(n, L::km(b, i))];
+      RD_UNROLL for (int k = 0; k < NS; ++k) nS[k] = stash[hs(n, L::kv(b, k))];
+    }
+  };
+  load(N - 1);
+  for (int j = (N - 1) / K; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;
+    for (int s = cnt - 1; s >= 0; --s) {
+      const int n = n0 + s;
+      if (n == 0) {                                        // row 0 = ode_init: x0 is known, not sampled
+        RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * ROW + b * P + i) * PITCH + tl] = x0[b * P + i];
+        break;
+      }
+      RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = nmu[i];
+      RD_UNROLL for (int k = 0; k < NS; ++k) f.S[k] = nS[k];
+      load(n - 1);
+      T z[P], xn[P];
+      normals(n, z);
+      T mp[P], Sp[NS], G[P][P], Ct[P][P], m[P], Cv[NS];
+      predict<T, P, QK>(f.Q, f.R, f.rs, f.mu, f.S, mp, Sp);               // pred[n+1]
+      smooth_gain<T, P, QK>(f.Q, f.S, Sp, G, Ct);
+      // m = mu_f + G (x' - mu_p) ;  C = S_f - G (S_f Q^T)^T      (standard.py:251-254)
+      RD_UNROLL for (int i = 0; i < P; ++i) {
+        T acc = f.mu[i];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma(G[i][jj], x[jj] - mp[jj], acc);
+        m[i] = acc;
+      }
+      cond_var<T, P>(f.S, G, Ct, Cv);
+      draw(m, Cv, z, xn);
+      RD_UNROLL for (int i = 0; i < P; ++i) { x[i] = xn[i]; buf[(s * ROW + b * P + i) * PITCH + tl] = xn[i]; }
+    }
+    __syncwarp();
+    {
+      // copy rows n0 .. n0+cnt-1: per theta one contiguous run of cnt*ROW elements
+      constexpr int NIT = (K * ROW + 31) / 32;
+      const int run = cnt * ROW;
+      const i64 stride = (i64)(N + 1) * ROW;
+      T* dst = x_out + (theta0 * (i64)(N + 1) + n0) * ROW + lane;
+      RD_UNROLL4 for (int th = 0; th < nth; ++th) {
+        RD_UNROLL for (int it = 0; it < NIT; ++it) {
+          const int r = lane + 32 * it;
+          if (r < run) dst[32 * it] = buf[r * PITCH + th];
+        }
+        dst += stride;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // solve_sim: forward filter, then the sampling smoother  (reference src/rodeo/solve.py:125-205)
 // ------------------------------------------------------------------------------------------------------------------

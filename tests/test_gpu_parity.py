@@ -488,3 +488,53 @@ def test_theta_dependent_prior_scale(rb):
         bad = Rb.copy(); bad[3, 0, 0, 1] *= 1.5
         rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(Q, bad),
                     theta=pr["theta"])
+
+
+# ---- ragged batch sizes and out-of-bounds canaries (compute-sanitizer is closed on this pool) -----------------------------
+@pytest.mark.parametrize("B", [1, 5, 33, 47])
+def test_ragged_batches_and_output_canaries(rb, B):
+    """Batch sizes that are not multiples of the warp's theta count: results must equal the corresponding rows of a
+    larger batch, and nothing may be written outside the output / workspace buffers (guard words on both sides)."""
+    import ctypes
+    import torch
+    from rodeo_b200 import _host, _lib
+    N, tm = 37, 2.0                                         # N not a multiple of any segment length
+    big = P.fitz_problem(64, n_steps=N, t_max=tm, seed=51)
+    kr = rb.interrogate.interrogate_kramer
+    ref_m, ref_v = rb.solve_mv(None, rb.models.fitzhugh_nagumo, big["W"], big["X0"], 0.0, tm, N, kr,
+                               prior_pars=(big["Q"], big["R"]), theta=big["theta"])
+    pb = _host.Problem(None, rb.models.fitzhugh_nagumo, big["W"], big["X0"][:B], 0.0, tm, N, kr,
+                       (big["Q"], big["R"]), None, None, "standard", {"theta": big["theta"][:B]})
+    G, SENT = 4096, -777.25
+
+    def guarded(n):
+        t = torch.full((n + 2 * G,), SENT, dtype=torch.float64, device="cuda")
+        return t, t[G:G + n]
+
+    nm, nv = B * (N + 1) * 6, B * (N + 1) * 18
+    wsb = pb.lib.rodeo_b200_workspace_bytes(_lib.OP_SOLVE_MV, ctypes.byref(pb.c), 8)
+    (gm, m), (gv, v), (gw, w) = guarded(nm), guarded(nv), guarded(max(wsb // 8, 1))
+    rc = pb.fn("solve_mv")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R), _host.ptr(pb.x0),
+                           _host.ptr(pb.theta), None, _host.ptr(m), _host.ptr(v), _host.ptr(w), wsb, pb.stream())
+    _lib.check(rc, "solve_mv")
+    torch.cuda.synchronize()
+    for g, n in ((gm, nm), (gv, nv), (gw, max(wsb // 8, 1))):
+        assert bool((g[:G] == SENT).all()) and bool((g[G + n:] == SENT).all()), "write outside the buffer"
+    assert not bool((m == SENT).any()) and not bool((v == SENT).any()), "output not fully written"
+    assert torch.equal(m.view(B, N + 1, 2, 3), ref_m[:B]) and torch.equal(v.view(B, N + 1, 2, 3, 3), ref_v[:B])
+
+    # solve_sim (injected normals) and the two log-likelihoods on the same ragged batch vs the big batch
+    rng = np.random.default_rng(0)
+    zs = rng.standard_normal((64, N + 1, 2, 3))
+    xs_big = rb.solve_sim(0, rb.models.fitzhugh_nagumo, big["W"], big["X0"], 0.0, tm, N, kr,
+                          prior_pars=(big["Q"], big["R"]), theta=big["theta"], _z_smooth=zs)
+    xs = rb.solve_sim(0, rb.models.fitzhugh_nagumo, big["W"], big["X0"][:B], 0.0, tm, N, kr,
+                      prior_pars=(big["Q"], big["R"]), theta=big["theta"][:B], _z_smooth=zs[:B])
+    assert torch.equal(xs.view(B, N + 1, 2, 3), xs_big[:B])
+    ob = P.fitz_obs(big, None, n_obs=5)
+    for fn in (rb.inference.dalton, rb.inference.fenrir):
+        a = fn(None, rb.models.fitzhugh_nagumo, big["W"], big["X0"], 0.0, tm, N, kr, prior_pars=(big["Q"], big["R"]),
+               theta=big["theta"], **ob)
+        b_ = fn(None, rb.models.fitzhugh_nagumo, big["W"], big["X0"][:B], 0.0, tm, N, kr,
+                prior_pars=(big["Q"], big["R"]), theta=big["theta"][:B], **ob)
+        assert torch.equal(b_.view(B), a[:B])
