@@ -139,6 +139,23 @@ int rodeo_b200_ode_init_pad_f64(const RodeoProblem* prob, double t, const double
                                 double* X0, void* stream);
 
 /*
+ * Data-adaptive solvers rodeo.inference.dalton.solve_mv / solve_sim (src/rodeo/inference/dalton.py:374-545): the
+ * forward filter also conditions on the Gaussian observations.  Same arguments as solve_mv / solve_sim plus the
+ * observation arrays of rodeo_b200_dalton_*; workspace of rodeo_b200_dalton_solve_workspace_bytes_*(op, prob) bytes,
+ * op = RODEO_OP_SOLVE_MV or RODEO_OP_SOLVE_SIM.  float64 only.
+ */
+size_t rodeo_b200_dalton_solve_workspace_bytes_f64(int op, const RodeoProblem* prob);
+int rodeo_b200_dalton_solve_mv_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                                   const double* prior_var, const double* ode_init, const double* theta,
+                                   const double* z_interr, const int32_t* obs_ind, const double* obs_data,
+                                   const double* obs_weight, const double* obs_var, double* mean_out, double* var_out,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+int rodeo_b200_dalton_solve_sim_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                                    const double* prior_var, const double* ode_init, const double* theta,
+                                    const double* z_interr, const double* z_smooth, const int32_t* obs_ind,
+                                    const double* obs_data, const double* obs_weight, const double* obs_var,
+                                    double* x_out, void* workspace, size_t workspace_bytes, void* stream);
+/*
  * float32 instantiations: identical argument lists with `float` buffers (and a `float` time in ode_init_pad).
  * The reference's float width follows jax_enable_x64; its own unit tests run in float32 when tox is not used.
  */

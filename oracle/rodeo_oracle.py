@@ -595,3 +595,77 @@ def dalton(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prio
         lp, m_z, v_z = _forecast_update(mp_z, vp_z, x_meas, mean_meas, W_meas, var_meas)
         logdens_z += lp.sum(axis=1)
     return logdens_zy - logdens_z
+
+
+# ----------------------------------------------------------------------------------------------------
+# data-adaptive solvers  (reference src/rodeo/inference/dalton.py:242-545)
+# ----------------------------------------------------------------------------------------------------
+
+def dalton_solve_filter(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_weight, prior_var,
+                        theta, obs_data, obs_times, obs_weight, obs_var, z_interrogate=None, **ikw):
+    """Forward pass that also conditions on the observations -- reference dalton.py:242-371."""
+    ode_init = np.asarray(ode_init, dtype=np.float64)
+    B, nb, p = ode_init.shape
+    m = ode_weight.shape[1]
+    Q, R = _bq(prior_weight, B), _bq(prior_var, B)
+    obs_data = np.asarray(obs_data, dtype=np.float64)
+    n_obs, _, n_bobs, _ = obs_weight.shape
+    obs_ind = obs_index(t_min, t_max, n_steps, obs_times)
+    x_meas = np.zeros((B, nb, m)); obs_mean = np.zeros((B, nb, n_bobs)); mean_state = np.zeros((B, nb, p))
+    mp = np.zeros((B, n_steps + 1, nb, p)); vp = np.zeros((B, n_steps + 1, nb, p, p))
+    mf = np.zeros((B, n_steps + 1, nb, p)); vf = np.zeros((B, n_steps + 1, nb, p, p))
+    mp[:, 0] = ode_init; mf[:, 0] = ode_init
+    m_f, v_f = ode_init, np.zeros((B, nb, p, p))
+    i = 1 if obs_ind[0] == 0 else 0                      # dalton.py:352
+    for n in range(n_steps):
+        m_p, v_p = predict(m_f, v_f, mean_state, Q, R)
+        z = None if z_interrogate is None else z_interrogate[:, n]
+        wgt_meas, mean_meas, var_meas = interrogate(z, model, ode_weight, _step_time(t_min, t_max, n, n_steps),
+                                                    m_p, v_p, theta, **ikw)
+        W_meas = ode_weight + wgt_meas
+        ic = min(i, n_obs - 1)
+        if n + 1 == obs_ind[ic]:
+            D = np.broadcast_to(obs_weight[ic], (B, nb, n_bobs, p))
+            wgt_obs = np.concatenate([W_meas, D], axis=2)
+            mean_obs = np.concatenate([mean_meas, obs_mean], axis=2)
+            var_obs = np.zeros((B, nb, m + n_bobs, m + n_bobs))
+            var_obs[:, :, :m, :m] = var_meas
+            var_obs[:, :, m:, m:] = obs_var[ic]
+            x_obs = np.concatenate([x_meas, np.broadcast_to(obs_data[ic], (B, nb, n_bobs))], axis=2)
+            m_f, v_f = update(m_p, v_p, x_obs, mean_obs, wgt_obs, var_obs)
+            i += 1
+        else:
+            m_f, v_f = update(m_p, v_p, x_meas, mean_meas, W_meas, var_meas)
+        mp[:, n + 1], vp[:, n + 1], mf[:, n + 1], vf[:, n + 1] = m_p, v_p, m_f, v_f
+    return mp, vp, mf, vf
+
+
+def dalton_solve_mv(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars, theta,
+                    obs_data, obs_times, obs_weight, obs_var, **kw):
+    """reference dalton.py:374-460 (same backward pass as solve_mv)"""
+    Qs, Rs = prior_pars
+    mp, vp, mf, vf = dalton_solve_filter(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, Qs, Rs,
+                                         theta, obs_data, obs_times, obs_weight, obs_var, **kw)
+    Q = _bq(Qs, mf.shape[0])
+    ms = np.zeros_like(mf); vs = np.zeros_like(vf)
+    ms[:, 0] = ode_init
+    ms[:, n_steps], vs[:, n_steps] = mf[:, n_steps], vf[:, n_steps]
+    for t in range(n_steps - 1, 0, -1):
+        ms[:, t], vs[:, t] = smooth_mv(ms[:, t + 1], vs[:, t + 1], mf[:, t], vf[:, t], mp[:, t + 1], vp[:, t + 1], Q)
+    return ms, vs
+
+
+def dalton_solve_sim(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars, theta,
+                     obs_data, obs_times, obs_weight, obs_var, z_smooth, factor="svd", **kw):
+    """reference dalton.py:463-545 (same backward pass as solve_sim)"""
+    Qs, Rs = prior_pars
+    mp, vp, mf, vf = dalton_solve_filter(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, Qs, Rs,
+                                         theta, obs_data, obs_times, obs_weight, obs_var, **kw)
+    Q = _bq(Qs, mf.shape[0])
+    xs = np.zeros_like(mf)
+    xs[:, 0] = ode_init
+    xs[:, n_steps] = mf[:, n_steps] + _mv(psd_factor(vf[:, n_steps], factor), z_smooth[:, n_steps])
+    for t in range(n_steps - 1, 0, -1):
+        m_sim, v_sim = smooth_sim(xs[:, t + 1], mf[:, t], vf[:, t], mp[:, t + 1], vp[:, t + 1], Q)
+        xs[:, t] = m_sim + _mv(psd_factor(v_sim, factor), z_smooth[:, t])
+    return xs

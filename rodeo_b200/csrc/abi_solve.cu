@@ -67,9 +67,10 @@ extern "C" int RODEO_FN(rodeo_b200_solve_mv)(const RodeoProblem* p, const real_t
     if (sizeof(real_t) != 8) { set_error("user (NVRTC) models are float64 only"); return RODEO_ERR_UNSUPPORTED; }
     real_t* stash = (real_t*)workspace;
     long long ldb = stash_ldb(p->B);
+    ObsHook<real_t> no_obs{};        // trailing kernel parameter of the solver kernels (unused: OBS = false)
     const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * (int)sizeof(real_t);
     return user_launch(*p, "solve_mv_kernel", "", (const double*)ode_weight, (const double*)prior_weight, (const double*)prior_var, p->user_wcol, p->B, smem,
-                       {&a, &stash, &ldb, &mean_out, &var_out}, (cudaStream_t)stream);
+                       {&a, &stash, &ldb, &mean_out, &var_out, &no_obs}, (cudaStream_t)stream);
   }
   return dispatch_model<SolveMvRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, (real_t*)workspace,
                                     mean_out, var_out, (cudaStream_t)stream);

@@ -21,14 +21,19 @@ struct SolveSimRun {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
-    if constexpr (Model::NB >= 2) {
+    // (theta, block) lanes buy parallelism at the price of redundant right-hand-side / Philox work per lane: worth it
+    // only while one-theta warps cannot fill the SM sub-partitions (fewer than ~3 warps on each of the 592)
+    bool block_lanes = false;
+    if constexpr (Model::NB >= 2) block_lanes = (p.B + 31) / 32 < 1776;
+    if constexpr (Model::NB >= 2) if (block_lanes) {
       typedef BlockLane<real_t, Model, INTERR, QK> L;
       constexpr int SMEM = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
       RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_bl_kernel<real_t, Model, INTERR, QK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       solve_sim_bl_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, L::TW), 32, SMEM, s>>>(
           C, a, z_smooth, stash, stash_ldb(p.B), x_out);
-    } else {
+    }
+    if (!block_lanes) {
       constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
       RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<real_t, Model, INTERR, QK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -67,9 +72,10 @@ extern "C" int RODEO_FN(rodeo_b200_solve_sim)(const RodeoProblem* p, const real_
     if (sizeof(real_t) != 8) { set_error("user (NVRTC) models are float64 only"); return RODEO_ERR_UNSUPPORTED; }
     real_t* stash = (real_t*)workspace;
     long long ldb = stash_ldb(p->B);
+    ObsHook<real_t> no_obs{};        // trailing kernel parameter of the solver kernels (unused: OBS = false)
     const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * (int)sizeof(real_t);
     return user_launch(*p, "solve_sim_kernel", "", (const double*)ode_weight, (const double*)prior_weight, (const double*)prior_var, p->user_wcol, p->B, smem,
-                       {&a, &z_smooth, &stash, &ldb, &x_out}, (cudaStream_t)stream);
+                       {&a, &z_smooth, &stash, &ldb, &x_out, &no_obs}, (cudaStream_t)stream);
   }
   return dispatch_model<SolveSimRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
                                      (real_t*)workspace, x_out, (cudaStream_t)stream);

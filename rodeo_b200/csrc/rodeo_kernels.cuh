@@ -45,6 +45,28 @@ struct ObsArgs {
   const T* obs_var;       // (n_obs, NB, NOBS, NOBS)
 };
 
+// Data-adaptive solvers (reference src/rodeo/inference/dalton.py:242-545): the forward filter of solve_mv / solve_sim
+// additionally conditions on the Gaussian observations, i.e. step n uses the augmented update of dalton.zy_update
+// when step_obs[n] >= 0 (the observation index the reference's pointer walk would use at that step, precomputed by
+// obs_step_map_kernel because the backward sweeps re-run forward steps out of order).
+template <typename T>
+struct ObsHook {
+  ObsArgs<T> o;
+  const int* step_obs;   // (n_steps) or nullptr
+};
+
+// step_obs[n] = i if the reference's scan (dalton.py:313-350) applies observation i at step n (t+1 == obs_ind[i],
+// i clamped, starting at 1 when obs_ind[0] == 0), else -1
+template <int UNUSED = 0>
+__global__ void obs_step_map_kernel(int n_steps, int n_obs, const int* __restrict__ obs_ind, int* __restrict__ map) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int i = (obs_ind[0] == 0) ? 1 : 0;
+  for (int n = 0; n < n_steps; ++n) {
+    const int ic = i < n_obs ? i : n_obs - 1;
+    if (n + 1 == obs_ind[ic]) { map[n] = ic; ++i; } else map[n] = -1;
+  }
+}
+
 // reference src/rodeo/solve.py:74: t = t_min + (t_max - t_min) * (n + 1) / n_steps
 template <typename T>
 RD_DEV T step_time(T t_min, T t_max, int n, int n_steps) {
@@ -65,6 +87,23 @@ RD_DEV void philox_normals(unsigned key0, unsigned key1, i64 particle, int step,
     z[k] = a;
     if (k + 1 < COUNT) z[k + 1] = b;
   }
+}
+
+// normals first .. first+COUNT-1 of the (theta, step, tag) stream (pairs g/2, component g&1), `first` a run-time value
+template <typename T, int COUNT>
+RD_DEV void philox_normal_range(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, int first,
+                                T (&z)[COUNT]) {
+  constexpr int NPAIR = COUNT / 2 + 1;
+  Philox ph{key0, key1};
+  T pr[2 * NPAIR];
+  const int p0 = first >> 1;
+  RD_UNROLL for (int k = 0; k < NPAIR; ++k) {
+    unsigned r[4];
+    ph((unsigned)particle, (unsigned)((unsigned long long)particle >> 32), (unsigned)step, tag + (unsigned)(p0 + k), r);
+    normal_pair(r, pr[2 * k], pr[2 * k + 1]);
+  }
+  const bool odd = (first & 1) != 0;
+  RD_UNROLL for (int k = 0; k < COUNT; ++k) z[k] = odd ? pr[k + 1] : pr[k];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -463,10 +502,11 @@ RD_DEV void ckpt_prefetch(const T* __restrict__ stash, i64 ldb, i64 idx, int j) 
   RD_UNROLL for (int k = 0; k < NSTATE; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(s + (i64)k * ldb));
 }
 
-// one forward step n -> n+1 of a plain (no log-density) filter
+// one forward step n -> n+1 of a plain (no log-density) filter; `hook` adds the observation rows at observation steps
 template <typename T, class Model, int INTERR, int QK>
 RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
-                         const typename Model::template Par<T>& q, i64 idx, int n, Fwd<T, Model, INTERR, QK>& f) {
+                         const typename Model::template Par<T>& q, i64 idx, int n, Fwd<T, Model, INTERR, QK>& f,
+                         const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
   constexpr int NB = F::NB, M = F::M, JC = F::JC, MS = F::MS;
   LogPdfAcc<T> dummy;
@@ -475,7 +515,10 @@ RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C
   f.predict_all(C);
   f.template interr_normals<1>(a, idx, n, 0, zc);
   f.interrogate(C, q, t, zc, jl, res, V);
-  f.template update_z<false>(C, jl, res, V, dummy);
+  int io = -1;
+  if (hook != nullptr) io = __ldg(hook->step_obs + n);
+  if (io >= 0) f.template update_zy<1, false>(C, jl, res, V, hook->o, io, dummy);
+  else f.template update_z<false>(C, jl, res, V, dummy);
 }
 
 // forward sweep 0 -> N storing filt[n] for every n that is a multiple of KC (history entry n / KC); on exit f holds
@@ -483,11 +526,12 @@ RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C
 template <typename T, class Model, int INTERR, int QK, int KC>
 RD_DEV void forward_with_checkpoints(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
                                      const typename Model::template Par<T>& q, i64 idx, bool live,
-                                     Fwd<T, Model, INTERR, QK>& f, T* __restrict__ stash, i64 ldb) {
+                                     Fwd<T, Model, INTERR, QK>& f, T* __restrict__ stash, i64 ldb,
+                                     const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
   int to_ckpt = KC, j = 0;
   for (int n = 0; n < a.n_steps; ++n) {
-    forward_step<T, Model, INTERR, QK>(C, a, q, idx, n, f);
+    forward_step<T, Model, INTERR, QK>(C, a, q, idx, n, f, hook);
     if (--to_ckpt == 0) {
       to_ckpt = KC;
       ++j;
@@ -503,7 +547,7 @@ template <typename T, class Model, int INTERR, int QK, int KC>
 RD_DEV void rebuild_segment(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
                             const typename Model::template Par<T>& q, i64 idx, int j, int cnt,
                             Fwd<T, Model, INTERR, QK>& f, const T* __restrict__ stash, i64 ldb,
-                            SegBuf<T, Fwd<T, Model, INTERR, QK>>& buf) {
+                            SegBuf<T, Fwd<T, Model, INTERR, QK>>& buf, const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
   constexpr int NB = F::NB, P = F::P, K = SegBuf<T, F>::K;
   if constexpr (KC == 1) {
@@ -518,7 +562,7 @@ RD_DEV void rebuild_segment(const FilterConsts<T, Model::NB, Model::P, Model::M>
     else ckpt_load<T, F>(stash, ldb, idx, j, f);
     buf.put(0, f.mu, f.S);
     for (int s = 1; s < cnt; ++s) {
-      forward_step<T, Model, INTERR, QK>(C, a, q, idx, j * K + s - 1, f);
+      forward_step<T, Model, INTERR, QK>(C, a, q, idx, j * K + s - 1, f, hook);
       buf.put(s, f.mu, f.S);
     }
   }
@@ -553,11 +597,12 @@ extern __shared__ double rodeo_dyn_smem[];
 // ------------------------------------------------------------------------------------------------------------------
 // solve_mv: forward filter, then the mean/variance smoother  (reference src/rodeo/solve.py:208-302)
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T, class Model, int INTERR, int QK>
+template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32)
 solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                 const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
-                T* __restrict__ mean_out, T* __restrict__ var_out) {
+                T* __restrict__ mean_out, T* __restrict__ var_out, const ObsHook<T> oh = ObsHook<T>()) {
+  const ObsHook<T>* hook = OBS ? &oh : nullptr;
   typedef Fwd<T, Model, INTERR, QK> F;
   typedef SegBuf<T, F> Buf;
   constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
@@ -571,7 +616,7 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   F f;
   f.init(a.ode_init + idx * NB * P);
   f.load_scale(a, idx);
-  forward_with_checkpoints<T, Model, INTERR, QK, K>(C, a, q, idx, live, f, stash, ldb);
+  forward_with_checkpoints<T, Model, INTERR, QK, K>(C, a, q, idx, live, f, stash, ldb, hook);
 
   // smoothed[N] = filt[N]   (solve.py:279-282)
   T ms[NB][P], Ss[NB][NS];
@@ -586,7 +631,7 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   for (int j = (N - 1) / K; j >= 0; --j) {
     const int n0 = j * K;
     const int cnt = (N - n0) < K ? (N - n0) : K;          // rows n0 .. n0+cnt-1  (all <= N-1)
-    rebuild_segment<T, Model, INTERR, QK, K>(C, a, q, idx, j, cnt, f, stash, ldb, buf);
+    rebuild_segment<T, Model, INTERR, QK, K>(C, a, q, idx, j, cnt, f, stash, ldb, buf, hook);
     for (int s = cnt - 1; s >= 0; --s) {
       if (n0 + s == 0) break;                              // row 0 stays (ode_init, 0): never smoothed (solve.py:295-301)
       buf.get(s, f.mu, f.S);                               // filt[n]
@@ -674,7 +719,7 @@ struct BlockLane {
   RD_DEV static int kv(int bb, int k) { return NB * P + bb * NS + k; }
 
   // one forward step n -> n+1 of this lane's block (predict, interrogate, update); all 32 lanes must call it
-  RD_DEV void step(const CommonArgs<T>& a, const Par& q, i64 idx, int n) {
+  RD_DEV void step(const CommonArgs<T>& a, const Par& q, i64 idx, int n, const ObsHook<T>* hook = nullptr) {
     {
       T mp[P], Sp[NS];
       predict<T, P, QK>(Q, R, rs, mu, S, mp, Sp);
@@ -689,14 +734,9 @@ struct BlockLane {
         const T* z = a.z_interr + (idx * a.n_steps + n) * (NB * P) + b * P;
         RD_UNROLL for (int j = 0; j < JC; ++j) zc[j] = z[j];
       } else {
-        // the same stream layout as the thread-per-theta kernels: normal k = b*JC + j of the step's vector
-        T z[NB * JC];
-        philox_normals<T, NB * JC>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, z);
-        RD_UNROLL for (int j = 0; j < JC; ++j) {
-          T v = z[j];
-          RD_UNROLL for (int c = 1; c < NB; ++c) v = (b == c) ? z[c * JC + j] : v;
-          zc[j] = v;
-        }
+        // the same stream layout as the thread-per-theta kernels: normal k = b*JC + j of the step's vector; only
+        // the Philox pair(s) that hold this block's normals are generated
+        philox_normal_range<T, JC>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, b * JC, zc);
       }
       T A[P][P];
       psd_factor<T, P>(S, A);
@@ -731,7 +771,36 @@ struct BlockLane {
       }
     }
     LogPdfAcc<T> dummy;
-    if constexpr (UNITW) {
+    int io = -1;
+    if (hook != nullptr) io = __ldg(hook->step_obs + n);
+    if (io >= 0) {
+      // augmented update with the observation rows of this block (dalton.py:136-149), scalar ODE row + one obs row
+      if constexpr (M == 1) {
+        T wa[2][P], ra[2], Va[3];
+        T acc = fo[0], ya = __ldg(hook->o.obs_data + (io * NB + b));
+        RD_UNROLL for (int j = 0; j < P; ++j) {
+          const T w = UNITW ? (j == WK ? T(1) : T(0)) : W[0][j];
+          wa[0][j] = (HAS_J && j < JC) ? w - jo[0][j] : w;
+          acc = rd_fma(-w, mu[j], acc);
+          wa[1][j] = __ldg(hook->o.obs_weight + (io * NB + b) * P + j);
+          ya = rd_fma(-wa[1][j], mu[j], ya);
+        }
+        ra[0] = acc; ra[1] = ya;
+        T V0 = T(0);
+        if constexpr (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) {
+          if (UNITW) V0 = S[sidx<P>(WK, WK)];
+          else {
+            RD_UNROLL for (int i = 0; i < P; ++i) {
+              T u = T(0);
+              RD_UNROLL for (int j = 0; j < P; ++j) u = rd_fma(S[sym<P>(i, j)], W[0][j], u);
+              V0 = rd_fma(W[0][i], u, V0);
+            }
+          }
+        }
+        Va[0] = V0; Va[1] = T(0); Va[2] = __ldg(hook->o.obs_var + (io * NB + b));
+        update<T, P, 2, false>(mu, S, wa, ra, Va, dummy);
+      }
+    } else if constexpr (UNITW) {
       const T res = fo[0] - mu[WK];
       const T V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) ? S[sidx<P>(WK, WK)] : T(0);
       update_unit_row<T, P, JC, WK, false, HAS_J>(mu, S, jo[0], res, V, dummy);
@@ -797,11 +866,12 @@ RD_DEV void seg_copy_out(const T* __restrict__ base, int lane, T* __restrict__ o
   }
 }
 
-template <typename T, class Model, int INTERR, int QK>
+template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32)
 solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                    const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
-                   T* __restrict__ mean_out, T* __restrict__ var_out) {
+                   T* __restrict__ mean_out, T* __restrict__ var_out, const ObsHook<T> oh = ObsHook<T>()) {
+  const ObsHook<T>* hook = OBS ? &oh : nullptr;
   typedef BlockLane<T, Model, INTERR, QK> L;
   constexpr int NB = L::NB, P = L::P, NS = L::NS, K = L::K, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
   const int lane = threadIdx.x;
@@ -836,7 +906,7 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   {
     int to_ckpt = K, j = 0;
     for (int n = 0; n < N; ++n) {
-      f.step(a, q, idx, n);
+      f.step(a, q, idx, n, hook);
       if (--to_ckpt == 0) {
         to_ckpt = K; ++j;
         if (live && n + 1 < N) {
@@ -869,7 +939,7 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
     }
     put(0, f.mu, f.S);
     for (int s = 1; s < cnt; ++s) {
-      f.step(a, q, idx, n0 + s - 1);
+      f.step(a, q, idx, n0 + s - 1, hook);
       put(s, f.mu, f.S);
     }
     for (int s = cnt - 1; s >= 0; --s) {
@@ -911,28 +981,12 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
 // is kept in HBM (per-lane loads are 9 doubles, prefetched one step ahead in registers); shared memory only stages
 // the draws so that they leave as runs of K time rows per theta.
 
-// normals first .. first+COUNT-1 of the (theta, step, tag) stream (pairs g/2, component g&1), `first` a run-time value
-template <typename T, int COUNT>
-RD_DEV void philox_normal_range(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, int first,
-                                T (&z)[COUNT]) {
-  constexpr int NPAIR = COUNT / 2 + 1;
-  Philox ph{key0, key1};
-  T pr[2 * NPAIR];
-  const int p0 = first >> 1;
-  RD_UNROLL for (int k = 0; k < NPAIR; ++k) {
-    unsigned r[4];
-    ph((unsigned)particle, (unsigned)((unsigned long long)particle >> 32), (unsigned)step, tag + (unsigned)(p0 + k), r);
-    normal_pair(r, pr[2 * k], pr[2 * k + 1]);
-  }
-  const bool odd = (first & 1) != 0;
-  RD_UNROLL for (int k = 0; k < COUNT; ++k) z[k] = odd ? pr[k + 1] : pr[k];
-}
-
-template <typename T, class Model, int INTERR, int QK>
+template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32)
 solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                     const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
-                    T* __restrict__ x_out) {
+                    T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>()) {
+  const ObsHook<T>* hook = OBS ? &oh : nullptr;
   typedef BlockLane<T, Model, INTERR, QK> L;
   constexpr int NB = L::NB, P = L::P, NS = L::NS, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
   constexpr int K = 16, ROW = NB * P;                    // staged time rows: K * ROW * PITCH elements per warp
@@ -957,7 +1011,7 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
   auto hs = [&](int n, int k) -> i64 { return ((i64)(n - 1) * NSTATE + k) * ldb + idx; };
 
   for (int n = 0; n < N; ++n) {
-    f.step(a, q, idx, n);
+    f.step(a, q, idx, n, hook);
     if (live && n + 1 < N) {
       RD_UNROLL for (int i = 0; i < P; ++i) stash[hs(n + 1, L::km(b, i))] = f.mu[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) stash[hs(n + 1, L::kv(b, k))] = f.S[k];
@@ -1053,11 +1107,12 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
 // ------------------------------------------------------------------------------------------------------------------
 // z_smooth: optional injected normals (B, N+1, NB, P); row N feeds the terminal draw, rows 1..N-1 the backward
 // draws.  Without it the draws come from Philox keyed by (key, particle, step).
-template <typename T, class Model, int INTERR, int QK>
+template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32)
 solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                  const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
-                 T* __restrict__ x_out) {
+                 T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>()) {
+  const ObsHook<T>* hook = OBS ? &oh : nullptr;
   typedef Fwd<T, Model, INTERR, QK> F;
   typedef SegBuf<T, F> Buf;
   constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
@@ -1071,7 +1126,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   F f;
   f.init(a.ode_init + idx * NB * P);
   f.load_scale(a, idx);
-  forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
+  forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb, hook);
 
   auto normals = [&](int n, T (&z)[NB * P]) {
     if (z_smooth != nullptr) {

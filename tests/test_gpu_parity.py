@@ -538,3 +538,33 @@ def test_ragged_batches_and_output_canaries(rb, B):
         b_ = fn(None, rb.models.fitzhugh_nagumo, big["W"], big["X0"][:B], 0.0, tm, N, kr,
                 prior_pars=(big["Q"], big["R"]), theta=big["theta"][:B], **ob)
         assert torch.equal(b_.view(B), a[:B])
+
+
+# ---- data-adaptive solvers ---------------------------------------------------------------------------------
+def test_dalton_data_adaptive_solvers(rb):
+    """rodeo.inference.dalton.solve_mv / solve_sim (dalton.py:374-545): observations enter the forward filter."""
+    for name, pr, obf in (("fitzhugh_nagumo", P.fitz_problem(40, n_steps=120, t_max=6.0, seed=61), P.fitz_obs),
+                          ("second_order_sin", P.second_order_problem(24, n_steps=150, t_max=5.0, sigma=1.0, seed=61),
+                           P.second_order_obs)):
+        N, tm = pr["n_steps"], pr["t_max"]
+        ob = obf(pr, None, n_obs=7) if name == "fitzhugh_nagumo" else obf(pr, n_obs=6)
+        mdl, om_ = getattr(rb.models, name), orc.MODELS[name]
+        kr = rb.interrogate.interrogate_kramer
+        m, v = rb.inference.dalton_solve_mv(None, mdl, pr["W"], pr["X0"], 0.0, tm, N, kr, prior_pars=(pr["Q"], pr["R"]),
+                                            theta=pr["theta"], **ob)
+        om, ov = orc.dalton_solve_mv(om_, pr["W"], pr["X0"], 0.0, tm, N, orc.interrogate_kramer, (pr["Q"], pr["R"]),
+                                     pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+        assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(v), ov) < TOL, name
+        # the data must actually matter: differs from the plain solver
+        m0, _ = rb.solve_mv(None, mdl, pr["W"], pr["X0"], 0.0, tm, N, kr, prior_pars=(pr["Q"], pr["R"]),
+                            theta=pr["theta"])
+        if name == "fitzhugh_nagumo":      # (the linear ODE is pinned by its interrogations; data barely move it)
+            assert P.maxnorm_rel(_np(m), _np(m0)) > 1e-6
+        rng = np.random.default_rng(1)
+        zs = rng.standard_normal((pr["X0"].shape[0], N + 1) + pr["X0"].shape[1:])
+        x = rb.inference.dalton_solve_sim(0, mdl, pr["W"], pr["X0"], 0.0, tm, N, kr, prior_pars=(pr["Q"], pr["R"]),
+                                          theta=pr["theta"], _z_smooth=zs, **ob)
+        ox = orc.dalton_solve_sim(om_, pr["W"], pr["X0"], 0.0, tm, N, orc.interrogate_kramer, (pr["Q"], pr["R"]),
+                                  pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"],
+                                  z_smooth=zs, factor="ldl")
+        assert P.maxnorm_rel(_np(x), ox) < 1e-7, name
