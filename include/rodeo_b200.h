@@ -156,6 +156,18 @@ int rodeo_b200_dalton_solve_sim_f64(const RodeoProblem* prob, const double* ode_
                                     const double* obs_data, const double* obs_weight, const double* obs_var,
                                     double* x_out, void* workspace, size_t workspace_bytes, void* stream);
 /*
+ * rodeo.solve_mv with kalman_type="square-root" (src/rodeo/solve.py:236-241 selecting src/rodeo/kalmantv/
+ * square_root.py): prior_var_sqrt is the lower Cholesky factor of R (docs/examples/higher_order.md:108-112) and
+ * var_sqrt_out receives lower-triangular factors L with var = L L^T (only L L^T is comparable across
+ * implementations: QR leaves the signs free).  interrogate_kramer / schober / chkrebtii; float64.
+ */
+size_t rodeo_b200_solve_mv_sqrt_workspace_bytes(const RodeoProblem* prob);
+int rodeo_b200_solve_mv_sqrt_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                                 const double* prior_var_sqrt, const double* ode_init, const double* theta,
+                                 const double* z_interr, double* mean_out, double* var_sqrt_out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+/*
  * float32 instantiations: identical argument lists with `float` buffers (and a `float` time in ode_init_pad).
  * The reference's float width follows jax_enable_x64; its own unit tests run in float32 when tox is not used.
  */

@@ -669,3 +669,106 @@ def dalton_solve_sim(model, ode_weight, ode_init, t_min, t_max, n_steps, interro
         m_sim, v_sim = smooth_sim(xs[:, t + 1], mf[:, t], vf[:, t], mp[:, t + 1], vp[:, t + 1], Q)
         xs[:, t] = m_sim + _mv(psd_factor(v_sim, factor), z_smooth[:, t])
     return xs
+
+
+# ----------------------------------------------------------------------------------------------------
+# square-root Kalman family  (reference src/rodeo/kalmantv/square_root.py, src/rodeo/utils.py:10-24)
+# variances are carried as lower-triangular factors L (var = L L^T); only L L^T is comparable across
+# implementations (QR leaves the signs of R's diagonal free)
+# ----------------------------------------------------------------------------------------------------
+
+def add_sqrt(sqrt_A, sqrt_B):
+    """R^T of qr(vstack([sqrt_A^T, sqrt_B^T])) -- reference src/rodeo/utils.py:10-24; batched over leading axes."""
+    stacked = np.concatenate([_T(sqrt_A), _T(sqrt_B)], axis=-2)
+    R = np.linalg.qr(stacked, mode="r")
+    return _T(R)
+
+
+def _solve_tri(L, B, lower, trans=False):
+    import scipy.linalg
+    L = np.asarray(L); B = np.asarray(B)
+    lead = np.broadcast_shapes(L.shape[:-2], B.shape[:-2])
+    Lb = np.broadcast_to(L, lead + L.shape[-2:]).reshape((-1,) + L.shape[-2:])
+    Bb = np.broadcast_to(B, lead + B.shape[-2:]).reshape((-1,) + B.shape[-2:])
+    out = np.stack([scipy.linalg.solve_triangular(l, b, lower=lower, trans="T" if trans else "N")
+                    for l, b in zip(Lb, Bb)])
+    return out.reshape(lead + B.shape[-2:])
+
+
+def sqrt_predict(mean_state_past, var_state_past, mean_state, wgt_state, var_state):
+    """reference square_root.py:30-59"""
+    return _mv(wgt_state, mean_state_past) + mean_state, add_sqrt(wgt_state @ var_state_past, var_state)
+
+
+def sqrt_update(mean_state_pred, var_state_pred, x_meas, mean_meas, wgt_meas, var_meas):
+    """reference square_root.py:62-103"""
+    mean_meas_pred = _mv(wgt_meas, mean_state_pred) + mean_meas
+    var_meas_meas_pred = add_sqrt(wgt_meas @ var_state_pred, var_meas)
+    inter = _solve_tri(var_meas_meas_pred, wgt_meas, lower=True)
+    inter = inter @ var_state_pred @ _T(var_state_pred)
+    var_state_temp = _T(_solve_tri(_T(var_meas_meas_pred), inter, lower=False))
+    mean_state_filt = mean_state_pred + _mv(var_state_temp, x_meas - mean_meas_pred)
+    var_state_filt = add_sqrt(var_state_pred - (var_state_temp @ wgt_meas) @ var_state_pred,
+                              var_state_temp @ var_meas)
+    return mean_state_filt, var_state_filt
+
+
+def _sqrt_smooth(var_state_filt, var_state_pred, wgt_state):
+    """reference square_root.py:160-178"""
+    variance_state_filt = var_state_filt @ _T(var_state_filt)
+    inter = _solve_tri(var_state_pred, wgt_state, lower=True) @ variance_state_filt
+    return _T(_solve_tri(_T(var_state_pred), inter, lower=False))
+
+
+def sqrt_smooth_mv(mean_state_next, var_state_next, mean_state_filt, var_state_filt, mean_state_pred, var_state_pred,
+                   wgt_state, var_state):
+    """reference square_root.py:181-222"""
+    G = _sqrt_smooth(var_state_filt, var_state_pred, wgt_state)
+    mean_state_smooth = mean_state_filt + _mv(G, mean_state_next - mean_state_pred)
+    J = np.eye(G.shape[-1]) - G @ wgt_state
+    lead = np.broadcast_shapes(var_state_next.shape[:-2], np.asarray(var_state).shape[:-2])
+    hs = np.concatenate([np.broadcast_to(var_state_next, lead + var_state_next.shape[-2:]),
+                         np.broadcast_to(var_state, lead + np.asarray(var_state).shape[-2:])], axis=-1)
+    return mean_state_smooth, add_sqrt(G @ hs, J @ var_state_filt)
+
+
+def interrogate_chkrebtii_sqrt(z, model, ode_weight, t, mean_state_pred, var_state_pred, theta):
+    """reference src/rodeo/interrogate.py:36-47, kalman_type="square-root" branch, restated literally:
+    var_meas = W L (an (m, p) block, not (m, m)) and x_state = mean + var_meas @ z, whose (m,) = (1,) result
+    BROADCASTS over all p state entries of the block."""
+    var_meas = ode_weight @ var_state_pred                               # (B, nb, m, p)
+    shift = np.einsum("bnmp,bnp->bnm", var_meas, z)                     # (B, nb, m)
+    x_state = mean_state_pred + shift[..., :1]                          # m == 1: broadcast over p
+    mean_meas = -model.fun(x_state, t, theta)
+    return np.zeros((mean_state_pred.shape[0],) + ode_weight.shape), mean_meas, var_meas
+
+
+def solve_mv_sqrt(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars, theta,
+                  z_interrogate=None):
+    """solve_mv with kalman_type="square-root" -- reference src/rodeo/solve.py:208-302 with
+    kalman_funs = square_root.  prior_pars = (Q, lower Cholesky factor of R).  Returns (mean, L)."""
+    ode_init = np.asarray(ode_init, dtype=np.float64)
+    B, nb, p = ode_init.shape
+    m = ode_weight.shape[1]
+    Q, Rh = _bq(prior_pars[0], B), _bq(prior_pars[1], B)
+    x_meas = np.zeros((B, nb, m)); mean_state = np.zeros((B, nb, p))
+    N = n_steps
+    mp = np.zeros((B, N + 1, nb, p)); Lp = np.zeros((B, N + 1, nb, p, p))
+    mf = np.zeros((B, N + 1, nb, p)); Lf = np.zeros((B, N + 1, nb, p, p))
+    mp[:, 0] = ode_init; mf[:, 0] = ode_init
+    m_f, l_f = ode_init, np.zeros((B, nb, p, p))
+    for n in range(N):
+        m_p, l_p = sqrt_predict(m_f, l_f, mean_state, Q, Rh)
+        z = None if z_interrogate is None else z_interrogate[:, n]
+        wgt_meas, mean_meas, var_meas = interrogate(z, model, ode_weight, _step_time(t_min, t_max, n, N), m_p, l_p,
+                                                    theta)
+        W_meas = ode_weight + wgt_meas
+        m_f, l_f = sqrt_update(m_p, l_p, x_meas, mean_meas, W_meas, var_meas)
+        mp[:, n + 1], Lp[:, n + 1], mf[:, n + 1], Lf[:, n + 1] = m_p, l_p, m_f, l_f
+    ms = np.zeros_like(mf); Ls = np.zeros_like(Lf)
+    ms[:, 0] = ode_init
+    ms[:, N], Ls[:, N] = mf[:, N], Lf[:, N]
+    for t in range(N - 1, 0, -1):
+        ms[:, t], Ls[:, t] = sqrt_smooth_mv(ms[:, t + 1], Ls[:, t + 1], mf[:, t], Lf[:, t], mp[:, t + 1],
+                                            Lp[:, t + 1], Q, Rh)
+    return ms, Ls

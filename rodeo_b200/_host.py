@@ -87,7 +87,7 @@ def kalman_id(kalman_type):
     if kalman_type == "standard":
         return _lib.KALMAN_STANDARD
     if kalman_type == "square-root":
-        raise NotImplementedError('kalman_type="square-root" is not built yet (SURVEY 8(f1))')
+        return _lib.KALMAN_SQUARE_ROOT
     raise NotImplementedError
 
 

@@ -495,6 +495,165 @@ RD_DEV void cond_var(const T (&Sf)[P * (P + 1) / 2], const T (&G)[P][P], const T
     }
 }
 
+
+// ====================================================================================================================
+// Square-root Kalman family (reference src/rodeo/kalmantv/square_root.py): variances are carried as lower-triangular
+// factors L (var = L L^T), packed row-major: lidx(i, j), j <= i.
+// ====================================================================================================================
+RD_DEV constexpr int lidx(int i, int j) { return i * (i + 1) / 2 + j; }
+template <typename T, int P>
+RD_DEV T lget(const T (&L)[P * (P + 1) / 2], int i, int j) { return j <= i ? L[lidx(i, j)] : T(0); }
+
+// L' (lower, packed) with L' L'^T = A^T A for a ROWS x P matrix A: the R factor of a Householder QR, transposed.
+// This is rodeo.utils.add_sqrt (src/rodeo/utils.py:10-24: R^T of qr(vstack([sqrt_A^T, sqrt_B^T]))) with the stacked
+// matrix built by the caller.  Only L' L'^T is meaningful across implementations (QR leaves the signs of R's diagonal
+// free).  A is destroyed.
+template <typename T, int ROWS, int P>
+RD_DEV void qr_lower(T (&A)[ROWS][P], T (&Lout)[P * (P + 1) / 2]) {
+  // Householder steps with LAPACK's conventions (dgeqr2 / dlarfg: beta = -sign(x_k) |x|, sign(0) = +, and NO reflection
+  // when the sub-diagonal part is exactly zero), so that the signs of R's diagonal are those jnp.linalg.qr /
+  // np.linalg.qr produce.  They only matter where the reference itself uses a factor un-squared: the
+  // interrogate_chkrebtii "square-root" draw x = mean + (W L) z (src/rodeo/interrogate.py:42-45).
+  RD_UNROLL for (int k = 0; k < P; ++k) {
+    T xn2 = T(0);
+    RD_UNROLL for (int r = k + 1; r < ROWS; ++r) xn2 = rd_fma(A[r][k], A[r][k], xn2);
+    const T x0 = A[k][k];
+    const bool reflect = xn2 > T(0);
+    const T nrm = sqrt(rd_fma(x0, x0, xn2));
+    const T beta = x0 >= T(0) ? -nrm : nrm;
+    // v = x - beta e_k ; H = I - 2 v v^T / (v^T v) ;  v^T v = 2 (|x|^2 - beta x0)
+    const T v0 = x0 - beta;
+    const T vtv = T(2) * (rd_fma(x0, x0, xn2) - beta * x0);
+    const T scale = reflect ? T(2) * rcp(vtv) : T(0);
+    RD_UNROLL for (int c = k + 1; c < P; ++c) {
+      T dot = v0 * A[k][c];
+      RD_UNROLL for (int r = k + 1; r < ROWS; ++r) dot = rd_fma(A[r][k], A[r][c], dot);
+      const T s = scale * dot;
+      A[k][c] = rd_fma(-s, v0, A[k][c]);
+      RD_UNROLL for (int r = k + 1; r < ROWS; ++r) A[r][c] = rd_fma(-s, A[r][k], A[r][c]);
+    }
+    Lout[lidx(k, k)] = reflect ? beta : x0;
+    RD_UNROLL for (int c = k + 1; c < P; ++c) Lout[lidx(c, k)] = A[k][c];   // R[k][c] -> L'[c][k]
+  }
+}
+
+// predict: mu_p = Q mu ;  L_p = add_sqrt(Q L, R^{1/2})            (square_root.py:57-58)
+template <typename T, int P>
+RD_DEV void sqrt_predict(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], const T (&mu)[P],
+                         const T (&L)[P * (P + 1) / 2], T (&mup)[P], T (&Lp)[P * (P + 1) / 2]) {
+  T A[2 * P][P];
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T m = Q[i][0] * mu[0];
+    RD_UNROLL for (int j = 1; j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+    mup[i] = m;
+  }
+  // rows 0..P-1: (Q L)^T, i.e. A[r][c] = sum_{k >= r} Q[c][k] L[k][r] ; rows P..2P-1: (R^{1/2})^T
+  RD_UNROLL for (int r = 0; r < P; ++r)
+    RD_UNROLL for (int c = 0; c < P; ++c) {
+      T a = T(0);
+      RD_UNROLL for (int k = r; k < P; ++k) a = rd_fma(Q[c][k], L[lidx(k, r)], a);
+      A[r][c] = a;
+      A[P + r][c] = lget<T, P>(Rh, c, r);
+    }
+  qr_lower<T, 2 * P, P>(A, Lp);
+}
+
+// update for one scalar measurement row (square_root.py:93-103 with n_meas = 1):
+//   wl = w L ;  s^2 = |wl|^2 + |vrow|^2 ;  K = L wl^T / s^2 ;  mu_f = mu_p + K res
+//   L_f = add_sqrt(L - K wl, K vrow)
+// `vrow` is the measurement-noise square-root BLOCK the reference stacks: a 1 x NV row (NV = 0: none, i.e.
+// interrogate_kramer / schober; NV = P for interrogate_chkrebtii's var_meas = W L).
+template <typename T, int P, int NV>
+RD_DEV void sqrt_update_row(T (&mu)[P], T (&L)[P * (P + 1) / 2], const T (&w)[P], T res, const T* vrow) {
+  T wl[P], K[P];
+  T s2 = T(0);
+  RD_UNROLL for (int c = 0; c < P; ++c) {
+    T a = T(0);
+    RD_UNROLL for (int k = c; k < P; ++k) a = rd_fma(w[k], L[lidx(k, c)], a);
+    wl[c] = a;
+    s2 = rd_fma(a, a, s2);
+  }
+  RD_UNROLL for (int c = 0; c < NV; ++c) s2 = rd_fma(vrow[c], vrow[c], s2);
+  const T rs2 = rcp(s2);
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T a = T(0);
+    RD_UNROLL for (int c = 0; c <= i; ++c) a = rd_fma(L[lidx(i, c)], wl[c], a);
+    K[i] = a * rs2;
+    mu[i] = rd_fma(K[i], res, mu[i]);
+  }
+  T A[P + NV][P];
+  RD_UNROLL for (int r = 0; r < P; ++r)
+    RD_UNROLL for (int c = 0; c < P; ++c) A[r][c] = rd_fma(-K[c], wl[r], lget<T, P>(L, c, r));   // (L - K wl)^T
+  RD_UNROLL for (int r = 0; r < NV; ++r)
+    RD_UNROLL for (int c = 0; c < P; ++c) A[P + r][c] = K[c] * vrow[r];                              // (K vrow)^T
+  qr_lower<T, P + NV, P>(A, L);
+}
+
+// smooth_mv (square_root.py:160-222):  G = S_f Q^T S_p^{-1} through two triangular solves with L_p,
+//   mu_s = mu_f + G (mu_s' - mu_p) ;  L_s = add_sqrt(G [L_s', R^{1/2}], (I - G Q) L_f)
+template <typename T, int P>
+RD_DEV void sqrt_smooth_mv(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], const T (&muf)[P],
+                           const T (&Lf)[P * (P + 1) / 2], const T (&mup)[P], const T (&Lp)[P * (P + 1) / 2],
+                           T (&ms)[P], T (&Ls)[P * (P + 1) / 2]) {
+  T Sf[P][P], X[P][P], G[P][P], rd[P];
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    rd[i] = rcp(Lp[lidx(i, i)]);
+    RD_UNROLL for (int j = 0; j < P; ++j) {
+      T a = T(0);
+      RD_UNROLL for (int k = 0; k <= (i < j ? i : j); ++k) a = rd_fma(Lf[lidx(i, k)], Lf[lidx(j, k)], a);
+      Sf[i][j] = a;
+    }
+  }
+  // X = L_p^{-1} Q   (forward substitution, column by column)
+  RD_UNROLL for (int c = 0; c < P; ++c)
+    RD_UNROLL for (int i = 0; i < P; ++i) {
+      T a = Q[i][c];
+      RD_UNROLL for (int k = 0; k < i; ++k) a = rd_fma(-Lp[lidx(i, k)], X[k][c], a);
+      X[i][c] = a * rd[i];
+    }
+  // Y = X S_f ;  G^T = L_p^{-T} Y  (back substitution);  store G = (G^T)^T
+  RD_UNROLL for (int c = 0; c < P; ++c) {
+    T y[P];
+    RD_UNROLL for (int i = 0; i < P; ++i) {
+      T a = T(0);
+      RD_UNROLL for (int k = 0; k < P; ++k) a = rd_fma(X[i][k], Sf[k][c], a);
+      y[i] = a;
+    }
+    RD_UNROLL for (int i = P - 1; i >= 0; --i) {
+      T a = y[i];
+      RD_UNROLL for (int k = i + 1; k < P; ++k) a = rd_fma(-Lp[lidx(k, i)], y[k], a);
+      y[i] = a * rd[i];
+    }
+    RD_UNROLL for (int i = 0; i < P; ++i) G[c][i] = y[i];
+  }
+  T J[P][P];     // I - G Q
+  RD_UNROLL for (int c = 0; c < P; ++c)
+    RD_UNROLL for (int k = 0; k < P; ++k) {
+      T a = (c == k) ? T(1) : T(0);
+      RD_UNROLL for (int q2 = 0; q2 < P; ++q2) a = rd_fma(-G[c][q2], Q[q2][k], a);
+      J[c][k] = a;
+    }
+  T A[3 * P][P];
+  RD_UNROLL for (int r = 0; r < P; ++r)
+    RD_UNROLL for (int c = 0; c < P; ++c) {
+      // (G L_s')^T[r][c] = sum_{k >= r} G[c][k] L_s'[k][r] ; (G R^{1/2})^T and ((I - G Q) L_f)^T likewise
+      T a = T(0), b = T(0), j = T(0);
+      RD_UNROLL for (int k = r; k < P; ++k) {
+        a = rd_fma(G[c][k], Ls[lidx(k, r)], a);
+        b = rd_fma(G[c][k], Rh[lidx(k, r)], b);
+        j = rd_fma(J[c][k], Lf[lidx(k, r)], j);
+      }
+      A[r][c] = a; A[P + r][c] = b; A[2 * P + r][c] = j;
+    }
+  RD_UNROLL for (int i = 0; i < P; ++i) {
+    T m = muf[i];
+    RD_UNROLL for (int jx = 0; jx < P; ++jx) m = rd_fma(G[i][jx], ms[jx] - mup[jx], m);
+    X[0][i] = m;   // reuse as scratch so that ms is read before it is overwritten
+  }
+  RD_UNROLL for (int i = 0; i < P; ++i) ms[i] = X[0][i];
+  qr_lower<T, 3 * P, P>(A, Ls);
+}
+
 // ---- counter-based RNG -------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  Draws are keyed by (user key, global particle index, step, stream tag) so
 // results do not depend on how the theta batch is sharded over GPUs.  Bit-parity with JAX's threefry key

@@ -446,7 +446,9 @@ struct SegBuf {
   // rows*ROW elements, so the warp walks the 32 thetas and, for each, consecutive lanes store consecutive elements
   // of the run.  A lane's position r in the run -- hence its source slot/state -- is the same for every theta:
   // the (s, k) decode is done once per call, and the loop body is one LDS, one STG and two pointer bumps.
-  template <bool VAR>
+  // LOWER: the slots hold lower-triangular factors (square-root Kalman): expand to a full matrix with a zero
+  // upper triangle instead of mirroring
+  template <bool VAR, bool LOWER = false>
   RD_DEV void copy_out(T* __restrict__ out, i64 theta0, i64 B, int n_rows_total, int n0, int rows) {
     constexpr int ROW = VAR ? NB * P * P : NB * P;
     constexpr int NIT = (K * ROW + 31) / 32;
@@ -456,19 +458,23 @@ struct SegBuf {
       const int r = lane + 32 * it;
       const int s = r / ROW, e = r - s * ROW;
       int k = e;
+      bool zero = false;
       if (VAR) {
         const int b = e / (P * P), ij = e - b * (P * P), i = ij / P, j = ij - i * P;
         const int lo = i < j ? i : j, hi = i < j ? j : i;
-        k = NB * P + b * NS + lo * P - (lo * (lo - 1)) / 2 + (hi - lo);
+        if (LOWER) { k = NB * P + b * NS + i * (i + 1) / 2 + j; zero = j > i; }
+        else k = NB * P + b * NS + lo * P - (lo * (lo - 1)) / 2 + (hi - lo);
       }
-      src[it] = r < run ? (s * NSTATE + k) * SEG_PITCH : -1;
+      src[it] = r < run ? (zero ? -2 : (s * NSTATE + k) * SEG_PITCH) : -1;
     }
     const i64 stride = (i64)n_rows_total * ROW;
     T* dst = out + (theta0 * (i64)n_rows_total + n0) * ROW + lane;
     const int nth = (B - theta0) < 32 ? (int)(B - theta0) : 32;
     RD_UNROLL4 for (int th = 0; th < nth; ++th) {
-      RD_UNROLL for (int it = 0; it < NIT; ++it)
+      RD_UNROLL for (int it = 0; it < NIT; ++it) {
         if (src[it] >= 0) dst[32 * it] = base[src[it] + th];
+        else if (LOWER && src[it] == -2) dst[32 * it] = T(0);
+      }
       dst += stride;
     }
   }
@@ -971,6 +977,138 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   }
 }
 
+
+
+// ==================================================================================================================
+// solve_mv with kalman_type = "square-root"  (reference src/rodeo/solve.py:208-302 with kalman_funs = square_root)
+// ==================================================================================================================
+// Thread per theta, generic (no structure exploitation): the reference's square-root path is the numerically robust
+// one, not the fast one.  Fwd<..>::S holds the packed LOWER factor L; FilterConsts::R holds the packed lower factor
+// of the prior variance (the caller passes prior_pars = (Q, cholesky(R)), docs/examples/higher_order.md:108-112).
+template <typename T, class Model, int INTERR>
+RD_DEV void forward_step_sqrt(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
+                              const typename Model::template Par<T>& q, i64 idx, int n,
+                              Fwd<T, Model, INTERR, QK_DENSE>& f) {
+  constexpr int NB = Model::NB, P = Model::P, M = Model::M, JC = Model::JCOLS, NS = P * (P + 1) / 2;
+  static_assert(M == 1, "square-root path: scalar measurements per block");
+  constexpr bool CHK = (INTERR == INTERR_CHKREBTII);
+  const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
+  RD_UNROLL for (int b = 0; b < NB; ++b) {
+    T mp[P], Lp[NS];
+    sqrt_predict<T, P>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Lp);
+    RD_UNROLL for (int i = 0; i < P; ++i) f.mu[b][i] = mp[i];
+    RD_UNROLL for (int k = 0; k < NS; ++k) f.S[b][k] = Lp[k];
+  }
+  T x[NB][JC], vrow[NB][CHK ? P : 1];
+  if constexpr (CHK) {
+    // interrogate.py:36-47 ("square-root" branch), literally: var_meas = W L is an (m, p) block and
+    // x_state = mean + var_meas @ z, whose single entry broadcasts over every state entry of the block
+    T z[NB * P];
+    if (a.z_interr != nullptr) {
+      const T* zp = a.z_interr + (idx * a.n_steps + n) * (NB * P);
+      RD_UNROLL for (int k = 0; k < NB * P; ++k) z[k] = zp[k];
+    } else {
+      philox_normals<T, NB * P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, z);
+    }
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      T shift = T(0);
+      RD_UNROLL for (int c = 0; c < P; ++c) {
+        T v = T(0);
+        RD_UNROLL for (int k = c; k < P; ++k) v = rd_fma(C.W[b][0][k], f.S[b][lidx(k, c)], v);
+        vrow[b][c] = v;
+        shift = rd_fma(v, z[b * P + c], shift);
+      }
+      RD_UNROLL for (int j = 0; j < JC; ++j) x[b][j] = f.mu[b][j] + shift;
+    }
+  } else {
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      vrow[b][0] = T(0);
+      RD_UNROLL for (int j = 0; j < JC; ++j) x[b][j] = f.mu[b][j];
+    }
+  }
+  T fv[NB][M], jl[NB][M][JC];
+  if constexpr (INTERR == INTERR_KRAMER) {
+    eval_f_jac<Model, T>(q, t, x, fv, jl);
+  } else {
+    Model::template rhs<T, T>(q, t, x, fv);
+    RD_UNROLL for (int b = 0; b < NB; ++b)
+      RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][0][j] = T(0);
+  }
+  RD_UNROLL for (int b = 0; b < NB; ++b) {
+    T w[P], res = fv[b][0];
+    RD_UNROLL for (int j = 0; j < P; ++j) {
+      w[j] = (INTERR == INTERR_KRAMER && j < JC) ? C.W[b][0][j] - jl[b][0][j] : C.W[b][0][j];
+      res = rd_fma(-C.W[b][0][j], f.mu[b][j], res);
+    }
+    sqrt_update_row<T, P, CHK ? P : 0>(f.mu[b], f.S[b], w, res, vrow[b]);
+  }
+}
+
+template <typename T, class Model, int INTERR>
+__global__ void __launch_bounds__(32)
+solve_mv_sqrt_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                     const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
+                     T* __restrict__ mean_out, T* __restrict__ var_out) {
+  typedef Fwd<T, Model, INTERR, QK_DENSE> F;
+  typedef SegBuf<T, F> Buf;
+  constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
+  const i64 theta0 = (i64)blockIdx.x * 32;
+  i64 idx = theta0 + threadIdx.x;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;
+  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const int N = a.n_steps;
+  Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
+  F f;
+  f.init(a.ode_init + idx * NB * P);
+  {
+    int to_ckpt = K, j = 0;
+    for (int n = 0; n < N; ++n) {
+      forward_step_sqrt<T, Model, INTERR>(C, a, q, idx, n, f);
+      if (--to_ckpt == 0) {
+        to_ckpt = K; ++j;
+        if (live && n + 1 < N) ckpt_store<T, F>(stash, ldb, idx, j, f);
+      }
+    }
+  }
+  T ms[NB][P], Ls[NB][NS];
+  RD_UNROLL for (int b = 0; b < NB; ++b) {
+    RD_UNROLL for (int i = 0; i < P; ++i) ms[b][i] = f.mu[b][i];
+    RD_UNROLL for (int k = 0; k < NS; ++k) Ls[b][k] = f.S[b][k];
+  }
+  if (live) {
+    store_mean_row<T, NB, P>(mean_out + (idx * (i64)(N + 1) + N) * (NB * P), ms);
+    T* vr = var_out + (idx * (i64)(N + 1) + N) * (NB * P * P);
+    RD_UNROLL for (int b = 0; b < NB; ++b)
+      RD_UNROLL for (int i = 0; i < P; ++i)
+        RD_UNROLL for (int j = 0; j < P; ++j) vr[(b * P + i) * P + j] = lget<T, P>(Ls[b], i, j);
+  }
+  for (int j = (N - 1) / K; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;
+    if (j == 0) f.init(a.ode_init + idx * NB * P);
+    else ckpt_load<T, F>(stash, ldb, idx, j, f);
+    buf.put(0, f.mu, f.S);
+    for (int s = 1; s < cnt; ++s) {
+      forward_step_sqrt<T, Model, INTERR>(C, a, q, idx, n0 + s - 1, f);
+      buf.put(s, f.mu, f.S);
+    }
+    for (int s = cnt - 1; s >= 0; --s) {
+      if (n0 + s == 0) break;
+      buf.get(s, f.mu, f.S);                               // filt[n] (mean, lower factor)
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        T mp[P], Lp[NS];
+        sqrt_predict<T, P>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Lp);      // pred[n+1]
+        sqrt_smooth_mv<T, P>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Lp, ms[b], Ls[b]);
+      }
+      buf.put(s, ms, Ls);
+    }
+    __syncwarp();
+    buf.template copy_out<false>(mean_out, theta0, a.B, N + 1, n0, cnt);
+    buf.template copy_out<true, true>(var_out, theta0, a.B, N + 1, n0, cnt);
+    __syncwarp();
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // solve_sim with one lane per (theta, block)

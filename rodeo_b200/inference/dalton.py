@@ -17,6 +17,8 @@ def dalton(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogat
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
     pb.set_obs(obs_data, obs_times, obs_weight, obs_var)
+    if kalman_type != "standard":
+        raise NotImplementedError('only kalman_type="standard" is built for the log-likelihood layers')
     out = pb.empty(pb.B)
     zi = None if _z_interr is None else pb.dev(_z_interr)
     rc = pb.fn("dalton")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
@@ -32,8 +34,8 @@ def _adaptive(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interro
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params, particle_offset=particle_offset)
     pb.set_obs(obs_data, obs_times, obs_weight, obs_var)
-    if pb.sfx != "f64":
-        raise NotImplementedError("the data-adaptive solvers are compiled for float64 only")
+    if pb.sfx != "f64" or kalman_type != "standard":
+        raise NotImplementedError("the data-adaptive solvers are compiled for float64, kalman_type=\"standard\" only")
     return pb
 
 

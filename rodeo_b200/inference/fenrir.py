@@ -16,6 +16,8 @@ def fenrir(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogat
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params)
     pb.set_obs(obs_data, obs_times, obs_weight, obs_var)
+    if kalman_type != "standard":
+        raise NotImplementedError('only kalman_type="standard" is built for the log-likelihood layers')
     out = pb.empty(pb.B)
     ws, n = pb.workspace(_lib.OP_FENRIR)
     zi = None if _z_interr is None else pb.dev(_z_interr)

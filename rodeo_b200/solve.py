@@ -21,8 +21,21 @@ def solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrog
     N, dev = pb.n_steps, _host.device()
     mean = pb.empty(pb.B, N + 1, pb.nb, pb.p)
     var = pb.empty(pb.B, N + 1, pb.nb, pb.p, pb.p)
-    ws, n = pb.workspace(_lib.OP_SOLVE_MV)
     zi = None if _z_interr is None else pb.dev(_z_interr)
+    if kalman_type == "square-root":
+        # prior_pars = (Q, cholesky(R)); `var` receives lower-triangular factors, as in the reference
+        # (src/rodeo/kalmantv/square_root.py; docs/examples/higher_order.md:108-127)
+        if pb.sfx != "f64" or pb.r_scale is not None:
+            raise NotImplementedError('kalman_type="square-root" is compiled for float64 and a shared prior only')
+        n = pb.lib.rodeo_b200_solve_mv_sqrt_workspace_bytes(ctypes.byref(pb.c))
+        ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        rc = pb.lib.rodeo_b200_solve_mv_sqrt_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q),
+                                                 _host.ptr(pb.R), _host.ptr(pb.x0), _host.ptr(pb.theta),
+                                                 _host.ptr(zi), _host.ptr(mean), _host.ptr(var), _host.ptr(ws), n,
+                                                 pb.stream())
+        _lib.check(rc, "solve_mv[square-root]")
+        return pb.unbatch(mean), pb.unbatch(var)
+    ws, n = pb.workspace(_lib.OP_SOLVE_MV)
     rc = pb.fn("solve_mv")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
                                         _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(mean),
                                         _host.ptr(var), _host.ptr(ws), n, pb.stream())
@@ -44,6 +57,10 @@ def solve_sim(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interro
     """
     if key is None and _z_smooth is None:
         raise TypeError("solve_sim needs a PRNG key")
+    if kalman_type == "square-root":
+        # the reference hands the square-root factor to multivariate_normal as if it were the covariance
+        # (src/rodeo/solve.py:179 with kalman_funs = square_root): its draws have covariance (L L^T)^(1/2)
+        raise NotImplementedError('solve_sim with kalman_type="square-root" is not built')
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
     N, dev = pb.n_steps, _host.device()

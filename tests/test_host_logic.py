@@ -49,7 +49,7 @@ def test_ibm_init_equals_oracle_and_is_unit_upper():
 
 def test_kalman_type_errors_like_the_reference():
     from rodeo_b200 import _host
-    assert _host.kalman_id("standard") == 0
+    assert _host.kalman_id("standard") == 0 and _host.kalman_id("square-root") == 1
     with pytest.raises(NotImplementedError):
         _host.kalman_id("bogus")                # reference src/rodeo/solve.py:236-241
 
