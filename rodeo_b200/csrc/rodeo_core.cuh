@@ -49,17 +49,15 @@ template <> struct Lim<float> {
 };
 
 // ---- reciprocal ---------------------------------------------------------------------------------------------------
-// 1/x to <= 1 ulp without the branchy slow path of the IEEE division sequence: MUFU.RCP64H seed (>= 20 bits) and two
-// Newton steps.  Zero, infinite, NaN and subnormal arguments yield inf/NaN garbage, exactly where the reference's
+// 1/x to <= 1 ulp without the branchy slow path of the IEEE division sequence: MUFU.RCP64H seed (>= 20 bits) and one
+// cubically convergent step (3 DFMA).  Zero, infinite, NaN and subnormal arguments yield inf/NaN garbage, exactly where the reference's
 // LAPACK solve would have produced inf/NaN as well (a singular innovation variance).
 RD_DEV double rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  // one third-order step: e = 1 - x y (|e| <= 2^-20 from the seed), y <- y (1 + e + e^2): error e^3 <= 2^-60
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);
 }
 RD_DEV float rcp(float x) { return __frcp_rn(x); }
 
@@ -135,59 +133,52 @@ RD_DEV void predict_mean(const T (&Q)[P][P], const T (&mu)[P], T (&mup)[P]) {
 // is what log(w) would have produced in the reference.
 template <typename T> struct LogAcc;
 template <> struct LogAcc<double> {
-  double prod; int esum;
-  RD_DEV void init() { prod = 1.0; esum = 0; }
-  RD_DEV void add(double w, bool keep) {
-    int hi = __double2hiint(w), lo = __double2loint(w);
-    int e = ((hi >> 20) & 0x7ff);
-    bool bad = (hi < 0) || (e == 0x7ff);   // negative, inf or nan: log(w) is nan (or inf) in the reference
-    double mant = bad ? Lim<double>::nan() : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    prod *= keep ? mant : 1.0;
-    esum += (keep && !bad) ? e - 1023 : 0;
+  double prod; int esum, sgn;
+  RD_DEV void init() { prod = 1.0; esum = 0; sgn = 0; }
+  // multiply in one kept term (w, or 1.0 for a dropped one); renorm() must follow within a few dozen terms
+  RD_DEV void add(double wk) { prod *= wk; sgn |= __double2hiint(wk); }
+  RD_DEV void renorm() {
+    const int hi = __double2hiint(prod), lo = __double2loint(prod);
+    const int e = (hi >> 20) & 0x7ff;
+    const bool fin = (unsigned)(e - 1) < 0x7feu;            // normal number: not 0 / subnormal / inf / nan
+    esum += fin ? e - 1023 : 0;
+    prod = fin ? __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo) : prod;
   }
-  RD_DEV void renorm() {  // call at least every ~500 add()s
-    int hi = __double2hiint(prod), lo = __double2loint(prod);
-    int e = ((hi >> 20) & 0x7ff);
-    if (e != 0x7ff && e != 0) {
-      esum += e - 1023;
-      prod = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo);
-    }
+  // sum of log(w) over the kept terms; a negative kept w makes it nan, as log(w) would have in the reference
+  RD_DEV double value() const {
+    const double v = log(fabs(prod)) + 0.6931471805599453094 * (double)esum;
+    return sgn < 0 ? Lim<double>::nan() : v;
   }
-  RD_DEV double value() const { return log(prod) + 0.6931471805599453094 * (double)esum; }
 };
 template <> struct LogAcc<float> {
-  float prod; int esum;
-  RD_DEV void init() { prod = 1.0f; esum = 0; }
-  RD_DEV void add(float w, bool keep) {
-    int b = __float_as_int(w);
-    int e = (b >> 23) & 0xff;
-    bool bad = (b < 0) || (e == 0xff);
-    float mant = bad ? Lim<float>::nan() : __int_as_float((b & 0x007fffff) | 0x3f800000);
-    prod *= keep ? mant : 1.0f;
-    esum += (keep && !bad) ? e - 127 : 0;
+  float prod; int esum, sgn;
+  RD_DEV void init() { prod = 1.0f; esum = 0; sgn = 0; }
+  RD_DEV void add(float wk) { prod *= wk; sgn |= __float_as_int(wk); }
+  RD_DEV void renorm() {
+    const int b = __float_as_int(prod);
+    const int e = (b >> 23) & 0xff;
+    const bool fin = (unsigned)(e - 1) < 0xfeu;
+    esum += fin ? e - 127 : 0;
+    prod = fin ? __int_as_float((b & 0x807fffff) | 0x3f800000) : prod;
   }
-  RD_DEV void renorm() {  // call at least every ~100 add()s
-    int b = __float_as_int(prod);
-    int e = (b >> 23) & 0xff;
-    if (e != 0xff && e != 0) {
-      esum += e - 127;
-      prod = __int_as_float((b & 0x807fffff) | 0x3f800000);
-    }
+  RD_DEV float value() const {
+    const float v = logf(fabsf(prod)) + 0.69314718056f * (float)esum;
+    return sgn < 0 ? Lim<float>::nan() : v;
   }
-  RD_DEV float value() const { return logf(prod) + 0.69314718056f * (float)esum; }
 };
 
 // Gaussian log-density accumulator: logdens = -1/2 (quad + logdet) - 1/2 cnt log(2 pi), with the reference's
 // absolute eigenvalue cut-off |w| > 1e-8 (src/rodeo/utils.py:74, jnp.isclose default atol) applied per term.
+// The caller renormalises the running product once per time step (ld.renorm()).
 template <typename T>
 struct LogPdfAcc {
   T quad; LogAcc<T> ld; int cnt;
   RD_DEV void init() { quad = T(0); ld.init(); cnt = 0; }
   // one eigen-direction: eigenvalue w, projected residual z
   RD_DEV void term(T w, T z, T rw /* = 1/w */) {
-    bool keep = !(fabs(w) <= T(1e-8));   // nan counts as kept, as ~isclose(nan, 0) does
-    quad = keep ? rd_fma(z * z, rw, quad) : quad;
-    ld.add(w, keep);
+    const bool keep = !(fabs(w) <= T(1e-8));   // nan counts as kept, as ~isclose(nan, 0) does
+    quad = rd_fma(z * z, keep ? rw : T(0), quad);
+    ld.add(keep ? w : T(1));
     cnt += keep ? 1 : 0;
   }
   RD_DEV T value() const {
@@ -365,7 +356,7 @@ RD_DEV void update(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], co
 // produces for W = e_WK and a right-hand side that reads the leading JC state columns; jl == 0 for the other
 // interrogations).  Same arithmetic as update<T,P,1,...> with the multiplications by the structural 0 / 1 entries
 // removed (those are exact, so the results are bitwise those of the general row).
-template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J>
+template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J, bool HAS_V = true>
 RD_DEV void update_unit_row(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[JC], T res, T V, LogPdfAcc<T>& acc) {
   T v[P];
   RD_UNROLL for (int i = 0; i < P; ++i) {
@@ -373,7 +364,7 @@ RD_DEV void update_unit_row(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[J
     if (HAS_J) { RD_UNROLL for (int j = 0; j < JC; ++j) a = rd_fma(-jl[j], S[sym<P>(i, j)], a); }
     v[i] = a;
   }
-  T Sm = V + v[WK];
+  T Sm = HAS_V ? V + v[WK] : v[WK];
   if (HAS_J) { RD_UNROLL for (int j = 0; j < JC; ++j) Sm = rd_fma(-jl[j], v[j], Sm); }
   const T rS = rcp(Sm);
   if (WITH_LOGPDF) acc.term(Sm, res, rS);

@@ -261,7 +261,8 @@ struct Fwd {
                        LogPdfAcc<T>& acc) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       if constexpr (UNITW) {
-        update_unit_row<T, P, JC, WK, WITH_LOGPDF, HAS_J>(mu[b], S[b], jl[b][0], res[b][0], V[b][0], acc);
+        update_unit_row<T, P, JC, WK, WITH_LOGPDF, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(
+            mu[b], S[b], jl[b][0], res[b][0], V[b][0], acc);
       } else {
         T wm[M][P];
         rows(C, b, jl[b], wm);
@@ -385,7 +386,7 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     } else {
       f.template update_z<true>(C, jl, res, V, acc);
     }
-    if ((n & 7) == 7) acc.ld.renorm();
+    acc.ld.renorm();
   }
   const T mine = acc.value();
   const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
@@ -809,7 +810,8 @@ struct BlockLane {
     } else if constexpr (UNITW) {
       const T res = fo[0] - mu[WK];
       const T V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) ? S[sidx<P>(WK, WK)] : T(0);
-      update_unit_row<T, P, JC, WK, false, HAS_J>(mu, S, jo[0], res, V, dummy);
+      update_unit_row<T, P, JC, WK, false, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(mu, S, jo[0], res, V,
+                                                                                                         dummy);
     } else {
       T wm[M][P], res[M], V[MS];
       RD_UNROLL for (int r = 0; r < M; ++r) {
@@ -1368,7 +1370,6 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     --i;
   }
   int next_obs = obs_at(i);
-  int cnt8 = 0;
   for (int j = (N - 1) / K; j >= 0; --j) {
     const int n0 = j * K;
     const int cnt = (N - n0) < K ? (N - n0) : K;
@@ -1399,7 +1400,7 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
         --i;
         next_obs = obs_at(i);
       }
-      if ((++cnt8 & 7) == 0) acc.ld.renorm();
+      acc.ld.renorm();
     }
     __syncwarp();
   }
