@@ -134,6 +134,12 @@ int rodeo_b200_basic_gather_f64(const RodeoProblem* prob, const double* Xt /* (B
                                 const int32_t* obs_ind,
                                 double* ode_data /* (B, n_obs, n_block, n_bstate) */, void* stream);
 
+/* loglik[b] = sum_{i,k} log N(obs_data[i, k]; Xt[b, obs_ind[i], k, 0], noise_sd^2): the Gaussian measurement model of
+ * the reference's parameter-inference walkthrough (docs/examples/parameter.md:192-205), fused with the gather; the
+ * inner call of a pseudo-marginal MCMC step (:333-354).  obs_data: (n_obs, n_block) device. */
+int rodeo_b200_gauss_obs_loglik_f64(const RodeoProblem* prob, const double* Xt, const int32_t* obs_ind,
+                                    const double* obs_data, double noise_sd, double* loglik_out, void* stream);
+
 /* X0[b] = [x0[b], f(x0[b], t, theta[b]), 0, ...]   x0: (B, n_block) device; X0: (B, n_block, n_bstate) device */
 int rodeo_b200_ode_init_pad_f64(const RodeoProblem* prob, double t, const double* theta, const double* x0,
                                 double* X0, void* stream);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "rodeo_b200_dalton_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
     "rodeo_b200_fenrir_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
     "rodeo_b200_basic_gather_f64": (_i, [_P, _vp, _vp, _vp, _vp]),
+    "rodeo_b200_gauss_obs_loglik_f64": (_i, [_P, _vp, _vp, _vp, _d, _vp, _vp]),
     "rodeo_b200_ode_init_pad_f64": (_i, [_P, _d, _vp, _vp, _vp, _vp]),
     "rodeo_b200_solve_mv_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_solve_sim_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),

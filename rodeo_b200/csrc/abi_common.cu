@@ -45,6 +45,31 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters,
   if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
 }
 
+// Gaussian observation log-likelihood on the solver output, fused with the gather Xt[obs_ind]:
+//   out[b] = sum_{i, k} log N(obs_data[i, k]; Xt[b, obs_ind[i], k, 0], noise_sd^2)
+// (the measurement model of the reference's parameter-inference walkthrough, docs/examples/parameter.md:192-205,
+// evaluated inside the pseudo-marginal MCMC step :333-354).  One thread per theta.
+template <typename T>
+__global__ void gauss_obs_loglik_kernel(i64 B, int n_rows, int n_obs, int nb, int p, const int* __restrict__ ind,
+                                        const T* __restrict__ Xt, const T* __restrict__ obs_data, T noise_sd,
+                                        T* __restrict__ out) {
+  const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const T rvar = T(1) / (noise_sd * noise_sd);
+  const T cst = T(-0.5) * T(1.8378770664093454836) - log(noise_sd);
+  T acc = T(0);
+  for (int i = 0; i < n_obs; ++i) {
+    int r = ind[i];
+    r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);
+    const T* row = Xt + (b * n_rows + r) * (i64)(nb * p);
+    for (int k = 0; k < nb; ++k) {
+      const T d = obs_data[i * nb + k] - row[k * p];
+      acc += cst - T(0.5) * d * d * rvar;
+    }
+  }
+  out[b] = acc;
+}
+
 template <class Model, int INTERR, int QK>
 struct InitPadRun {
   template <typename T>
@@ -151,6 +176,17 @@ int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out) {
   return RODEO_OK;
 }
 
+int rodeo_b200_gauss_obs_loglik_f64(const RodeoProblem* p, const double* Xt, const int32_t* obs_ind,
+                                    const double* obs_data, double noise_sd, double* loglik_out, void* stream) {
+  if (int rc = check_common(p)) return rc;
+  if (p->n_obs < 1 || !(noise_sd > 0.0)) { set_error("gauss_obs_loglik needs n_obs >= 1 and noise_sd > 0"); return RODEO_ERR_INVALID; }
+  if (p->B == 0) return RODEO_OK;
+  gauss_obs_loglik_kernel<double><<<grid_for(p->B, 128), 128, 0, (cudaStream_t)stream>>>(
+      p->B, p->n_steps + 1, p->n_obs, p->n_block, p->n_bstate, obs_ind, Xt, obs_data, noise_sd, loglik_out);
+  g_launches++;
+  RODEO_CUDA_OK(cudaGetLastError());
+  return RODEO_OK;
+}
 int rodeo_b200_basic_gather_f64(const RodeoProblem* p, const double* Xt, const int32_t* obs_ind, double* ode_data,
                                 void* stream) { return basic_gather_impl<double>(p, Xt, obs_ind, ode_data, stream); }
 int rodeo_b200_basic_gather_f32(const RodeoProblem* p, const float* Xt, const int32_t* obs_ind, float* ode_data,

@@ -612,3 +612,57 @@ def test_square_root_higher_order_docs_example(rb):
     om, oL = orc.solve_mv_sqrt(orc.MODELS["second_order_sin"], pr["W"], pr["X0"], 0.0, 10.0, 400,
                                orc.interrogate_kramer, (pr["Q"], Rh), pr["theta"])
     assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_sq(_np(L)), _sq(oL)) < 1e-8
+
+
+# ---- device-resident pseudo-marginal MCMC ---------------------------------------------------------------------
+def test_pseudo_marginal_random_walk_many_chains(rb):
+    """The reference's pseudo-marginal RW-MH (src/rodeo/inference/pseudo_marginal.py) with solve_sim + chkrebtii inside
+    (docs/examples/parameter.md:333-396), here for 256 chains at once without leaving the device."""
+    import torch
+    from rodeo_b200.inference import pseudo_marginal as pm
+    N, tm, C = 100, 5.0, 256
+    pr0 = P.fitz_problem(1, n_steps=N, t_max=tm, jitter=False)
+    truth, _ = orc.solve_mv(orc.MODELS["fitzhugh_nagumo"], pr0["W"], pr0["X0"], 0.0, tm, N, orc.interrogate_kramer,
+                            (pr0["Q"], pr0["R"]), pr0["theta"])
+    ob = P.fitz_obs(pr0, truth[0], n_obs=6)
+    Y = ob["obs_data"][:, :, 0]
+    ind = orc.obs_index(0.0, tm, N, ob["obs_times"])
+    # fused observation log-likelihood == the docs' fitz_loglik on Xt[obs_ind]
+    Xt = torch.as_tensor(np.repeat(truth, 3, axis=0)).cuda()
+    ll = _np(pm.gauss_obs_loglik(Xt, ind, Y, np.sqrt(0.005)))
+    import scipy.stats
+    want = scipy.stats.norm.logpdf(Y, loc=truth[0][ind, :, 0], scale=np.sqrt(0.005)).sum()
+    assert np.allclose(ll, want, rtol=1e-12)
+
+    chk = functools.partial(rb.interrogate.interrogate_chkrebtii, kalman_type="standard")
+    W, fitz_init = rb.utils.first_order_pad(rb.models.fitzhugh_nagumo, 2, 3)
+
+    def logpost(upars, key):                       # upars = (log a, log b, log c, V0, R0), one row per chain
+        theta = torch.exp(upars[:, :3]); x0 = upars[:, 3:5]
+        X0 = fitz_init(x0, 0.0, theta=theta)
+        xs = rb.solve_sim(key, rb.models.fitzhugh_nagumo, W, X0, 0.0, tm, N, chk, prior_pars=(pr0["Q"], pr0["R"]),
+                          theta=theta)
+        lp = pm.gauss_obs_loglik(xs, ind, Y, np.sqrt(0.005)) - 0.5 * (upars ** 2).sum(dim=1) / 100.0
+        return lp, xs
+
+    start = np.tile(np.concatenate([np.log([0.2, 0.2, 3.0]), [-1.0, 1.0]]), (C, 1))
+    alg = pm.normal_random_walk(logpost, sigma=np.array([0.02, 0.02, 0.01, 0.01, 0.01]))
+    state = alg.init(start, rng_key=1)
+    assert state.position.shape == (C, 5) and state.auxdata.shape == (C, N + 1, 2, 3)
+    n_acc = torch.zeros(C, device="cuda")
+    for it in range(30):
+        state, info = alg.step(np.array([7, it], dtype=np.uint32), state)
+        n_acc += info.is_accepted
+        # accepted chains carry the proposal's log-density and trajectory, rejected ones keep theirs
+        assert torch.equal(state.logdensity[info.is_accepted], info.proposal.logdensity[info.is_accepted])
+    rate = float(n_acc.mean() / 30)
+    assert torch.isfinite(state.logdensity).all() and torch.isfinite(state.position).all()
+    assert 0.02 < rate < 0.98, rate
+    # reproducible for the same keys
+    s2 = alg.init(start, rng_key=1)
+    for it in range(3):
+        s2, _ = alg.step(np.array([7, it], dtype=np.uint32), s2)
+    s3 = alg.init(start, rng_key=1)
+    for it in range(3):
+        s3, _ = alg.step(np.array([7, it], dtype=np.uint32), s3)
+    assert torch.equal(s2.position, s3.position)
