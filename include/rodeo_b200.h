@@ -161,6 +161,15 @@ int rodeo_b200_dalton_solve_sim_f64(const RodeoProblem* prob, const double* ode_
                                     const double* z_interr, const double* z_smooth, const int32_t* obs_ind,
                                     const double* obs_data, const double* obs_weight, const double* obs_var,
                                     double* x_out, void* workspace, size_t workspace_bytes, void* stream);
+/* rodeo.inference.fenrir.solve_mv (src/rodeo/inference/fenrir.py:404-457); same arguments as
+ * rodeo_b200_dalton_solve_mv_f64; workspace of rodeo_b200_fenrir_solve_mv_workspace_bytes(prob) bytes. */
+size_t rodeo_b200_fenrir_solve_mv_workspace_bytes(const RodeoProblem* prob);
+int rodeo_b200_fenrir_solve_mv_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                                   const double* prior_var, const double* ode_init, const double* theta,
+                                   const double* z_interr, const int32_t* obs_ind, const double* obs_data,
+                                   const double* obs_weight, const double* obs_var, double* mean_out, double* var_out,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /*
  * rodeo.solve_mv with kalman_type="square-root" (src/rodeo/solve.py:236-241 selecting src/rodeo/kalmantv/
  * square_root.py): prior_var_sqrt is the lower Cholesky factor of R (docs/examples/higher_order.md:108-112) and

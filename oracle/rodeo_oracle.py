@@ -772,3 +772,53 @@ def solve_mv_sqrt(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogat
         ms[:, t], Ls[:, t] = sqrt_smooth_mv(ms[:, t + 1], Ls[:, t + 1], mf[:, t], Lf[:, t], mp[:, t + 1],
                                             Lp[:, t + 1], Q, Rh)
     return ms, Ls
+
+
+# ----------------------------------------------------------------------------------------------------
+# fenrir solver  (reference src/rodeo/inference/fenrir.py:86-259 _backward stacks, :333-457 _smooth_mv / solve_mv)
+# ----------------------------------------------------------------------------------------------------
+
+def fenrir_solve_mv(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars, theta,
+                    obs_data, obs_times, obs_weight, obs_var, z_interrogate=None, **ikw):
+    """Posterior mean / variance of p(X_{0:N} | Z_{1:N}, Y_{0:M}) by the Fenrir construction: forward ODE filter,
+    backward Markov chain filtered with the observations (fenrir.py:86-259), then an RTS pass over that chain forward
+    in time (fenrir.py:333-401).  Returns (mean, var) of shapes (B, N+1, nb, p[, p])."""
+    Qs, Rs = prior_pars
+    mp, vp, mf, vf = solve_filter(model, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, Qs, Rs, theta,
+                                  z_interrogate, **ikw)
+    B, _, nb, p = mf.shape
+    N = n_steps
+    Q = _bq(Qs, B)
+    obs_data = np.asarray(obs_data, dtype=np.float64)
+    n_obs, _, n_bobs, _ = obs_weight.shape
+    obs_ind = obs_index(t_min, t_max, N, obs_times)
+    obs_mean = np.zeros((B, nb, n_bobs))
+    # stacks over t = 0..N (entry N = terminal point)
+    bmp = np.zeros((B, N + 1, nb, p)); bvp = np.zeros((B, N + 1, nb, p, p))
+    bmf = np.zeros((B, N + 1, nb, p)); bvf = np.zeros((B, N + 1, nb, p, p))
+    A_all = np.zeros((B, N, nb, p, p))
+    i = n_obs - 1
+    bm, bv = mf[:, N], vf[:, N]
+    bmp[:, N], bvp[:, N] = bm, bv                        # "state_pred" terminal entry = forward filt[N]  (fenrir.py:240-245)
+    if obs_ind[i] >= N:
+        _, bm, bv = _forecast_update(bm, bv, np.broadcast_to(obs_data[i], (B, nb, n_bobs)), obs_mean, obs_weight[i],
+                                     obs_var[i])
+        i -= 1
+    bmf[:, N], bvf[:, N] = bm, bv
+    for t in range(N - 1, -1, -1):
+        A, b, C = smooth_cond(mf[:, t], vf[:, t], mp[:, t + 1], vp[:, t + 1], Q)
+        bm, bv = predict(bm, bv, b, A, C)
+        bmp[:, t], bvp[:, t] = bm, bv
+        A_all[:, t] = A
+        if obs_ind[i] == t:
+            _, bm, bv = _forecast_update(bm, bv, np.broadcast_to(obs_data[i], (B, nb, n_bobs)), obs_mean, obs_weight[i],
+                                         obs_var[i])
+            i -= 1
+        bmf[:, t], bvf[:, t] = bm, bv
+    # forward-in-time smoothing of the backward chain  (fenrir.py:333-401)
+    ms = np.zeros_like(bmf); vs = np.zeros_like(bvf)
+    ms[:, 0:2], vs[:, 0:2] = bmf[:, 0:2], bvf[:, 0:2]
+    for k in range(N - 1):                               # scan index; produces row k + 2
+        ms[:, k + 2], vs[:, k + 2] = smooth_mv(ms[:, k + 1], vs[:, k + 1], bmf[:, k + 2], bvf[:, k + 2],
+                                               bmp[:, k + 1], bvp[:, k + 1], A_all[:, k + 1])
+    return ms, vs

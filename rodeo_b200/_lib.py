@@ -71,6 +71,8 @@ SIGNATURES = {
     "rodeo_b200_dalton_solve_sim_f64": (_i, [_P] + [_vp] * 12 + [_vp, _sz, _vp]),
     "rodeo_b200_solve_mv_sqrt_workspace_bytes": (_sz, [_P]),
     "rodeo_b200_solve_mv_sqrt_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "rodeo_b200_fenrir_solve_mv_workspace_bytes": (_sz, [_P]),
+    "rodeo_b200_fenrir_solve_mv_f64": (_i, [_P] + [_vp] * 12 + [_vp, _sz, _vp]),
     "rodeo_b200_dalton_f64_host": (_i, [_P] + [_vp] * 10),
     "rodeo_b200_solve_mv_f64_host": (_i, [_P] + [_vp] * 7),
     "rodeo_b200_host_arena_release": (None, []),

@@ -1407,6 +1407,153 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   if (live) loglik[idx] = acc.value();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// fenrir.solve_mv: posterior mean / variance p(X_{0:N} | Z_{1:N}, Y_{0:M}) by the Fenrir construction
+// (reference src/rodeo/inference/fenrir.py:86-259 `_backward` stacks, :333-401 `_smooth_mv`, :404-457 `solve_mv`)
+// ------------------------------------------------------------------------------------------------------------------
+// Three sweeps per theta, thread per theta:
+//   1. forward ODE filter, filt[n] kept in history H1;
+//   2. backward filter over the smoothing Markov chain X_t = A_t X_{t+1} + b_t + N(0, C_t) with the observations,
+//      its filtered states bfilt[t] kept in history H2 (rows 0 and 1 of the output are bfilt[0], bfilt[1]);
+//   3. RTS pass over that chain forward in time: row k+1 from row k, bfilt[k+1] and bpred[k], where
+//      (A_k, b_k, C_k) and bpred[k] = predict(bfilt[k+1]; A_k, b_k, C_k) are recomputed from filt[k] instead of stored.
+template <typename T, class Model, int INTERR, int QK, int NOBS>
+__global__ void __launch_bounds__(32)
+fenrir_solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                       const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ h1, T* __restrict__ h2, i64 ldb,
+                       T* __restrict__ mean_out, T* __restrict__ var_out) {
+  typedef Fwd<T, Model, INTERR, QK> F;
+  typedef SegBuf<T, F> Buf;
+  constexpr int NB = F::NB, P = F::P, NS = F::NS, K = Buf::K;
+  const i64 theta0 = (i64)blockIdx.x * 32;
+  i64 idx = theta0 + threadIdx.x;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;
+  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const int N = a.n_steps;
+  Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
+  F f;
+  f.init(a.ode_init + idx * NB * P);
+  f.load_scale(a, idx);
+  forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, h1, ldb);     // H1 entry n = filt[n], 1..N-1
+
+  // the chain parameters of step t from filt[t]:  A = G, bvec = mu_f - G mu_p, Cv = S_f - G (S_f Q^T)^T
+  auto chain = [&](int b, const F& fl, T (&G)[P][P], T (&mp)[P], T (&Cv)[NS]) {
+    T Sp[NS], Ct[P][P];
+    predict<T, P, QK>(C.Q[b], C.R[b], fl.rs[b], fl.mu[b], fl.S[b], mp, Sp);
+    smooth_gain<T, P, QK>(C.Q[b], fl.S[b], Sp, G, Ct);
+    cond_var<T, P>(fl.S[b], G, Ct, Cv);
+  };
+  auto load_filt = [&](int t, F& fl) {
+    if (t >= 1) ckpt_load<T, F>(h1, ldb, idx, t, fl);
+    else fl.init(a.ode_init + idx * NB * P);
+  };
+
+  // ---- sweep 2: backward filter, bfilt[t] -> H2 entry t (t = 1..N)
+  F bk;
+  bk.load_scale(a, idx);
+  RD_UNROLL for (int b = 0; b < NB; ++b) {
+    RD_UNROLL for (int i = 0; i < P; ++i) bk.mu[b][i] = f.mu[b][i];
+    RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = f.S[b][k];
+  }
+  LogPdfAcc<T> acc;
+  acc.init();
+  int i = o.n_obs - 1;
+  auto obs_at = [&](int k) { return __ldg(o.obs_ind + (k < 0 ? k + o.n_obs : k)); };
+  if (obs_at(i) >= N) { bk.template update_y<NOBS>(o, i, acc); --i; }
+  if (live) ckpt_store<T, F>(h2, ldb, idx, N, bk);
+  int next_obs = obs_at(i);
+  for (int t = N - 1; t >= 0; --t) {
+    load_filt(t, f);
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      T G[P][P], mp[P], Cv[NS], nm[P];
+      chain(b, f, G, mp, Cv);
+      RD_UNROLL for (int r = 0; r < P; ++r) {
+        T s = f.mu[b][r];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) s = rd_fma(G[r][jj], bk.mu[b][jj] - mp[jj], s);
+        nm[r] = s;
+      }
+      add_GDGt<T, P>(G, bk.S[b], Cv);
+      RD_UNROLL for (int r = 0; r < P; ++r) bk.mu[b][r] = nm[r];
+      RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = Cv[k];
+    }
+    if (next_obs == t) {
+      bk.template update_y<NOBS>(o, i < 0 ? i + o.n_obs : i, acc);
+      --i;
+      next_obs = obs_at(i);
+    }
+    acc.ld.renorm();
+    if (t >= 1) { if (live) ckpt_store<T, F>(h2, ldb, idx, t, bk); }
+    else if (live) {                                       // row 0 = bfilt[0]
+      store_mean_row<T, NB, P>(mean_out + idx * (i64)(N + 1) * (NB * P), bk.mu);
+      store_var_row<T, NB, P>(var_out + idx * (i64)(N + 1) * (NB * P * P), bk.S);
+    }
+  }
+
+  // ---- sweep 3: forward-in-time RTS over the backward chain; rows 1..N staged K at a time
+  T ms[NB][P], Ss[NB][NS];
+  F bf;                                                    // bfilt[k+1]
+  for (int n0 = 1; n0 <= N; n0 += K) {
+    const int cnt = (N + 1 - n0) < K ? (N + 1 - n0) : K;
+    for (int s = 0; s < cnt; ++s) {
+      const int row = n0 + s;
+      ckpt_load<T, F>(h2, ldb, idx, row, bf);
+      if (row == 1) {                                      // row 1 = bfilt[1]  (fenrir.py:373-376, 394-399)
+        RD_UNROLL for (int b = 0; b < NB; ++b) {
+          RD_UNROLL for (int i2 = 0; i2 < P; ++i2) ms[b][i2] = bf.mu[b][i2];
+          RD_UNROLL for (int k = 0; k < NS; ++k) Ss[b][k] = bf.S[b][k];
+        }
+      } else {
+        const int k = row - 1;                             // chain step X_k = A_k X_{k+1} + ...
+        load_filt(k, f);
+        RD_UNROLL for (int b = 0; b < NB; ++b) {
+          T A[P][P], mp[P], Cv[NS], bpm[P];
+          chain(b, f, A, mp, Cv);
+          // bpred[k] = predict(bfilt[k+1]; A, bvec, Cv)
+          RD_UNROLL for (int r = 0; r < P; ++r) {
+            T sacc = f.mu[b][r];
+            RD_UNROLL for (int jj = 0; jj < P; ++jj) sacc = rd_fma(A[r][jj], bf.mu[b][jj] - mp[jj], sacc);
+            bpm[r] = sacc;
+          }
+          add_GDGt<T, P>(A, bf.S[b], Cv);                  // Cv <- bvar_pred[k]
+          // smooth_mv(next = row k, filt = bfilt[k+1], pred = bpred[k], wgt_state = A)   (standard.py:210-216)
+          //   G2 = bS_f[k+1] A^T bS_p[k]^{-1}
+          T Ct[P][P], G2[P][P], L[P][P], rD[P];
+          RD_UNROLL for (int r = 0; r < P; ++r)
+            RD_UNROLL for (int c = 0; c < P; ++c) {
+              T sacc = T(0);
+              RD_UNROLL for (int kk = 0; kk < P; ++kk) sacc = rd_fma(bf.S[b][sym<P>(r, kk)], A[c][kk], sacc);
+              Ct[r][c] = sacc;
+            }
+          ldlt<T, P>(Cv, L, rD);
+          RD_UNROLL for (int r = 0; r < P; ++r) {
+            T x[P];
+            RD_UNROLL for (int c = 0; c < P; ++c) x[c] = Ct[r][c];
+            ldlt_solve<T, P>(L, rD, x);
+            RD_UNROLL for (int c = 0; c < P; ++c) G2[r][c] = x[c];
+          }
+          T dm[P], D[NS];
+          RD_UNROLL for (int r = 0; r < P; ++r) dm[r] = ms[b][r] - bpm[r];
+          RD_UNROLL for (int kk = 0; kk < NS; ++kk) D[kk] = Ss[b][kk] - Cv[kk];
+          RD_UNROLL for (int r = 0; r < P; ++r) {
+            T m = bf.mu[b][r];
+            RD_UNROLL for (int c = 0; c < P; ++c) m = rd_fma(G2[r][c], dm[c], m);
+            ms[b][r] = m;
+          }
+          RD_UNROLL for (int kk = 0; kk < NS; ++kk) Ss[b][kk] = bf.S[b][kk];
+          add_GDGt<T, P>(G2, D, Ss[b]);
+        }
+      }
+      buf.put(s, ms, Ss);
+    }
+    __syncwarp();
+    buf.template copy_out<false>(mean_out, theta0, a.B, N + 1, n0, cnt);
+    buf.template copy_out<true>(var_out, theta0, a.B, N + 1, n0, cnt);
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // first_order_pad initial value: X0 = [x0, f(x0, t, theta), 0, ...]   (reference src/rodeo/utils.py:94-96)
 // ------------------------------------------------------------------------------------------------------------------

@@ -666,3 +666,17 @@ def test_pseudo_marginal_random_walk_many_chains(rb):
     for it in range(3):
         s3, _ = alg.step(np.array([7, it], dtype=np.uint32), s3)
     assert torch.equal(s2.position, s3.position)
+
+
+def test_fenrir_solve_mv(rb):
+    """rodeo.inference.fenrir.solve_mv (fenrir.py:404-457)."""
+    pr = P.fitz_problem(40, n_steps=100, t_max=5.0, seed=81)
+    for times in (np.linspace(0.0, 5.0, 6), np.array([0.4, 1.3, 2.0, 3.7])):
+        ob = P.fitz_obs(pr, None, n_obs=len(times)); ob["obs_times"] = times
+        m, v = rb.inference.fenrir_solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 5.0, 100,
+                                            rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]),
+                                            theta=pr["theta"], **ob)
+        om, ov = orc.fenrir_solve_mv(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 5.0, 100,
+                                     orc.interrogate_kramer, (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"],
+                                     ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+        assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(v), ov) < 1e-9

@@ -218,3 +218,17 @@ def test_dalton_obs_pointer_semantics():
     y0 = np.array([sum(orc.multivariate_normal_logpdf(obs_data[0, b], D[0, b] @ X0[k, b], Om[0, b]) for b in range(2))
                    for k in range(2)])
     assert np.allclose(full, tail + y0, rtol=1e-12)
+
+
+def test_fenrir_and_dalton_data_adaptive_posteriors_agree_for_a_linear_ode():
+    # both are the exact posterior p(X | Z = 0, Y) of a linear-Gaussian model: pins the stacks / index conventions of
+    # fenrir._backward + _smooth_mv (fenrir.py:86-401) against dalton._solve_filter + smoother (dalton.py:242-460)
+    mdl, W, X0, theta, prior = so_setup(60, 1.0, B=3, seed=2, t_max=3.0)
+    obs_times = np.array([0.0, 1.0, 2.0, 3.0])
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal((4, 1, 1))
+    D = np.zeros((4, 1, 1, 4)); D[..., 0] = 1.0
+    Om = np.full((4, 1, 1, 1), 0.05)
+    a = orc.fenrir_solve_mv(mdl, W, X0, 0.0, 3.0, 60, orc.interrogate_kramer, prior, theta, y, obs_times, D, Om)
+    b = orc.dalton_solve_mv(mdl, W, X0, 0.0, 3.0, 60, orc.interrogate_kramer, prior, theta, y, obs_times, D, Om)
+    assert maxnorm_rel(a[0], b[0]) < 1e-9 and maxnorm_rel(a[1], b[1]) < 1e-9
