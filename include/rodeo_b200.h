@@ -222,6 +222,29 @@ int rodeo_b200_solve_mv_f64_host(const RodeoProblem* prob, const double* ode_wei
 void rodeo_b200_host_arena_release(void);
 
 /*
+ * Batched Kalman primitives, one problem per leading index: rodeo.kalmantv.standard.{predict, update, forecast,
+ * smooth_mv, smooth_sim, smooth_cond} (src/rodeo/kalmantv/standard.py:31-103, 160-255, 308-371) and
+ * rodeo.utils.multivariate_normal_logpdf (src/rodeo/utils.py:60-78).  Full row-major matrices, device pointers,
+ * float64, n_state in 1..7, n_meas in 1..3.  They call the same __device__ functions the fused kernels inline.
+ *   update: pass mean_state_filt/var_state_filt for the update, mean_fore/var_fore for the forecast (either may be NULL);
+ *   smooth: mode 0 = smooth_mv (x_next = mean_state_next, var_next = var_state_next), 1 = smooth_sim
+ *           (x_next = x_state_next), 2 = smooth_cond (out_wgt = A, out_mean = b, out_var = C).
+ */
+int rodeo_b200_ktv_predict_f64(int64_t B, int n_state, const double* mean_state_past, const double* var_state_past,
+                               const double* mean_state, const double* wgt_state, const double* var_state,
+                               double* mean_state_pred, double* var_state_pred, void* stream);
+int rodeo_b200_ktv_update_f64(int64_t B, int n_state, int n_meas, const double* mean_state_pred,
+                              const double* var_state_pred, const double* x_meas, const double* mean_meas,
+                              const double* wgt_meas, const double* var_meas, double* mean_state_filt,
+                              double* var_state_filt, double* mean_fore, double* var_fore, void* stream);
+int rodeo_b200_ktv_smooth_f64(int64_t B, int n_state, int mode, const double* x_next, const double* var_next,
+                              const double* mean_state_filt, const double* var_state_filt,
+                              const double* mean_state_pred, const double* var_state_pred, const double* wgt_state,
+                              double* out_mean, double* out_var, double* out_wgt, void* stream);
+int rodeo_b200_mvn_logpdf_f64(int64_t B, int n, const double* x, const double* mean, const double* cov, double* out,
+                              void* stream);
+
+/*
  * Register a user ODE right-hand side given as CUDA source defining `struct UserModel` with the functor interface
  * documented in rodeo_b200/csrc/rodeo_models.cuh (rodeo_b200.models.CudaOde generates it from a one-line rhs).  The
  * kernels are compiled for sm_100a with NVRTC on first use.  Replaces: an arbitrary `ode_fun` callable passed to

@@ -5,6 +5,6 @@ Mirrors the reference's public names (reference src/rodeo/__init__.py:1-6):
 """
 __version__ = "0.1.0"
 
-from . import interrogate, prior, utils, models, inference  # noqa: F401
+from . import interrogate, prior, utils, models, inference, kalmantv  # noqa: F401
 from .prior import ibm_init  # noqa: F401
 from .solve import solve_sim, solve_mv  # noqa: F401

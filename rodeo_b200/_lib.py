@@ -73,6 +73,10 @@ SIGNATURES = {
     "rodeo_b200_solve_mv_sqrt_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_fenrir_solve_mv_workspace_bytes": (_sz, [_P]),
     "rodeo_b200_fenrir_solve_mv_f64": (_i, [_P] + [_vp] * 12 + [_vp, _sz, _vp]),
+    "rodeo_b200_ktv_predict_f64": (_i, [ctypes.c_int64, _i] + [_vp] * 7 + [_vp]),
+    "rodeo_b200_ktv_update_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
+    "rodeo_b200_ktv_smooth_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
+    "rodeo_b200_mvn_logpdf_f64": (_i, [ctypes.c_int64, _i] + [_vp] * 4 + [_vp]),
     "rodeo_b200_dalton_f64_host": (_i, [_P] + [_vp] * 10),
     "rodeo_b200_solve_mv_f64_host": (_i, [_P] + [_vp] * 7),
     "rodeo_b200_host_arena_release": (None, []),

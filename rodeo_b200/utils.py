@@ -42,3 +42,19 @@ def first_order_pad(ode_fun, n_vars, n_deriv):
     W = np.zeros((n_vars, 1, n_deriv))
     W[:, :, 1] = 1.0
     return W, ode_init
+
+
+def multivariate_normal_logpdf(x, mean, cov):
+    """Eigendecomposition log-pdf with the reference's absolute 1e-8 eigenvalue cut-off (src/rodeo/utils.py:60-78),
+    batched over leading axes; dimension 1..3; float64 CUDA tensor out."""
+    x, mean, cov = _host.to_dev(x), _host.to_dev(mean), _host.to_dev(cov)
+    n = cov.shape[-1]
+    lead = torch.broadcast_shapes(x.shape[:-1], mean.shape[:-1], cov.shape[:-2])
+    xf = x.expand(*lead, n).reshape(-1, n).contiguous()
+    mf = mean.expand(*lead, n).reshape(-1, n).contiguous()
+    cf = cov.expand(*lead, n, n).reshape(-1, n, n).contiguous()
+    out = torch.empty((xf.shape[0],), dtype=torch.float64, device=xf.device)
+    rc = _lib.load().rodeo_b200_mvn_logpdf_f64(xf.shape[0], n, _host.ptr(xf), _host.ptr(mf), _host.ptr(cf),
+                                               _host.ptr(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "multivariate_normal_logpdf")
+    return out.reshape(lead)
