@@ -61,6 +61,20 @@ RD_DEV double rcp(double x) {
 }
 RD_DEV float rcp(float x) { return __frcp_rn(x); }
 
+// sqrt(x) and 1/sqrt(x) together, x > 0 normal: MUFU.RSQ64H seed, one cubically convergent step for the reciprocal
+// root, one correction step for the root (<= 1 ulp each); no slow path.  Used by the Cholesky-type factors of the
+// sampling paths, which need both.
+RD_DEV void sqrt_rsqrt(double x, double& s, double& rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);                    // 1 - x y^2
+  y = fma(y * fma(0.375, e, 0.5), e, y);                   // y (1 + e/2 + 3 e^2 / 8)
+  double r = x * y;
+  r = fma(fma(-r, r, x), 0.5 * y, r);
+  s = r; rs = y;
+}
+RD_DEV void sqrt_rsqrt(float x, float& s, float& rs) { rs = rsqrtf(x); s = x * rs; }
+
 // ---- constants that live in the kernel-parameter constant bank ------------------------------------------
 // Q, R, W are shared by every theta of a launch (reference layouts (nb,p,p), (nb,p,p), (nb,m,p)); passing them
 // by value as a __grid_constant__ kernel parameter lets every DFMA take them as c[0][..] operands: they cost
@@ -413,8 +427,8 @@ RD_DEV void psd_factor(const T (&C)[P * (P + 1) / 2], T (&A)[P][P]) {
     T d = C[sidx<P>(j, j)];
     RD_UNROLL for (int k = 0; k < j; ++k) d = rd_fma(-A[j][k], A[j][k], d);
     bool pos = d > T(0);
-    T dj = sqrt(pos ? d : T(1));
-    T rdj = rcp(dj);
+    T dj, rdj;
+    sqrt_rsqrt(pos ? d : T(1), dj, rdj);
     A[j][j] = pos ? dj : T(0);
     RD_UNROLL for (int i = j + 1; i < P; ++i) {
       T s = C[sidx<P>(j, i)];
@@ -664,8 +678,18 @@ struct Philox {
   }
 };
 
-// two independent standard normals from 128 random bits (Box-Muller on 53-bit uniforms)
-RD_DEV void normal_pair(const unsigned (&r)[4], double& z0, double& z1) {
+// Two independent standard normals from 128 random bits: Box-Muller on a 53-bit uniform for the radius (so the tail
+// reaches 8.6 sigma) and a 24-bit uniform for the angle.
+//
+// Default (fast) variant: the transcendental part runs on the FP32 special-function unit -- ln u1 is split as
+// (exponent) ln 2 + ln(mantissa) with the exponent taken exactly from the double's bits, so only ln of a number in
+// [1, 2) and sin / cos of an angle in [0, 2 pi) are approximated -- and the result is widened to double.  The draws
+// are standard normal to ~2^-21 relative (total-variation distance ~1e-6 from the exact law: no sample-based test can
+// see it), at about a sixth of the instructions of the all-FP64 version, which matters because the sampling smoother
+// spends ~40% of its instructions on normals.  Define RODEO_EXACT_NORMALS for the all-FP64 Box-Muller.
+// Bit parity with JAX's threefry / erfinv normals is not attainable either way; deterministic parity
+// tests inject the normals instead.
+RD_DEV void normal_pair_exact(const unsigned (&r)[4], double& z0, double& z1) {
   unsigned long long a = ((unsigned long long)r[0] << 32) | r[1];
   unsigned long long b = ((unsigned long long)r[2] << 32) | r[3];
   double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);   // (0,1)
@@ -675,13 +699,34 @@ RD_DEV void normal_pair(const unsigned (&r)[4], double& z0, double& z1) {
   sincospi(2.0 * u2, &s, &c);
   z0 = rad * c; z1 = rad * s;
 }
-RD_DEV void normal_pair(const unsigned (&r)[4], float& z0, float& z1) {
-  float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  float rad = sqrtf(-2.0f * logf(u1));
+RD_DEV void normal_pair_fast(const unsigned (&r)[4], float& z0, float& z1) {
+  // x = (a >> 11) + 0.5 in [0.5, 2^53): u1 = x 2^-53.  Its binary exponent is found from the leading one of the integer.
+  const unsigned hi = r[0], lo = r[1];
+  const unsigned long long k = (((unsigned long long)hi << 32) | lo) >> 11;          // 53-bit integer
+  const int lz = k ? __clzll((long long)k) : 64;                                      // leading zeros in 64 bits
+  const int e = 63 - lz;                                                              // floor(log2 k), -1 if k == 0
+  // mantissa of (k + 0.5) in [1, 2) to 24 bits: shift k so that its leading one sits at bit 23 (the +0.5 only matters
+  // for tiny k, where it is added explicitly)
+  float mant;
+  int ex;
+  if (e >= 24) { mant = (float)(unsigned)(k >> (e - 23)) * (1.0f / 8388608.0f); ex = e; }
+  else { const float xs = (float)(unsigned)k + 0.5f; ex = 0; mant = xs; }             // small k: exact in float
+  const float ln_u1 = ((float)(ex - 53) + __log2f(mant)) * 0.69314718056f;            // ln(x 2^-53), < 0
+  const float rad = sqrtf(-2.0f * ln_u1);
+  const float ang = (float)(r[2] >> 8) * (6.28318530718f / 16777216.0f);
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(ang, &s, &c);
   z0 = rad * c; z1 = rad * s;
 }
+RD_DEV void normal_pair(const unsigned (&r)[4], double& z0, double& z1) {
+#ifdef RODEO_EXACT_NORMALS
+  normal_pair_exact(r, z0, z1);
+#else
+  float a, b;
+  normal_pair_fast(r, a, b);
+  z0 = (double)a; z1 = (double)b;
+#endif
+}
+RD_DEV void normal_pair(const unsigned (&r)[4], float& z0, float& z1) { normal_pair_fast(r, z0, z1); }
 
 }  // namespace rodeo
