@@ -75,6 +75,14 @@ RD_DEV void sqrt_rsqrt(double x, double& s, double& rs) {
 }
 RD_DEV void sqrt_rsqrt(float x, float& s, float& rs) { rs = rsqrtf(x); s = x * rs; }
 
+// ---- mixed precision -----------------------------------------------------------------------------------------------
+// The block MEANS (and everything that feeds the ODE right-hand side and the update residual) are always carried in
+// double, also by the float32 instantiation: the residual f - W mu_p ~ 1e-3 is a difference of O(1) numbers and the
+// mean recursion is iterated n_steps times, so a float mean drifts by ~n_steps * 6e-8 (3.9e-5 at N = 800, above the
+// 1e-5 float32 budget).  Covariances, gains and log-density terms -- the bulk of the arithmetic -- stay in T.
+// For T = double the two types coincide and nothing changes.
+template <typename T> struct MeanOf { typedef double type; };
+
 // ---- constants that live in the kernel-parameter constant bank ------------------------------------------
 // Q, R, W are shared by every theta of a launch (reference layouts (nb,p,p), (nb,p,p), (nb,m,p)); passing them
 // by value as a __grid_constant__ kernel parameter lets every DFMA take them as c[0][..] operands: they cost
@@ -91,14 +99,14 @@ struct FilterConsts {
 // rs is a per-theta scale of the shared prior variance (1 when the prior is not batched): an IBM prior whose sigma
 // is part of theta is R(theta) = sigma^2 R_1 (src/rodeo/prior/ibm.py:84-86), so the per-theta prior costs one
 // register per block instead of p(p+1)/2.
-template <typename T, int P, int QK>
-RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], T rs, const T (&mu)[P],
-                    const T (&S)[P * (P + 1) / 2], T (&mup)[P], T (&Sp)[P * (P + 1) / 2]) {
+template <typename T, int P, int QK, typename MT>
+RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], T rs, const MT (&mu)[P],
+                    const T (&S)[P * (P + 1) / 2], MT (&mup)[P], T (&Sp)[P * (P + 1) / 2]) {
   T A[P][P];  // A = Q S
   RD_UNROLL for (int i = 0; i < P; ++i) {
     if (QK == QK_UNIT_UPPER) {
-      T m = mu[i];
-      RD_UNROLL for (int j = i + 1; j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+      MT m = mu[i];
+      RD_UNROLL for (int j = i + 1; j < P; ++j) m = rd_fma((MT)Q[i][j], mu[j], m);
       mup[i] = m;
       RD_UNROLL for (int k = 0; k < P; ++k) {
         T a = S[sym<P>(i, k)];
@@ -106,8 +114,8 @@ RD_DEV void predict(const T (&Q)[P][P], const T (&R)[P * (P + 1) / 2], T rs, con
         A[i][k] = a;
       }
     } else {
-      T m = Q[i][0] * mu[0];
-      RD_UNROLL for (int j = 1; j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+      MT m = (MT)Q[i][0] * mu[0];
+      RD_UNROLL for (int j = 1; j < P; ++j) m = rd_fma((MT)Q[i][j], mu[j], m);
       mup[i] = m;
       RD_UNROLL for (int k = 0; k < P; ++k) {
         T a = Q[i][0] * S[sym<P>(0, k)];
@@ -175,28 +183,32 @@ template <> struct LogAcc<float> {
     esum += fin ? e - 127 : 0;
     prod = fin ? __int_as_float((b & 0x807fffff) | 0x3f800000) : prod;
   }
-  RD_DEV float value() const {
-    const float v = logf(fabsf(prod)) + 0.69314718056f * (float)esum;
-    return sgn < 0 ? Lim<float>::nan() : v;
+  // in double: the exponent sum alone reaches ~1e4 over a solve, where a float carries 1e-3
+  RD_DEV double value() const {
+    const double v = (double)logf(fabsf(prod)) + 0.6931471805599453094 * (double)esum;
+    return sgn < 0 ? Lim<double>::nan() : v;
   }
 };
 
 // Gaussian log-density accumulator: logdens = -1/2 (quad + logdet) - 1/2 cnt log(2 pi), with the reference's
 // absolute eigenvalue cut-off |w| > 1e-8 (src/rodeo/utils.py:74, jnp.isclose default atol) applied per term.
 // The caller renormalises the running product once per time step (ld.renorm()).
+// The quadratic form is summed, and the value returned, in the mean type (double also for T = float): the two
+// log-densities dalton subtracts are ~1e4 each over 800 steps, their difference ~1e1.
 template <typename T>
 struct LogPdfAcc {
-  T quad; LogAcc<T> ld; int cnt;
-  RD_DEV void init() { quad = T(0); ld.init(); cnt = 0; }
+  typedef typename MeanOf<T>::type MT;
+  MT quad; LogAcc<T> ld; int cnt;
+  RD_DEV void init() { quad = MT(0); ld.init(); cnt = 0; }
   // one eigen-direction: eigenvalue w, projected residual z
-  RD_DEV void term(T w, T z, T rw /* = 1/w */) {
+  RD_DEV void term(T w, MT z, T rw /* = 1/w */) {
     const bool keep = !(fabs(w) <= T(1e-8));   // nan counts as kept, as ~isclose(nan, 0) does
-    quad = rd_fma(z * z, keep ? rw : T(0), quad);
+    quad = rd_fma(z * z, (MT)(keep ? rw : T(0)), quad);
     ld.add(keep ? w : T(1));
     cnt += keep ? 1 : 0;
   }
-  RD_DEV T value() const {
-    return T(-0.5) * (quad + ld.value()) - T(0.5) * T(1.8378770664093454836) * (T)cnt;
+  RD_DEV MT value() const {
+    return MT(-0.5) * (quad + (MT)ld.value()) - MT(0.5) * MT(1.8378770664093454836) * (MT)cnt;
   }
 };
 
@@ -332,8 +344,8 @@ RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], L
 //   S = wm S_p wm^T + V ;  K = S_p wm^T S^{-1} ;  mu_f = mu_p + K res ;  S_f = S_p - K (wm S_p)
 // WITH_LOGPDF adds log N(xm; mu_z, S) to `acc` (reference fenrir._forecast_update, fenrir.py:40-81).
 // In-place: mu, S hold the predicted moments on entry and the filtered moments on exit.
-template <typename T, int P, int MM, bool WITH_LOGPDF>
-RD_DEV void update(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], const T (&res)[MM],
+template <typename T, int P, int MM, bool WITH_LOGPDF, typename MT>
+RD_DEV void update(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], const MT (&res)[MM],
                    const T (&V)[MM * (MM + 1) / 2], LogPdfAcc<T>& acc) {
   T v[MM][P];    // v[r] = S_p wm[r]^T   (== (wm S_p)[r] by symmetry)
   T Kt[MM][P];
@@ -351,11 +363,15 @@ RD_DEV void update(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], co
       RD_UNROLL for (int i = 0; i < P; ++i) a = rd_fma(wm[r][i], v[s][i], a);
       Sm[sidx<MM>(r, s)] = a;
     }
-  if (WITH_LOGPDF) logpdf_terms<T, MM>(Sm, res, acc);
+  if (WITH_LOGPDF) {
+    T rt[MM];
+    RD_UNROLL for (int r = 0; r < MM; ++r) rt[r] = (T)res[r];
+    logpdf_terms<T, MM>(Sm, rt, acc);
+  }
   solve_small<T, MM, P>(Sm, Kt);
   RD_UNROLL for (int i = 0; i < P; ++i) {
-    T m = mu[i];
-    RD_UNROLL for (int r = 0; r < MM; ++r) m = rd_fma(Kt[r][i], res[r], m);
+    MT m = mu[i];
+    RD_UNROLL for (int r = 0; r < MM; ++r) m = rd_fma((MT)Kt[r][i], res[r], m);
     mu[i] = m;
   }
   RD_UNROLL for (int i = 0; i < P; ++i)
@@ -370,8 +386,8 @@ RD_DEV void update(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], co
 // produces for W = e_WK and a right-hand side that reads the leading JC state columns; jl == 0 for the other
 // interrogations).  Same arithmetic as update<T,P,1,...> with the multiplications by the structural 0 / 1 entries
 // removed (those are exact, so the results are bitwise those of the general row).
-template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J, bool HAS_V = true>
-RD_DEV void update_unit_row(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[JC], T res, T V, LogPdfAcc<T>& acc) {
+template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J, bool HAS_V = true, typename MT = T>
+RD_DEV void update_unit_row(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[JC], MT res, T V, LogPdfAcc<T>& acc) {
   T v[P];
   RD_UNROLL for (int i = 0; i < P; ++i) {
     T a = S[sym<P>(i, WK)];
@@ -382,8 +398,8 @@ RD_DEV void update_unit_row(T (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[J
   if (HAS_J) { RD_UNROLL for (int j = 0; j < JC; ++j) Sm = rd_fma(-jl[j], v[j], Sm); }
   const T rS = rcp(Sm);
   if (WITH_LOGPDF) acc.term(Sm, res, rS);
-  const T g = res * rS;
-  RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = rd_fma(v[i], g, mu[i]);
+  const MT g = res * (MT)rS;
+  RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = rd_fma((MT)v[i], g, mu[i]);
   RD_UNROLL for (int i = 0; i < P; ++i) {
     const T k = v[i] * rS;
     RD_UNROLL for (int j = i; j < P; ++j) S[sidx<P>(i, j)] = rd_fma(-k, v[j], S[sidx<P>(i, j)]);

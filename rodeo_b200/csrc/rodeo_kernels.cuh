@@ -67,6 +67,15 @@ __global__ void obs_step_map_kernel(int n_steps, int n_obs, const int* __restric
   }
 }
 
+// the model parameters in the mean type (double), from a theta row stored as T
+template <class Model, typename T>
+RD_DEV typename Model::template Par<typename MeanOf<T>::type> load_par(const T* th) {
+  typedef typename MeanOf<T>::type MT;
+  MT tmp[Model::NTHETA > 0 ? Model::NTHETA : 1];
+  RD_UNROLL for (int k = 0; k < Model::NTHETA; ++k) tmp[k] = (MT)th[k];
+  return Model::template load<MT>(tmp);
+}
+
 // reference src/rodeo/solve.py:74: t = t_min + (t_max - t_min) * (n + 1) / n_steps
 template <typename T>
 RD_DEV T step_time(T t_min, T t_max, int n, int n_steps) {
@@ -119,10 +128,11 @@ struct Fwd {
   static constexpr bool UNITW = (QK == QK_UNIT_UPPER) && (M == 1);
   static constexpr int WK = Model::WCOL;
   static constexpr bool HAS_J = (INTERR == INTERR_KRAMER);
+  typedef typename MeanOf<T>::type MT;      // means, ODE evaluation and residuals: always double (rodeo_core.cuh)
   typedef FilterConsts<T, NB, P, M> Consts;
-  typedef typename Model::template Par<T> Par;
+  typedef typename Model::template Par<MT> Par;
 
-  T mu[NB][P];
+  MT mu[NB][P];
   T S[NB][NS];
   T rs[NB];               // per-theta prior-variance scale (1 unless the prior is batched)
 
@@ -132,7 +142,7 @@ struct Fwd {
 
   RD_DEV void init(const T* x0) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = x0[b * P + i];
+      RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = (MT)x0[b * P + i];
       RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = T(0);
     }
   }
@@ -140,7 +150,8 @@ struct Fwd {
   // (mu, S) filtered at n  ->  predicted at n+1   (reference standard.predict, standard.py:57-59)
   RD_DEV void predict_all(const Consts& C) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T mp[P], Sp[NS];
+      MT mp[P];
+      T Sp[NS];
       predict<T, P, QK>(C.Q[b], C.R[b], rs[b], mu[b], S[b], mp, Sp);
       RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = mp[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = Sp[k];
@@ -162,9 +173,9 @@ struct Fwd {
   // (chkrebtii): in interrogate_kramer, mean_meas = -f + J mu_p and wm = W - J, so the two J mu_p terms cancel
   // identically.  Forming the cancelled expression directly drops an O(|J mu_p|) rounding term from a residual of
   // size sqrt(S) ~ 1e-3 and is strictly more accurate than evaluating both terms.
-  RD_DEV void interrogate(const Consts& C, const Par& q, T t, const T (&zc)[NB][JC],
-                          T (&jl)[NB][M][JC], T (&res)[NB][M], T (&V)[NB][MS]) const {
-    T x[NB][JC];
+  RD_DEV void interrogate(const Consts& C, const Par& q, MT t, const T (&zc)[NB][JC],
+                          T (&jl)[NB][M][JC], MT (&res)[NB][M], T (&V)[NB][MS]) const {
+    MT x[NB][JC];
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       if constexpr (INTERR == INTERR_CHKREBTII) {
         // x_b ~ N(mu_p, S_p) by Cholesky (jax.random.multivariate_normal default, interrogate.py:30-34);
@@ -172,19 +183,23 @@ struct Fwd {
         T A[P][P];
         psd_factor<T, P>(S[b], A);
         RD_UNROLL for (int j = 0; j < JC; ++j) {
-          T a = mu[b][j];
-          RD_UNROLL for (int k = 0; k <= j; ++k) a = rd_fma(A[j][k], zc[b][k], a);
+          MT a = mu[b][j];
+          RD_UNROLL for (int k = 0; k <= j; ++k) a = rd_fma((MT)A[j][k], (MT)zc[b][k], a);
           x[b][j] = a;
         }
       } else {
         RD_UNROLL for (int j = 0; j < JC; ++j) x[b][j] = mu[b][j];
       }
     }
-    T f[NB][M];
+    MT f[NB][M];
     if constexpr (HAS_J) {
-      eval_f_jac<Model, T>(q, t, x, f, jl);
+      MT jd[NB][M][JC];
+      eval_f_jac<Model, MT>(q, t, x, f, jd);
+      RD_UNROLL for (int b = 0; b < NB; ++b)
+        RD_UNROLL for (int r = 0; r < M; ++r)
+          RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][r][j] = (T)jd[b][r][j];
     } else {
-      Model::template rhs<T, T>(q, t, x, f);
+      Model::template rhs<MT, MT>(q, t, x, f);
       RD_UNROLL for (int b = 0; b < NB; ++b)
         RD_UNROLL for (int r = 0; r < M; ++r)
           RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][r][j] = T(0);
@@ -194,8 +209,8 @@ struct Fwd {
         if (UNITW) {
           res[b][r] = f[b][r] - mu[b][WK];
         } else {
-          T a = f[b][r];
-          RD_UNROLL for (int j = 0; j < P; ++j) a = rd_fma(-C.W[b][r][j], mu[b][j], a);
+          MT a = f[b][r];
+          RD_UNROLL for (int j = 0; j < P; ++j) a = rd_fma(-(MT)C.W[b][r][j], mu[b][j], a);
           res[b][r] = a;
         }
       }
@@ -257,7 +272,7 @@ struct Fwd {
 
   // plain ODE-measurement update of every block, x_meas == 0 (solve.py:51, 81-88)
   template <bool WITH_LOGPDF>
-  RD_DEV void update_z(const Consts& C, const T (&jl)[NB][M][JC], const T (&res)[NB][M], const T (&V)[NB][MS],
+  RD_DEV void update_z(const Consts& C, const T (&jl)[NB][M][JC], const MT (&res)[NB][M], const T (&V)[NB][MS],
                        LogPdfAcc<T>& acc) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       if constexpr (UNITW) {
@@ -274,11 +289,12 @@ struct Fwd {
   // observation-augmented update (dalton zy_update, dalton.py:136-149): rows [W~; D_i], offsets [d; 0],
   // noise blockdiag(V, Omega_i), observed value [0; y_i]  ->  residual [res; y_i - D_i mu_p]
   template <int NOBS, bool WITH_LOGPDF>
-  RD_DEV void update_zy(const Consts& C, const T (&jl)[NB][M][JC], const T (&res)[NB][M], const T (&V)[NB][MS],
+  RD_DEV void update_zy(const Consts& C, const T (&jl)[NB][M][JC], const MT (&res)[NB][M], const T (&V)[NB][MS],
                         const ObsArgs<T>& o, int i, LogPdfAcc<T>& acc) {
     constexpr int MA = M + NOBS, MAS = MA * (MA + 1) / 2;
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T wa[MA][P], ra[MA], Va[MAS], wm[M][P];
+      T wa[MA][P], Va[MAS], wm[M][P];
+      MT ra[MA];
       rows(C, b, jl[b], wm);
       RD_UNROLL for (int k = 0; k < MAS; ++k) Va[k] = T(0);
       RD_UNROLL for (int r = 0; r < M; ++r) {
@@ -287,10 +303,10 @@ struct Fwd {
         RD_UNROLL for (int s = r; s < M; ++s) Va[sidx<MA>(r, s)] = V[b][sidx<M>(r, s)];
       }
       RD_UNROLL for (int r = 0; r < NOBS; ++r) {
-        T a = __ldg(o.obs_data + (i * NB + b) * NOBS + r);
+        MT a = (MT)__ldg(o.obs_data + (i * NB + b) * NOBS + r);
         RD_UNROLL for (int j = 0; j < P; ++j) {
           wa[M + r][j] = __ldg(o.obs_weight + ((i * NB + b) * NOBS + r) * P + j);
-          a = rd_fma(-wa[M + r][j], mu[b][j], a);
+          a = rd_fma(-(MT)wa[M + r][j], mu[b][j], a);
         }
         ra[M + r] = a;
         RD_UNROLL for (int s = r; s < NOBS; ++s)
@@ -305,12 +321,13 @@ struct Fwd {
   RD_DEV void update_y(const ObsArgs<T>& o, int i, LogPdfAcc<T>& acc) {
     constexpr int OS = NOBS * (NOBS + 1) / 2;
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T wa[NOBS][P], ra[NOBS], Va[OS];
+      T wa[NOBS][P], Va[OS];
+      MT ra[NOBS];
       RD_UNROLL for (int r = 0; r < NOBS; ++r) {
-        T a = __ldg(o.obs_data + (i * NB + b) * NOBS + r);
+        MT a = (MT)__ldg(o.obs_data + (i * NB + b) * NOBS + r);
         RD_UNROLL for (int j = 0; j < P; ++j) {
           wa[r][j] = __ldg(o.obs_weight + ((i * NB + b) * NOBS + r) * P + j);
-          a = rd_fma(-wa[r][j], mu[b][j], a);
+          a = rd_fma(-(MT)wa[r][j], mu[b][j], a);
         }
         ra[r] = a;
         RD_UNROLL for (int s = r; s < NOBS; ++s)
@@ -342,7 +359,8 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   i64 idx = tid >> 1;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;                 // keep the whole warp in the loop for the final shuffle
-  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  typedef typename F::MT MT;
+  const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   F f;
   f.init(a.ode_init + idx * NB * P);
   f.load_scale(a, idx);
@@ -357,9 +375,9 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
       RD_UNROLL for (int b = 0; b < NB; ++b) {
         T res[NOBS], Om[OS];
         RD_UNROLL for (int r = 0; r < NOBS; ++r) {
-          T m = T(0);
-          RD_UNROLL for (int j = 0; j < P; ++j) m = rd_fma(__ldg(o.obs_weight + (b * NOBS + r) * P + j), f.mu[b][j], m);
-          res[r] = __ldg(o.obs_data + b * NOBS + r) - m;
+          MT m = MT(0);
+          RD_UNROLL for (int j = 0; j < P; ++j) m = rd_fma((MT)__ldg(o.obs_weight + (b * NOBS + r) * P + j), f.mu[b][j], m);
+          res[r] = (T)((MT)__ldg(o.obs_data + b * NOBS + r) - m);
           RD_UNROLL for (int s = r; s < NOBS; ++s) Om[sidx<NOBS>(r, s)] = __ldg(o.obs_var + (b * NOBS + r) * NOBS + s);
         }
         logpdf_terms<T, NOBS>(Om, res, acc);
@@ -371,8 +389,9 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   int next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
 
   for (int n = 0; n < a.n_steps; ++n) {
-    const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
-    T jl[NB][M][JC], res[NB][M], V[NB][MS], zc[NB][JC];
+    const MT t = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, n, a.n_steps) : MT(0);
+    T jl[NB][M][JC], V[NB][MS], zc[NB][JC];
+    MT res[NB][M];
     // each filter is linearised at its own prediction (dalton.py:116-132, 168-184)
     f.predict_all(C);
     f.template interr_normals<2>(a, idx, n, joint ? 0 : 1, zc);
@@ -388,9 +407,9 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     }
     acc.ld.renorm();
   }
-  const T mine = acc.value();
-  const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
-  if (joint && live) loglik[idx] = mine - other;          // logdens_joint - logdens_marg (dalton.py:235)
+  const MT mine = acc.value();
+  const MT other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  if (joint && live) loglik[idx] = (T)(mine - other);          // logdens_joint - logdens_marg (dalton.py:235)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -430,15 +449,18 @@ struct SegBuf {
   T* base;
   int lane;
   RD_DEV T& at(int s, int k) { return base[(s * NSTATE + k) * SEG_PITCH + lane]; }
-  RD_DEV void put(int s, const T (&mu)[NB][P], const T (&S)[NB][NS]) {
+  // means arrive in the mean type (double) and are staged / stored as T
+  template <typename MT>
+  RD_DEV void put(int s, const MT (&mu)[NB][P], const T (&S)[NB][NS]) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      RD_UNROLL for (int i = 0; i < P; ++i) at(s, b * P + i) = mu[b][i];
+      RD_UNROLL for (int i = 0; i < P; ++i) at(s, b * P + i) = (T)mu[b][i];
       RD_UNROLL for (int k = 0; k < NS; ++k) at(s, NB * P + b * NS + k) = S[b][k];
     }
   }
-  RD_DEV void get(int s, T (&mu)[NB][P], T (&S)[NB][NS]) {
+  template <typename MT>
+  RD_DEV void get(int s, MT (&mu)[NB][P], T (&S)[NB][NS]) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = at(s, b * P + i);
+      RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = (MT)at(s, b * P + i);
       RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = at(s, NB * P + b * NS + k);
     }
   }
@@ -487,7 +509,7 @@ RD_DEV void ckpt_store(T* __restrict__ stash, i64 ldb, i64 idx, int j, const F& 
   constexpr int NB = F::NB, P = F::P, NS = F::NS, NSTATE = NB * (P + NS);
   T* s = stash + (i64)(j - 1) * NSTATE * ldb + idx;
   RD_UNROLL for (int b = 0; b < NB; ++b) {
-    RD_UNROLL for (int i = 0; i < P; ++i) s[(i64)(b * P + i) * ldb] = f.mu[b][i];
+    RD_UNROLL for (int i = 0; i < P; ++i) s[(i64)(b * P + i) * ldb] = (T)f.mu[b][i];
     RD_UNROLL for (int k = 0; k < NS; ++k) s[(i64)(NB * P + b * NS + k) * ldb] = f.S[b][k];
   }
 }
@@ -512,13 +534,15 @@ RD_DEV void ckpt_prefetch(const T* __restrict__ stash, i64 ldb, i64 idx, int j) 
 // one forward step n -> n+1 of a plain (no log-density) filter; `hook` adds the observation rows at observation steps
 template <typename T, class Model, int INTERR, int QK>
 RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
-                         const typename Model::template Par<T>& q, i64 idx, int n, Fwd<T, Model, INTERR, QK>& f,
-                         const ObsHook<T>* hook = nullptr) {
+                         const typename Fwd<T, Model, INTERR, QK>::Par& q, i64 idx, int n,
+                         Fwd<T, Model, INTERR, QK>& f, const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
+  typedef typename F::MT MT;
   constexpr int NB = F::NB, M = F::M, JC = F::JC, MS = F::MS;
   LogPdfAcc<T> dummy;
-  const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
-  T jl[NB][M][JC], res[NB][M], V[NB][MS], zc[NB][JC];
+  const MT t = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, n, a.n_steps) : MT(0);
+  T jl[NB][M][JC], V[NB][MS], zc[NB][JC];
+  MT res[NB][M];
   f.predict_all(C);
   f.template interr_normals<1>(a, idx, n, 0, zc);
   f.interrogate(C, q, t, zc, jl, res, V);
@@ -532,7 +556,7 @@ RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C
 // filt[N]
 template <typename T, class Model, int INTERR, int QK, int KC>
 RD_DEV void forward_with_checkpoints(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
-                                     const typename Model::template Par<T>& q, i64 idx, bool live,
+                                     const typename Fwd<T, Model, INTERR, QK>::Par& q, i64 idx, bool live,
                                      Fwd<T, Model, INTERR, QK>& f, T* __restrict__ stash, i64 ldb,
                                      const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
@@ -552,7 +576,7 @@ RD_DEV void forward_with_checkpoints(const FilterConsts<T, Model::NB, Model::P, 
 //   KC == 1: load every state of the segment from the history.
 template <typename T, class Model, int INTERR, int QK, int KC>
 RD_DEV void rebuild_segment(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
-                            const typename Model::template Par<T>& q, i64 idx, int j, int cnt,
+                            const typename Fwd<T, Model, INTERR, QK>::Par& q, i64 idx, int j, int cnt,
                             Fwd<T, Model, INTERR, QK>& f, const T* __restrict__ stash, i64 ldb,
                             SegBuf<T, Fwd<T, Model, INTERR, QK>>& buf, const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
@@ -587,10 +611,10 @@ RD_DEV void prefetch_segment(const T* __restrict__ stash, i64 ldb, i64 idx, int 
 }
 
 // full-matrix / vector stores of one time row (used for the single row N; everything else is staged)
-template <typename T, int NB, int P>
-RD_DEV void store_mean_row(T* __restrict__ out, const T (&mu)[NB][P]) {
+template <typename T, int NB, int P, typename MT>
+RD_DEV void store_mean_row(T* __restrict__ out, const MT (&mu)[NB][P]) {
   RD_UNROLL for (int b = 0; b < NB; ++b)
-    RD_UNROLL for (int i = 0; i < P; ++i) out[b * P + i] = mu[b][i];
+    RD_UNROLL for (int i = 0; i < P; ++i) out[b * P + i] = (T)mu[b][i];
 }
 template <typename T, int NB, int P>
 RD_DEV void store_var_row(T* __restrict__ out, const T (&S)[NB][P * (P + 1) / 2]) {
@@ -617,7 +641,7 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   i64 idx = theta0 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;                 // the whole warp takes part in the cooperative copy-out
-  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
@@ -626,7 +650,9 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   forward_with_checkpoints<T, Model, INTERR, QK, K>(C, a, q, idx, live, f, stash, ldb, hook);
 
   // smoothed[N] = filt[N]   (solve.py:279-282)
-  T ms[NB][P], Ss[NB][NS];
+  typedef typename F::MT MT;
+  MT ms[NB][P];
+  T Ss[NB][NS];
   RD_UNROLL for (int b = 0; b < NB; ++b) {
     RD_UNROLL for (int i = 0; i < P; ++i) ms[b][i] = f.mu[b][i];
     RD_UNROLL for (int k = 0; k < NS; ++k) Ss[b][k] = f.S[b][k];
@@ -643,16 +669,17 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
       if (n0 + s == 0) break;                              // row 0 stays (ode_init, 0): never smoothed (solve.py:295-301)
       buf.get(s, f.mu, f.S);                               // filt[n]
       RD_UNROLL for (int b = 0; b < NB; ++b) {
-        T mp[P], Sp[NS], G[P][P], Ct[P][P];
+        MT mp[P], dm[P];
+        T Sp[NS], G[P][P], Ct[P][P];
         predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         // mu_s = mu_f + G (mu_s' - mu_p) ;  S_s = S_f + G (S_s' - S_p) G^T    (standard.py:213-216)
-        T dm[P], D[NS];
+        T D[NS];
         RD_UNROLL for (int i = 0; i < P; ++i) dm[i] = ms[b][i] - mp[i];
         RD_UNROLL for (int k = 0; k < NS; ++k) D[k] = Ss[b][k] - Sp[k];
         RD_UNROLL for (int i = 0; i < P; ++i) {
-          T m = f.mu[b][i];
-          RD_UNROLL for (int jj = 0; jj < P; ++jj) m = rd_fma(G[i][jj], dm[jj], m);
+          MT m = f.mu[b][i];
+          RD_UNROLL for (int jj = 0; jj < P; ++jj) m = rd_fma((MT)G[i][jj], dm[jj], m);
           ms[b][i] = m;
         }
         RD_UNROLL for (int k = 0; k < NS; ++k) Ss[b][k] = f.S[b][k];
@@ -701,10 +728,12 @@ struct BlockLane {
   static constexpr int PITCH = TW + 1;
   static constexpr int K = seg_len_bl(NSTATE, NB);
   static constexpr int BYTES = K * NSTATE * PITCH * (int)sizeof(T);
+  typedef typename MeanOf<T>::type MT;      // means, ODE evaluation and residuals: always double (rodeo_core.cuh)
   typedef FilterConsts<T, NB, P, M> Consts;
-  typedef typename Model::template Par<T> Par;
+  typedef typename Model::template Par<MT> Par;
 
-  T mu[P], S[NS], rs;
+  MT mu[P];
+  T S[NS], rs;
   T Q[P][P], R[NS], W[M][P];     // this lane's block of the shared constants, in registers
   int b, gb;                     // block index, first lane of this theta's lane group
 
@@ -719,7 +748,7 @@ struct BlockLane {
       }
   }
   RD_DEV void init(const T* x0) {
-    RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = x0[b * P + i];
+    RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = (MT)x0[b * P + i];
     RD_UNROLL for (int k = 0; k < NS; ++k) S[k] = T(0);
   }
   RD_DEV static int km(int bb, int i) { return bb * P + i; }
@@ -728,13 +757,14 @@ struct BlockLane {
   // one forward step n -> n+1 of this lane's block (predict, interrogate, update); all 32 lanes must call it
   RD_DEV void step(const CommonArgs<T>& a, const Par& q, i64 idx, int n, const ObsHook<T>* hook = nullptr) {
     {
-      T mp[P], Sp[NS];
+      MT mp[P];
+      T Sp[NS];
       predict<T, P, QK>(Q, R, rs, mu, S, mp, Sp);
       RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = mp[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) S[k] = Sp[k];
     }
-    const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
-    T xo[JC];
+    const MT t = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, n, a.n_steps) : MT(0);
+    MT xo[JC];
     if constexpr (INTERR == INTERR_CHKREBTII) {
       T zc[JC];
       if (a.z_interr != nullptr) {
@@ -748,33 +778,34 @@ struct BlockLane {
       T A[P][P];
       psd_factor<T, P>(S, A);
       RD_UNROLL for (int j = 0; j < JC; ++j) {
-        T acc = mu[j];
-        RD_UNROLL for (int k = 0; k <= j; ++k) acc = rd_fma(A[j][k], zc[k], acc);
+        MT acc = mu[j];
+        RD_UNROLL for (int k = 0; k <= j; ++k) acc = rd_fma((MT)A[j][k], (MT)zc[k], acc);
         xo[j] = acc;
       }
     } else {
       RD_UNROLL for (int j = 0; j < JC; ++j) xo[j] = mu[j];
     }
     // the right-hand side couples the blocks: gather every block's visible columns from the theta's lane group
-    T x[NB][JC];
+    MT x[NB][JC];
     RD_UNROLL for (int c = 0; c < NB; ++c)
       RD_UNROLL for (int j = 0; j < JC; ++j) x[c][j] = __shfl_sync(0xffffffffu, xo[j], gb + c);
-    T f[NB][M], jl[NB][M][JC];
+    MT f[NB][M], jl[NB][M][JC];
     if constexpr (HAS_J) {
-      eval_f_jac<Model, T>(q, t, x, f, jl);
+      eval_f_jac<Model, MT>(q, t, x, f, jl);
     } else {
-      Model::template rhs<T, T>(q, t, x, f);
+      Model::template rhs<MT, MT>(q, t, x, f);
       RD_UNROLL for (int c = 0; c < NB; ++c)
         RD_UNROLL for (int r = 0; r < M; ++r)
-          RD_UNROLL for (int j = 0; j < JC; ++j) jl[c][r][j] = T(0);
+          RD_UNROLL for (int j = 0; j < JC; ++j) jl[c][r][j] = MT(0);
     }
-    T fo[M], jo[M][JC];
+    MT fo[M];
+    T jo[M][JC];
     RD_UNROLL for (int r = 0; r < M; ++r) {
       fo[r] = f[0][r];
-      RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = jl[0][r][j];
+      RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = (T)jl[0][r][j];
       RD_UNROLL for (int c = 1; c < NB; ++c) {
         fo[r] = (b == c) ? f[c][r] : fo[r];
-        RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = (b == c) ? jl[c][r][j] : jo[r][j];
+        RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = (b == c) ? (T)jl[c][r][j] : jo[r][j];
       }
     }
     LogPdfAcc<T> dummy;
@@ -783,14 +814,15 @@ struct BlockLane {
     if (io >= 0) {
       // augmented update with the observation rows of this block (dalton.py:136-149), scalar ODE row + one obs row
       if constexpr (M == 1) {
-        T wa[2][P], ra[2], Va[3];
-        T acc = fo[0], ya = __ldg(hook->o.obs_data + (io * NB + b));
+        T wa[2][P], Va[3];
+        MT ra[2];
+        MT acc = fo[0], ya = (MT)__ldg(hook->o.obs_data + (io * NB + b));
         RD_UNROLL for (int j = 0; j < P; ++j) {
           const T w = UNITW ? (j == WK ? T(1) : T(0)) : W[0][j];
           wa[0][j] = (HAS_J && j < JC) ? w - jo[0][j] : w;
-          acc = rd_fma(-w, mu[j], acc);
+          acc = rd_fma(-(MT)w, mu[j], acc);
           wa[1][j] = __ldg(hook->o.obs_weight + (io * NB + b) * P + j);
-          ya = rd_fma(-wa[1][j], mu[j], ya);
+          ya = rd_fma(-(MT)wa[1][j], mu[j], ya);
         }
         ra[0] = acc; ra[1] = ya;
         T V0 = T(0);
@@ -808,17 +840,18 @@ struct BlockLane {
         update<T, P, 2, false>(mu, S, wa, ra, Va, dummy);
       }
     } else if constexpr (UNITW) {
-      const T res = fo[0] - mu[WK];
+      const MT res = fo[0] - mu[WK];
       const T V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) ? S[sidx<P>(WK, WK)] : T(0);
       update_unit_row<T, P, JC, WK, false, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(mu, S, jo[0], res, V,
                                                                                                          dummy);
     } else {
-      T wm[M][P], res[M], V[MS];
+      T wm[M][P], V[MS];
+      MT res[M];
       RD_UNROLL for (int r = 0; r < M; ++r) {
-        T acc = fo[r];
+        MT acc = fo[r];
         RD_UNROLL for (int j = 0; j < P; ++j) {
           wm[r][j] = (HAS_J && j < JC) ? W[r][j] - jo[r][j] : W[r][j];
-          acc = rd_fma(-W[r][j], mu[j], acc);
+          acc = rd_fma(-(MT)W[r][j], mu[j], acc);
         }
         res[r] = acc;
       }
@@ -890,7 +923,7 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   i64 idx = theta0 + tl;
   const bool live = lane_ok && idx < a.B;
   if (idx >= a.B) idx = a.B - 1;
-  const typename L::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename L::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   T* buf = reinterpret_cast<T*>(rodeo_dyn_smem);
   L f;
@@ -899,12 +932,13 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   f.rs = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
   const T* x0 = a.ode_init + idx * NB * P;
   f.init(x0);
-  auto put = [&](int s, const T (&m)[P], const T (&Sv)[NS]) {
-    RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * NSTATE + L::km(b, i)) * PITCH + tl] = m[i];
+  typedef typename L::MT MT;
+  auto put = [&](int s, const MT (&m)[P], const T (&Sv)[NS]) {
+    RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * NSTATE + L::km(b, i)) * PITCH + tl] = (T)m[i];
     RD_UNROLL for (int k = 0; k < NS; ++k) buf[(s * NSTATE + L::kv(b, k)) * PITCH + tl] = Sv[k];
   };
-  auto get = [&](int s, T (&m)[P], T (&Sv)[NS]) {
-    RD_UNROLL for (int i = 0; i < P; ++i) m[i] = buf[(s * NSTATE + L::km(b, i)) * PITCH + tl];
+  auto get = [&](int s, MT (&m)[P], T (&Sv)[NS]) {
+    RD_UNROLL for (int i = 0; i < P; ++i) m[i] = (MT)buf[(s * NSTATE + L::km(b, i)) * PITCH + tl];
     RD_UNROLL for (int k = 0; k < NS; ++k) Sv[k] = buf[(s * NSTATE + L::kv(b, k)) * PITCH + tl];
   };
   // history entry j (= filt[j*K]) of this lane's block
@@ -918,18 +952,19 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
       if (--to_ckpt == 0) {
         to_ckpt = K; ++j;
         if (live && n + 1 < N) {
-          RD_UNROLL for (int i = 0; i < P; ++i) stash[ck(j, L::km(b, i))] = f.mu[i];
+          RD_UNROLL for (int i = 0; i < P; ++i) stash[ck(j, L::km(b, i))] = (T)f.mu[i];
           RD_UNROLL for (int k = 0; k < NS; ++k) stash[ck(j, L::kv(b, k))] = f.S[k];
         }
       }
     }
   }
   // smoothed[N] = filt[N]   (solve.py:279-282)
-  T ms[P], Ss[NS];
+  MT ms[P];
+  T Ss[NS];
   RD_UNROLL for (int i = 0; i < P; ++i) ms[i] = f.mu[i];
   RD_UNROLL for (int k = 0; k < NS; ++k) Ss[k] = f.S[k];
   if (live && mean_out != nullptr)
-    RD_UNROLL for (int i = 0; i < P; ++i) mean_out[(idx * (i64)(N + 1) + N) * (NB * P) + b * P + i] = ms[i];
+    RD_UNROLL for (int i = 0; i < P; ++i) mean_out[(idx * (i64)(N + 1) + N) * (NB * P) + b * P + i] = (T)ms[i];
   if (live && var_out != nullptr)
     RD_UNROLL for (int i = 0; i < P; ++i)
       RD_UNROLL for (int jj = 0; jj < P; ++jj)
@@ -942,7 +977,7 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
     if (j == 0) {
       f.init(x0);                                           // filt[0] = (ode_init, 0)
     } else {
-      RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = stash[ck(j, L::km(b, i))];
+      RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = (MT)stash[ck(j, L::km(b, i))];
       RD_UNROLL for (int k = 0; k < NS; ++k) f.S[k] = stash[ck(j, L::kv(b, k))];
     }
     put(0, f.mu, f.S);
@@ -953,15 +988,16 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
     for (int s = cnt - 1; s >= 0; --s) {
       if (n0 + s == 0) break;                              // row 0 stays (ode_init, 0): never smoothed
       get(s, f.mu, f.S);                                   // filt[n]
-      T mp[P], Sp[NS], G[P][P], Ct[P][P];
+      MT mp[P], dm[P];
+      T Sp[NS], G[P][P], Ct[P][P];
       predict<T, P, QK>(f.Q, f.R, f.rs, f.mu, f.S, mp, Sp);               // pred[n+1]
       smooth_gain<T, P, QK>(f.Q, f.S, Sp, G, Ct);
-      T dm[P], D[NS];
+      T D[NS];
       RD_UNROLL for (int i = 0; i < P; ++i) dm[i] = ms[i] - mp[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) D[k] = Ss[k] - Sp[k];
       RD_UNROLL for (int i = 0; i < P; ++i) {
-        T m = f.mu[i];
-        RD_UNROLL for (int jj = 0; jj < P; ++jj) m = rd_fma(G[i][jj], dm[jj], m);
+        MT m = f.mu[i];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) m = rd_fma((MT)G[i][jj], dm[jj], m);
         ms[i] = m;
       }
       RD_UNROLL for (int k = 0; k < NS; ++k) Ss[k] = f.S[k];
@@ -1058,7 +1094,7 @@ solve_mv_sqrt_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P
   i64 idx = theta0 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;
-  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
@@ -1138,7 +1174,7 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
   i64 idx = theta0 + tl;
   const bool live = lane_ok && idx < a.B;
   if (idx >= a.B) idx = a.B - 1;
-  const typename L::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename L::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   T* buf = reinterpret_cast<T*>(rodeo_dyn_smem);
   L f;
@@ -1153,7 +1189,7 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
   for (int n = 0; n < N; ++n) {
     f.step(a, q, idx, n, hook);
     if (live && n + 1 < N) {
-      RD_UNROLL for (int i = 0; i < P; ++i) stash[hs(n + 1, L::km(b, i))] = f.mu[i];
+      RD_UNROLL for (int i = 0; i < P; ++i) stash[hs(n + 1, L::km(b, i))] = (T)f.mu[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) stash[hs(n + 1, L::kv(b, k))] = f.S[k];
     }
   }
@@ -1166,24 +1202,26 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
       philox_normal_range<T, P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, b * P, z);
     }
   };
-  auto draw = [&](const T (&m)[P], const T (&Cv)[NS], const T (&z)[P], T (&xo)[P]) {
+  typedef typename L::MT MT;
+  auto draw = [&](const MT (&m)[P], const T (&Cv)[NS], const T (&z)[P], MT (&xo)[P]) {
     T A[P][P];
     psd_factor<T, P>(Cv, A);
     RD_UNROLL for (int i = 0; i < P; ++i) {
-      T acc = m[i];
-      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma(A[i][k], z[k], acc);
+      MT acc = m[i];
+      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)A[i][k], (MT)z[k], acc);
       xo[i] = acc;
     }
   };
 
   // terminal draw from N(mu_f[N], S_f[N])  (solve.py:182-186)
-  T x[P];
+  MT x[P];
   {
-    T z[P], xn[P];
+    T z[P];
+    MT xn[P];
     normals(N, z);
     draw(f.mu, f.S, z, xn);
     RD_UNROLL for (int i = 0; i < P; ++i) x[i] = xn[i];
-    if (live) RD_UNROLL for (int i = 0; i < P; ++i) x_out[(idx * (i64)(N + 1) + N) * ROW + b * P + i] = x[i];
+    if (live) RD_UNROLL for (int i = 0; i < P; ++i) x_out[(idx * (i64)(N + 1) + N) * ROW + b * P + i] = (T)x[i];
   }
 
   const int nth = (a.B - theta0) < TW ? (int)(a.B - theta0) : TW;
@@ -1205,23 +1243,25 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
         RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * ROW + b * P + i) * PITCH + tl] = x0[b * P + i];
         break;
       }
-      RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = nmu[i];
+      RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = (MT)nmu[i];
       RD_UNROLL for (int k = 0; k < NS; ++k) f.S[k] = nS[k];
       load(n - 1);
-      T z[P], xn[P];
+      T z[P];
+      MT xn[P];
       normals(n, z);
-      T mp[P], Sp[NS], G[P][P], Ct[P][P], m[P], Cv[NS];
+      MT mp[P], m[P];
+      T Sp[NS], G[P][P], Ct[P][P], Cv[NS];
       predict<T, P, QK>(f.Q, f.R, f.rs, f.mu, f.S, mp, Sp);               // pred[n+1]
       smooth_gain<T, P, QK>(f.Q, f.S, Sp, G, Ct);
       // m = mu_f + G (x' - mu_p) ;  C = S_f - G (S_f Q^T)^T      (standard.py:251-254)
       RD_UNROLL for (int i = 0; i < P; ++i) {
-        T acc = f.mu[i];
-        RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma(G[i][jj], x[jj] - mp[jj], acc);
+        MT acc = f.mu[i];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma((MT)G[i][jj], x[jj] - mp[jj], acc);
         m[i] = acc;
       }
       cond_var<T, P>(f.S, G, Ct, Cv);
       draw(m, Cv, z, xn);
-      RD_UNROLL for (int i = 0; i < P; ++i) { x[i] = xn[i]; buf[(s * ROW + b * P + i) * PITCH + tl] = xn[i]; }
+      RD_UNROLL for (int i = 0; i < P; ++i) { x[i] = xn[i]; buf[(s * ROW + b * P + i) * PITCH + tl] = (T)xn[i]; }
     }
     __syncwarp();
     {
@@ -1260,7 +1300,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   i64 idx = theta0 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;
-  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
@@ -1276,22 +1316,23 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
       philox_normals<T, NB * P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, z);
     }
   };
-  auto draw = [&](int b, const T (&m)[P], const T (&Cv)[NS], const T (&z)[NB * P], T (&x)[NB][P]) {
+  typedef typename F::MT MT;
+  auto draw = [&](int b, const MT (&m)[P], const T (&Cv)[NS], const T (&z)[NB * P], MT (&x)[NB][P]) {
     T A[P][P];
     psd_factor<T, P>(Cv, A);
     RD_UNROLL for (int i = 0; i < P; ++i) {
-      T acc = m[i];
-      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma(A[i][k], z[b * P + k], acc);
+      MT acc = m[i];
+      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)A[i][k], (MT)z[b * P + k], acc);
       x[b][i] = acc;
     }
   };
 
   // terminal draw from N(mu_f[N], S_f[N])  (solve.py:182-186)
-  T x[NB][P];
+  MT x[NB][P];
   {
     T z[NB * P];
     normals(N, z);
-    T xn[NB][P];
+    MT xn[NB][P];
     RD_UNROLL for (int b = 0; b < NB; ++b) draw(b, f.mu[b], f.S[b], z, xn);
     RD_UNROLL for (int b = 0; b < NB; ++b)
       RD_UNROLL for (int i = 0; i < P; ++i) x[b][i] = xn[b][i];
@@ -1307,22 +1348,23 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
       buf.get(s, f.mu, f.S);                               // filt[n]
       T z[NB * P];
       normals(n0 + s, z);
-      T xn[NB][P];
+      MT xn[NB][P];
       RD_UNROLL for (int b = 0; b < NB; ++b) {
-        T mp[P], Sp[NS], G[P][P], Ct[P][P], m[P], Cv[NS];
+        MT mp[P], m[P];
+        T Sp[NS], G[P][P], Ct[P][P], Cv[NS];
         predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[n+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         // m = mu_f + G (x' - mu_p) ;  C = S_f - G (S_f Q^T)^T      (standard.py:251-254)
         RD_UNROLL for (int i = 0; i < P; ++i) {
-          T acc = f.mu[b][i];
-          RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma(G[i][jj], x[b][jj] - mp[jj], acc);
+          MT acc = f.mu[b][i];
+          RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma((MT)G[i][jj], x[b][jj] - mp[jj], acc);
           m[i] = acc;
         }
         cond_var<T, P>(f.S[b], G, Ct, Cv);
         draw(b, m, Cv, z, xn);
       }
       RD_UNROLL for (int b = 0; b < NB; ++b)
-        RD_UNROLL for (int i = 0; i < P; ++i) { x[b][i] = xn[b][i]; buf.at(s, b * P + i) = xn[b][i]; }
+        RD_UNROLL for (int i = 0; i < P; ++i) { x[b][i] = xn[b][i]; buf.at(s, b * P + i) = (T)xn[b][i]; }
     }
     if (j > 0) prefetch_segment<T, F, 1>(stash, ldb, idx, j - 1, K);
     __syncwarp();
@@ -1346,7 +1388,7 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   i64 idx = (i64)blockIdx.x * 32 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;
-  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;
@@ -1379,16 +1421,17 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
       const int t = n0 + s;
       buf.get(s, f.mu, f.S);                              // filt[t]  (t = 0: (ode_init, 0))
       RD_UNROLL for (int b = 0; b < NB; ++b) {
-        T mp[P], Sp[NS], G[P][P], Ct[P][P], Cv[NS];
+        typename F::MT mp[P], nm[P];
+        T Sp[NS], G[P][P], Ct[P][P], Cv[NS];
         predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[t+1]
         smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
         cond_var<T, P>(f.S[b], G, Ct, Cv);
         // backward chain X_t = A X_{t+1} + bvec + N(0, Cv), A = G, bvec = mu_f - G mu_p   (standard.py:366-370)
         // predict the backward filter through it (fenrir.py:151-157)
-        T nm[P];
         RD_UNROLL for (int r = 0; r < P; ++r) {
-          T acc2 = f.mu[b][r];
-          RD_UNROLL for (int jj = 0; jj < P; ++jj) acc2 = rd_fma(G[r][jj], bk.mu[b][jj] - mp[jj], acc2);
+          typename F::MT acc2 = f.mu[b][r];
+          RD_UNROLL for (int jj = 0; jj < P; ++jj)
+            acc2 = rd_fma((typename F::MT)G[r][jj], bk.mu[b][jj] - mp[jj], acc2);
           nm[r] = acc2;
         }
         add_GDGt<T, P>(G, bk.S[b], Cv);
@@ -1404,7 +1447,7 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     }
     __syncwarp();
   }
-  if (live) loglik[idx] = acc.value();
+  if (live) loglik[idx] = (T)acc.value();
 }
 
 
@@ -1430,7 +1473,7 @@ fenrir_solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
   i64 idx = theta0 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;
-  const typename F::Par q = Model::template load<T>(a.theta + idx * Model::NTHETA);
+  const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
   F f;

@@ -428,15 +428,15 @@ def test_nvrtc_reports_compile_errors(rb):
 
 # ---- float32 instantiation -----------------------------------------------------------------------------------------
 def test_float32_solve_mv_and_dalton(rb):
-    """float32 kernels against the FLOAT64 oracle (i.e. against the truth, not against another float32 run).
-    BASELINE's float32 gate is 1e-5 relative to the reference's float32 result; SURVEY App. C measured that a plain
-    float32 evaluation of the README problem is itself 1.4e-5 away from float64 -- the covariance-form recursion
-    (cond(S_pred) ~ 1e6..1e8, update residual ~1e-3 formed from O(1) terms) sits AT that budget in float32, so two
-    faithful float32 implementations differ by about that much.  Gates here, against float64 truth: posterior mean
-    3e-5 (N=200) and 1e-4 (README length N=800); variances 2e-3; dalton log-likelihood 1e-3."""
+    """float32 kernels against the FLOAT64 oracle (i.e. against the truth, not against another float32 run), at
+    BASELINE's float32 gate of 1e-5.  A plain float32 evaluation of the reference algorithm drifts 1.4e-5 (N=200) to
+    4e-5 (N=800) from float64: the state x integrates its derivative over N steps and the update
+    residual ~1e-3 is a difference of O(1) numbers.  The *_f32 kernels therefore carry the block means, the ODE
+    evaluation, the residuals and the log-density sums in double (MeanOf<T>, rodeo_core.cuh) and only the
+    covariances / gains -- the bulk of the arithmetic -- in float.  Measured: mean 5.9e-6, var 1.4e-6, dalton 7.5e-6."""
     import torch
     kr = rb.interrogate.interrogate_kramer
-    for N, tm, tol_m in ((200, 10.0, 3e-5), (800, 40.0, 1e-4)):
+    for N, tm, tol_m in ((200, 10.0, 1e-5), (800, 40.0, 1e-5)):
         pr = P.fitz_problem(64, n_steps=N, t_max=tm, seed=31)
         th32, X32 = pr["theta"].astype(np.float32), pr["X0"].astype(np.float32)
         m, v = rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], X32, 0.0, tm, N, kr,
@@ -446,7 +446,7 @@ def test_float32_solve_mv_and_dalton(rb):
                               orc.interrogate_kramer, (pr["Q"], pr["R"]), th32.astype(np.float64))
         em, ev = P.maxnorm_rel(_np(m), om), P.maxnorm_rel(_np(v), ov)
         print(f"float32 N={N}: mean {em:.2e} var {ev:.2e}")
-        assert em < tol_m and ev < 2e-3
+        assert em < tol_m and ev < 1e-5
     pr = P.fitz_problem(64, n_steps=200, t_max=10.0, seed=32)
     ob = P.fitz_obs(pr, None, n_obs=11)
     th32, X32 = pr["theta"].astype(np.float32), pr["X0"].astype(np.float32)
@@ -457,7 +457,7 @@ def test_float32_solve_mv_and_dalton(rb):
                       ob["obs_times"], ob["obs_weight"], ob["obs_var"])
     e = ll_err(_np(ll).astype(np.float64), want)
     print(f"float32 dalton: {e:.2e}")
-    assert ll.dtype == torch.float32 and e < 1e-3
+    assert ll.dtype == torch.float32 and e < 1e-5
 
 
 # ---- per-theta prior ---------------------------------------------------------------------------------------------------
