@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/reference_vectors.npz by RUNNING THE REFERENCE'S OWN SOURCE.
+
+The unmodified files under /root/reference/src/rodeo (mlysy/rodeo v1.1.3) are imported and executed with
+``oracle/jaxshim`` -- a NumPy stand-in for the handful of jax entry points they use -- first on sys.path (JAX itself
+is not installed in this image and there is no network).  Every output below therefore comes from the reference's
+own solve.py / interrogate.py / kalmantv/*.py / inference/*.py / prior/ibm.py / utils.py control flow and formulas,
+evaluated in float64 through the same LAPACK routines jaxlib's CPU backend calls.  See the shim's docstring for what
+this does and does not pin (not pinned: XLA's operation order, JAX's threefry streams).
+
+This script can only run where /root/reference exists (the build container); the vectors it writes are committed and
+are what tests/test_reference_golden.py checks the oracle (CPU) and the CUDA path (GPU box) against.
+
+    python tests/golden/make_reference_golden.py
+"""
+import functools
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("RODEO_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.dirname(HERE))
+import problems as P  # noqa: E402
+
+
+def _import_reference():
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "jaxshim"), os.path.join(REF, "src")]
+    warnings.simplefilter("ignore", SyntaxWarning)
+    import jax
+    import jax.numpy as jnp
+    import rodeo
+    import importlib
+    # `import rodeo.inference.dalton as m` would bind the FUNCTION that rodeo/inference/__init__.py re-exports
+    rdalton = importlib.import_module("rodeo.inference.dalton")
+    rfenrir = importlib.import_module("rodeo.inference.fenrir")
+    import rodeo.kalmantv.standard as rstd
+    import rodeo.kalmantv.square_root as rsqrt
+    return jax, jnp, rodeo, rdalton, rfenrir, rstd, rsqrt
+
+
+def build():
+    jax, jnp, rodeo, rdalton, rfenrir, rstd, rsqrt = _import_reference()
+    A = np.asarray
+    out = {}
+
+    # ---- ODE right-hand sides exactly as the reference's README / docs write them ---------------------------------
+    def fitz_fun(X, t, **params):                      # README.md:92-99
+        a, b, c = params["theta"]
+        V, R = X[:, 0]
+        return jnp.array([[c * (V - V * V * V / 3 + R)],
+                          [-1 / c * (V - a + b * R)]])
+
+    def lorenz(X_t, t, theta):                         # docs/examples/lorenz.md:95-101
+        rho, sigma, beta = theta
+        x, y, z = X_t[:, 0]
+        dx = -sigma * x + sigma * y
+        dy = rho * x - y - x * z
+        dz = -beta * z + x * y
+        return jnp.array([[dx], [dy], [dz]])
+
+    def higher_fun(x, t, **params):                    # docs/examples/higher_order.md:47-58, with theta = (omega, k)
+        w, k = params["theta"]
+        return jnp.array([[jnp.sin(w * t) - k * x[0, 0]]])
+
+    kramer = rodeo.interrogate.interrogate_kramer
+    key = jax.random.PRNGKey(0)
+
+    def per_theta(fn, pr, **extra):
+        """call an un-batched reference function once per theta and stack (the reference leaves the theta batch to
+        the user's jit(vmap))"""
+        res = []
+        for i in range(pr["theta"].shape[0]):
+            r = fn(jnp.array(pr["X0"][i]), jnp.array(pr["theta"][i]), **extra)
+            res.append(r)
+        if isinstance(res[0], tuple):
+            return tuple(np.stack([A(r[k]) for r in res]) for k in range(len(res[0])))
+        return np.stack([A(r) for r in res])
+
+    def save_problem(tag, pr, ob=None):
+        for k in ("W", "X0", "theta", "Q", "R"):
+            out[f"{tag}_in_{k}"] = pr[k]
+        if ob is not None:
+            for k, v in ob.items():
+                out[f"{tag}_in_{k}"] = v
+
+    # ===============================================================================================================
+    # FitzHugh-Nagumo, 3 thetas, N = 60 on [0, 3], observations at t = 0, 1, 2, 3
+    # ===============================================================================================================
+    pr = P.fitz_problem(3, n_steps=60, t_max=3.0, seed=123)
+    ob = P.fitz_obs(pr, None, n_obs=4)
+    save_problem("fitz", pr, ob)
+    # the reference's own helpers must reproduce the inputs: first_order_pad / ibm_init (utils.py:80-102, ibm.py:65-88)
+    W, pad = rodeo.utils.first_order_pad(fitz_fun, 2, 3)
+    out["fitz_ref_W"] = A(W)
+    out["fitz_ref_X0"] = np.stack([A(pad(jnp.array(pr["x0"][i]), 0.0, theta=jnp.array(pr["theta"][i])))
+                                   for i in range(3)])
+    Qr, Rr = rodeo.prior.ibm_init(dt=3.0 / 60, n_deriv=3, sigma=jnp.array([0.1, 0.1]))
+    out["fitz_ref_Q"], out["fitz_ref_R"] = A(Qr), A(Rr)
+    pp = (jnp.array(pr["Q"]), jnp.array(pr["R"]))
+    common = dict(ode_fun=fitz_fun, ode_weight=jnp.array(pr["W"]), t_min=0.0, t_max=3.0, n_steps=60, prior_pars=pp)
+    obs = dict(obs_data=jnp.array(ob["obs_data"]), obs_times=jnp.array(ob["obs_times"]),
+               obs_weight=jnp.array(ob["obs_weight"]), obs_var=jnp.array(ob["obs_var"]))
+
+    for name in ("kramer", "schober", "rodeo"):
+        interr = getattr(rodeo.interrogate, "interrogate_" + name)
+        m, v = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=interr, theta=th, **common), pr)
+        out[f"fitz_{name}_mean"], out[f"fitz_{name}_var"] = m, v
+
+    # interrogate_chkrebtii: the shim logs the standard normals of every jax.random.multivariate_normal call, in call
+    # order (step-major, block-minor: interrogate.py:23-34 under solve.py's scan)
+    chk = functools.partial(rodeo.interrogate.interrogate_chkrebtii, kalman_type="standard")
+    zs, ms, vs = [], [], []
+    for i in range(3):
+        del jax.random.DRAW_LOG[:]
+        m, v = rodeo.solve_mv(key=jax.random.PRNGKey(10 + i), ode_init=jnp.array(pr["X0"][i]), interrogate=chk,
+                              theta=jnp.array(pr["theta"][i]), **common)
+        z = np.stack([e[2] for e in jax.random.DRAW_LOG])
+        assert z.shape == (60 * 2, 3) and all(e[1] == "mvn-cholesky" for e in jax.random.DRAW_LOG)
+        zs.append(z.reshape(60, 2, 3)); ms.append(A(m)); vs.append(A(v))
+    out["fitz_chkrebtii_z"], out["fitz_chkrebtii_mean"], out["fitz_chkrebtii_var"] = np.stack(zs), np.stack(ms), np.stack(vs)
+
+    # solve_sim (kramer forward pass => the only draws are the smoother's, method='svd': solve.py:179-186)
+    zs, xs = [], []
+    for i in range(3):
+        del jax.random.DRAW_LOG[:]
+        x = rodeo.solve_sim(key=jax.random.PRNGKey(20 + i), ode_init=jnp.array(pr["X0"][i]), interrogate=kramer,
+                            theta=jnp.array(pr["theta"][i]), **common)
+        log = jax.random.DRAW_LOG
+        assert len(log) == 60 and all(e[1] == "mvn-svd" and e[2].shape == (2, 3) for e in log)
+        z = np.zeros((61, 2, 3))
+        z[60] = log[0][2]                               # terminal draw first, then t = N-1 .. 1 (reverse scan)
+        for k in range(1, 60):
+            z[60 - k] = log[k][2]
+        zs.append(z); xs.append(A(x))
+    out["fitz_sim_z"], out["fitz_sim_x"] = np.stack(zs), np.stack(xs)
+
+    out["fitz_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs), pr)
+    out["fitz_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs), pr)
+
+    def obs_loglik(obs_data, ode_data, **params):      # Gaussian measurement model of docs/examples/parameter.md:333-340
+        return jnp.sum(jax.scipy.stats.norm.logpdf(obs_data[:, :, 0], ode_data[:, :, 0], np.sqrt(0.005)))
+    ll, Xt = per_theta(lambda X0, th: rodeo.inference.basic(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, obs_data=obs["obs_data"], obs_times=obs["obs_times"],
+        obs_loglik=obs_loglik, **common), pr)
+    out["fitz_basic"], out["fitz_basic_Xt"] = ll, Xt
+
+    m, v = per_theta(lambda X0, th: rdalton.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs), pr)
+    out["fitz_dalton_mean"], out["fitz_dalton_var"] = m, v
+    m, v = per_theta(lambda X0, th: rfenrir.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs), pr)
+    out["fitz_fenrir_mean"], out["fitz_fenrir_var"] = m, v
+
+    # observations that do NOT start on t_min and do not end on t_max (dalton.py:207-215 `_no_logy0`, fenrir's
+    # terminal `_no_obs` branch, fenrir.py:196-220), and fall between grid points (left insertion of searchsorted)
+    ob2 = {k: v[1:3] for k, v in ob.items()}
+    ob2["obs_times"] = np.array([0.97, 2.04])
+    save_problem("fitzmid", pr, ob2)
+    obs2 = {k: jnp.array(v) for k, v in ob2.items()}
+    out["fitzmid_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs2), pr)
+    out["fitzmid_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs2), pr)
+
+    # square-root Kalman family (solve.py:236-241 with kalman_type="square-root"; docs/examples/higher_order.md:108-112)
+    chol = jax.vmap(jnp.linalg.cholesky)(pp[1])
+    common_sq = dict(common, prior_pars=(pp[0], chol))
+    m, L = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th,
+                                                   kalman_type="square-root", **common_sq), pr)
+    out["fitz_sqrt_mean"], out["fitz_sqrt_var"] = m, L @ np.swapaxes(L, -1, -2)      # compare L L^T (QR sign freedom)
+
+    # ===============================================================================================================
+    # BASELINE configs[0]: the README walkthrough itself (single theta, N = 800 on [0, 40])
+    # ===============================================================================================================
+    pr1 = P.fitz_problem(1, jitter=False)
+    ob1 = P.fitz_obs(pr1, None, n_obs=41)
+    save_problem("readme", pr1, ob1)
+    common1 = dict(ode_fun=fitz_fun, ode_weight=jnp.array(pr1["W"]), t_min=0.0, t_max=40.0, n_steps=800,
+                   prior_pars=(jnp.array(pr1["Q"]), jnp.array(pr1["R"])))
+    obs1 = {k: jnp.array(v) for k, v in ob1.items()}
+    m, v = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **common1), pr1)
+    out["readme_mean"], out["readme_var"] = m, v
+    out["readme_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common1, **obs1), pr1)
+    out["readme_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common1, **obs1), pr1)
+
+    # ===============================================================================================================
+    # Lorenz63 (docs/examples/lorenz.md), 2 thetas, N = 100 on [0, 0.5]; sigma = 5e7 as in the docs
+    # ===============================================================================================================
+    prl = P.lorenz_problem(2, n_steps=100, t_max=0.5, seed=7)
+    save_problem("lorenz", prl)
+    commonl = dict(ode_fun=lorenz, ode_weight=jnp.array(prl["W"]), t_min=0.0, t_max=0.5, n_steps=100,
+                   prior_pars=(jnp.array(prl["Q"]), jnp.array(prl["R"])))
+    m, v = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **commonl), prl)
+    out["lorenz_mean"], out["lorenz_var"] = m, v
+
+    # ===============================================================================================================
+    # second-order ODE x'' = sin(w t) - k x  (docs/examples/higher_order.md), n_block = 1, n_bstate = 4
+    # ===============================================================================================================
+    pr2 = P.second_order_problem(2, n_steps=80, t_max=4.0, sigma=0.1, seed=123)
+    ob2 = P.second_order_obs(pr2, n_obs=5)
+    save_problem("so", pr2, ob2)
+    common2 = dict(ode_fun=higher_fun, ode_weight=jnp.array(pr2["W"]), t_min=0.0, t_max=4.0, n_steps=80,
+                   prior_pars=(jnp.array(pr2["Q"]), jnp.array(pr2["R"])))
+    obs2 = {k: jnp.array(v) for k, v in ob2.items()}
+    m, v = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **common2), pr2)
+    out["so_mean"], out["so_var"] = m, v
+    out["so_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common2, **obs2), pr2)
+    out["so_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common2, **obs2), pr2)
+
+    # ===============================================================================================================
+    # Kalman primitives on random inputs (kalmantv/standard.py), incl. the log-pdf's 1e-8 eigenvalue cut-off
+    # ===============================================================================================================
+    rng = np.random.default_rng(99)
+    n, p, m_ = 6, 4, 2
+
+    def spd(k, d):
+        a = rng.standard_normal((k, d, d))
+        return a @ np.swapaxes(a, -1, -2) + 0.5 * np.eye(d)
+    kin = dict(mu=rng.standard_normal((n, p)), S=spd(n, p), c=rng.standard_normal((n, p)),
+               Qm=rng.standard_normal((n, p, p)), Rm=spd(n, p), xm=rng.standard_normal((n, m_)),
+               d=rng.standard_normal((n, m_)), Wm=rng.standard_normal((n, m_, p)), Vm=spd(n, m_),
+               xn=rng.standard_normal((n, p)), mun=rng.standard_normal((n, p)), Sn=spd(n, p))
+    for k, v in kin.items():
+        out["kal_in_" + k] = v
+    res = {k: [] for k in ("pm", "pS", "um", "uS", "fm", "fS", "sm", "sS", "ssm", "ssS", "cA", "cb", "cV", "lp")}
+    for i in range(n):
+        g = {k: jnp.array(v[i]) for k, v in kin.items()}
+        pm, pS = rstd.predict(g["mu"], g["S"], g["c"], g["Qm"], g["Rm"])
+        um, uS = rstd.update(pm, pS, g["xm"], g["d"], g["Wm"], g["Vm"])
+        fm, fS = rstd.forecast(pm, pS, g["d"], g["Wm"], g["Vm"])
+        sm, sS = rstd.smooth_mv(g["mun"], g["Sn"], um, uS, pm, pS, g["Qm"])
+        ssm, ssS = rstd.smooth_sim(g["xn"], um, uS, pm, pS, g["Qm"])
+        cA, cb, cV = rstd.smooth_cond(um, uS, pm, pS, g["Qm"])
+        lp = rodeo.utils.multivariate_normal_logpdf(g["xm"], fm, fS)
+        for k, v in zip(res, (pm, pS, um, uS, fm, fS, sm, sS, ssm, ssS, cA, cb, cV, lp)):
+            res[k].append(A(v))
+    for k, v in res.items():
+        out["kal_" + k] = np.stack(v)
+    # eigenvalues around the absolute 1e-8 cut-off (utils.py:74)
+    cov = np.stack([np.diag([w, 2.0]) for w in (0.5e-8, 0.99e-8, 1.01e-8, 2e-8, 0.0)])
+    x = np.tile(np.array([1e-4, 0.3]), (5, 1))
+    out["lpcut_in_cov"], out["lpcut_in_x"] = cov, x
+    out["lpcut"] = np.array([float(rodeo.utils.multivariate_normal_logpdf(jnp.array(x[i]), jnp.zeros(2), jnp.array(cov[i])))
+                             for i in range(5)])
+    return out
+
+
+if __name__ == "__main__":
+    vec = build()
+    path = os.path.join(HERE, "reference_vectors.npz")
+    np.savez_compressed(path, **vec)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(vec), "arrays")

@@ -1,0 +1,257 @@
+"""The reference's OWN SOURCE, executed over oracle/jaxshim (tests/golden/make_reference_golden.py), produced
+tests/golden/reference_vectors.npz.  Here the oracle (CPU) and the CUDA path (GPU, through the C ABI) are checked
+against those committed vectors: this is what pins the oracle to the reference's code rather than to a restatement.
+/root/reference is not needed at test time."""
+import functools
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import rodeo_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "reference_vectors.npz"))
+
+TOL = 1e-10          # BASELINE north_star: 1e-10 relative in float64
+
+
+def prob(tag):
+    pr = {k: G[f"{tag}_in_{k}"] for k in ("W", "X0", "theta", "Q", "R")}
+    ob = {k: G[f"{tag}_in_{k}"] for k in ("obs_data", "obs_times", "obs_weight", "obs_var") if f"{tag}_in_{k}" in G.files}
+    return pr, ob
+
+
+def ll_err(a, b):
+    return float(np.max(np.abs(np.asarray(a) - b) / np.maximum(1.0, np.abs(b))))
+
+
+SETUPS = {"fitz": ("fitzhugh_nagumo", 3.0, 60), "fitzmid": ("fitzhugh_nagumo", 3.0, 60),
+          "readme": ("fitzhugh_nagumo", 40.0, 800), "lorenz": ("lorenz63", 0.5, 100),
+          "so": ("second_order_sin", 4.0, 80)}
+
+
+def oargs(tag, interr=orc.interrogate_kramer):
+    model, t_max, N = SETUPS[tag]
+    pr, ob = prob(tag)
+    a = (orc.MODELS[model], pr["W"], pr["X0"], 0.0, t_max, N, interr, (pr["Q"], pr["R"]), pr["theta"])
+    o = (ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"]) if ob else None
+    return a, o
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU: oracle == reference source
+# ---------------------------------------------------------------------------------------------------------------------
+def test_inputs_are_what_the_reference_helpers_build():
+    """tests/problems.py builds W, X0, Q, R with local closed forms; the reference's first_order_pad / ibm_init
+    (utils.py:80-102, prior/ibm.py:65-88) must give the same arrays, and so must the oracle's."""
+    pr, _ = prob("fitz")
+    assert np.array_equal(G["fitz_ref_W"], pr["W"])
+    assert P.maxnorm_rel(pr["X0"], G["fitz_ref_X0"]) < 1e-15
+    assert P.maxnorm_rel(pr["Q"], G["fitz_ref_Q"]) < 1e-15 and P.maxnorm_rel(pr["R"], G["fitz_ref_R"]) < 1e-14
+    Q, R = orc.ibm_init(3.0 / 60, 3, np.array([0.1, 0.1]))
+    assert P.maxnorm_rel(Q, G["fitz_ref_Q"]) < 1e-15 and P.maxnorm_rel(R, G["fitz_ref_R"]) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["kramer", "schober", "rodeo"])
+def test_oracle_solve_mv_fitz(name):
+    a, _ = oargs("fitz", getattr(orc, "interrogate_" + name))
+    m, v = orc.solve_mv(*a)
+    assert P.maxnorm_rel(m, G[f"fitz_{name}_mean"]) < 1e-12
+    assert P.maxnorm_rel(v, G[f"fitz_{name}_var"]) < 1e-12
+
+
+def test_oracle_solve_mv_chkrebtii_same_normals():
+    a, _ = oargs("fitz", orc.interrogate_chkrebtii)
+    m, v = orc.solve_mv(*a, z_interrogate=G["fitz_chkrebtii_z"])
+    assert P.maxnorm_rel(m, G["fitz_chkrebtii_mean"]) < 1e-11
+    assert P.maxnorm_rel(v, G["fitz_chkrebtii_var"]) < 1e-11
+
+
+def test_oracle_solve_sim_same_normals_svd_factor():
+    a, _ = oargs("fitz")
+    x = orc.solve_sim(*a, z_smooth=G["fitz_sim_z"], factor="svd")
+    assert P.maxnorm_rel(x, G["fitz_sim_x"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "readme", "so"])
+def test_oracle_dalton_fenrir(tag):
+    a, o = oargs(tag)
+    assert ll_err(orc.fenrir(*a, *o), G[f"{tag}_fenrir"]) < 1e-11
+    if f"{tag}_dalton" in G.files:
+        # the README-length dalton sum sits on its float64 noise floor
+        assert ll_err(orc.dalton(*a, *o), G[f"{tag}_dalton"]) < (1e-9 if tag == "readme" else 1e-11)
+
+
+def test_oracle_basic_and_data_adaptive_solvers():
+    a, o = oargs("fitz")
+    gauss = lambda y, x, th: np.sum(-0.5 * (y[None, :, :, 0] - x[:, :, :, 0]) ** 2 / 0.005
+                                    - 0.5 * np.log(2 * np.pi * 0.005), axis=(1, 2))
+    ll, Xt = orc.basic(*a, o[0], o[1], gauss)
+    assert ll_err(ll, G["fitz_basic"]) < 1e-11 and P.maxnorm_rel(Xt, G["fitz_basic_Xt"]) < 1e-12
+    m, v = orc.dalton_solve_mv(*a, *o)
+    assert P.maxnorm_rel(m, G["fitz_dalton_mean"]) < 1e-12 and P.maxnorm_rel(v, G["fitz_dalton_var"]) < 1e-12
+    m, v = orc.fenrir_solve_mv(*a, *o)
+    assert P.maxnorm_rel(m, G["fitz_fenrir_mean"]) < 1e-11 and P.maxnorm_rel(v, G["fitz_fenrir_var"]) < 1e-10
+
+
+def test_oracle_square_root_family():
+    a, _ = oargs("fitz")
+    pr, _ = prob("fitz")
+    a = a[:7] + ((pr["Q"], np.linalg.cholesky(pr["R"])),) + a[8:]
+    m, L = orc.solve_mv_sqrt(*a)
+    assert P.maxnorm_rel(m, G["fitz_sqrt_mean"]) < 1e-11
+    assert P.maxnorm_rel(L @ np.swapaxes(L, -1, -2), G["fitz_sqrt_var"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["readme", "lorenz", "so"])
+def test_oracle_solve_mv_other_models(tag):
+    a, _ = oargs(tag)
+    m, v = orc.solve_mv(*a)
+    assert P.maxnorm_rel(m, G[f"{tag}_mean"]) < 1e-11
+    assert P.maxnorm_rel(v, G[f"{tag}_var"]) < 1e-10
+
+
+def test_oracle_kalman_primitives():
+    k = {n[7:]: G[n] for n in G.files if n.startswith("kal_in_")}
+    pm, pS = orc.predict(k["mu"], k["S"], k["c"], k["Qm"], k["Rm"])
+    um, uS = orc.update(pm, pS, k["xm"], k["d"], k["Wm"], k["Vm"])
+    fm, fS = orc.forecast(pm, pS, k["d"], k["Wm"], k["Vm"])
+    sm, sS = orc.smooth_mv(k["mun"], k["Sn"], um, uS, pm, pS, k["Qm"])
+    ssm, ssS = orc.smooth_sim(k["xn"], um, uS, pm, pS, k["Qm"])
+    cA, cb, cV = orc.smooth_cond(um, uS, pm, pS, k["Qm"])
+    lp = orc.multivariate_normal_logpdf(k["xm"], fm, fS)
+    for name, val in zip(("pm", "pS", "um", "uS", "fm", "fS", "sm", "sS", "ssm", "ssS", "cA", "cb", "cV", "lp"),
+                         (pm, pS, um, uS, fm, fS, sm, sS, ssm, ssS, cA, cb, cV, lp)):
+        assert P.maxnorm_rel(val, G["kal_" + name]) < 1e-12, name
+    lp = orc.multivariate_normal_logpdf(G["lpcut_in_x"], np.zeros((5, 2)), G["lpcut_in_cov"])
+    assert np.allclose(lp, G["lpcut"], rtol=1e-14, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU: CUDA path (drop-in Python API -> C ABI -> kernels) == reference source
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def rb():
+    import rodeo_b200
+    from rodeo_b200 import _lib
+    _lib.load()
+    return rodeo_b200
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def gargs(rb, tag, interr=None):
+    model, t_max, N = SETUPS[tag]
+    pr, ob = prob(tag)
+    interr = interr or rb.interrogate.interrogate_kramer
+    a = (None, getattr(rb.models, model), pr["W"], pr["X0"], 0.0, t_max, N, interr)
+    return a, dict(prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"]), ob
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["kramer", "schober", "rodeo"])
+def test_cuda_solve_mv_fitz(rb, name):
+    a, kw, _ = gargs(rb, "fitz", getattr(rb.interrogate, "interrogate_" + name))
+    m, v = rb.solve_mv(*a, **kw)
+    assert P.maxnorm_rel(_np(m), G[f"fitz_{name}_mean"]) < TOL
+    assert P.maxnorm_rel(_np(v), G[f"fitz_{name}_var"]) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_solve_mv_chkrebtii_same_normals(rb):
+    chk = functools.partial(rb.interrogate.interrogate_chkrebtii, kalman_type="standard")
+    a, kw, _ = gargs(rb, "fitz", chk)
+    m, v = rb.solve_mv(0, *a[1:], **kw, _z_interr=G["fitz_chkrebtii_z"])
+    assert P.maxnorm_rel(_np(m), G["fitz_chkrebtii_mean"]) < TOL
+    assert P.maxnorm_rel(_np(v), G["fitz_chkrebtii_var"]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "readme", "so"])
+def test_cuda_dalton_fenrir(rb, tag):
+    a, kw, ob = gargs(rb, tag)
+    assert ll_err(_np(rb.inference.fenrir(*a, **kw, **ob)), G[f"{tag}_fenrir"]) < TOL
+    # dalton's N = 800 sum sits on its float64 noise floor: the float64 oracle itself is
+    # ~1e-10 from the exact value there
+    assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G[f"{tag}_dalton"]) < (2e-9 if tag == "readme" else TOL)
+
+
+@pytest.mark.gpu
+def test_cuda_basic_and_data_adaptive_solvers(rb):
+    import torch
+    a, kw, ob = gargs(rb, "fitz")
+    y = torch.as_tensor(ob["obs_data"], device="cuda")
+
+    def gauss(obs_data, ode_data, **params):
+        return torch.sum(-0.5 * (y[None, :, :, 0] - ode_data[:, :, :, 0]) ** 2 / 0.005
+                         - 0.5 * np.log(2 * np.pi * 0.005), dim=(1, 2))
+    ll, Xt = rb.inference.basic(*a, **kw, obs_data=ob["obs_data"], obs_times=ob["obs_times"], obs_loglik=gauss)
+    assert ll_err(_np(ll), G["fitz_basic"]) < TOL and P.maxnorm_rel(_np(Xt), G["fitz_basic_Xt"]) < TOL
+    m, v = rb.inference.dalton_solve_mv(*a, **kw, **ob)
+    assert P.maxnorm_rel(_np(m), G["fitz_dalton_mean"]) < TOL and P.maxnorm_rel(_np(v), G["fitz_dalton_var"]) < TOL
+    m, v = rb.inference.fenrir_solve_mv(*a, **kw, **ob)
+    assert P.maxnorm_rel(_np(m), G["fitz_fenrir_mean"]) < TOL and P.maxnorm_rel(_np(v), G["fitz_fenrir_var"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_square_root_family(rb):
+    a, kw, _ = gargs(rb, "fitz")
+    pr, _ = prob("fitz")
+    m, L = rb.solve_mv(*a, prior_pars=(pr["Q"], np.linalg.cholesky(pr["R"])), theta=pr["theta"],
+                       kalman_type="square-root")
+    L = _np(L)
+    assert P.maxnorm_rel(_np(m), G["fitz_sqrt_mean"]) < TOL
+    assert P.maxnorm_rel(L @ np.swapaxes(L, -1, -2), G["fitz_sqrt_var"]) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["readme", "lorenz", "so"])
+def test_cuda_solve_mv_other_models(rb, tag):
+    a, kw, _ = gargs(rb, tag)
+    m, v = rb.solve_mv(*a, **kw)
+    assert P.maxnorm_rel(_np(m), G[f"{tag}_mean"]) < TOL
+    assert P.maxnorm_rel(_np(v), G[f"{tag}_var"]) < (1e-9 if tag == "lorenz" else TOL)
+
+
+@pytest.mark.gpu
+def test_cuda_first_order_pad_and_ibm_init(rb):
+    pr, _ = prob("fitz")
+    W, init = rb.utils.first_order_pad(rb.models.fitzhugh_nagumo, 2, 3)
+    assert np.array_equal(np.asarray(W), G["fitz_ref_W"])
+    X0 = init(pr["X0"][:, :, 0], 0.0, theta=pr["theta"])
+    assert P.maxnorm_rel(_np(X0), G["fitz_ref_X0"]) < 1e-15
+    Q, R = rb.prior.ibm_init(3.0 / 60, 3, np.array([0.1, 0.1]))
+    assert P.maxnorm_rel(np.asarray(Q), G["fitz_ref_Q"]) < 1e-15 and P.maxnorm_rel(np.asarray(R), G["fitz_ref_R"]) < 1e-14
+
+
+@pytest.mark.gpu
+def test_cuda_kalman_primitives(rb):
+    ktv = rb.kalmantv.standard
+    k = {n[7:]: G[n] for n in G.files if n.startswith("kal_in_")}
+    got = {n: [] for n in ("pm", "pS", "um", "uS", "fm", "fS", "sm", "sS", "ssm", "ssS", "cA", "cb", "cV", "lp")}
+    for i in range(k["mu"].shape[0]):
+        g = {n: v[i] for n, v in k.items()}
+        pm, pS = ktv.predict(mean_state_past=g["mu"], var_state_past=g["S"], mean_state=g["c"], wgt_state=g["Qm"],
+                             var_state=g["Rm"])
+        um, uS = ktv.update(mean_state_pred=pm, var_state_pred=pS, x_meas=g["xm"], mean_meas=g["d"], wgt_meas=g["Wm"],
+                            var_meas=g["Vm"])
+        fm, fS = ktv.forecast(mean_state_pred=pm, var_state_pred=pS, mean_meas=g["d"], wgt_meas=g["Wm"],
+                              var_meas=g["Vm"])
+        sm, sS = ktv.smooth_mv(mean_state_next=g["mun"], var_state_next=g["Sn"], mean_state_filt=um,
+                               var_state_filt=uS, mean_state_pred=pm, var_state_pred=pS, wgt_state=g["Qm"])
+        ssm, ssS = ktv.smooth_sim(x_state_next=g["xn"], mean_state_filt=um, var_state_filt=uS, mean_state_pred=pm,
+                                  var_state_pred=pS, wgt_state=g["Qm"])
+        cA, cb, cV = ktv.smooth_cond(mean_state_filt=um, var_state_filt=uS, mean_state_pred=pm, var_state_pred=pS,
+                                     wgt_state=g["Qm"])
+        lp = rb.utils.multivariate_normal_logpdf(g["xm"], fm, fS)
+        for n, val in zip(got, (pm, pS, um, uS, fm, fS, sm, sS, ssm, ssS, cA, cb, cV, lp)):
+            got[n].append(_np(val) if hasattr(val, "detach") else np.asarray(val))
+    for n, val in got.items():
+        assert P.maxnorm_rel(np.stack(val), G["kal_" + n]) < TOL, n
+    lp = [float(rb.utils.multivariate_normal_logpdf(G["lpcut_in_x"][i], np.zeros(2), G["lpcut_in_cov"][i]))
+          for i in range(5)]
+    assert np.allclose(lp, G["lpcut"], rtol=1e-12, atol=0)
