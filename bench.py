@@ -292,11 +292,12 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    traffic = None
+    traffic, fp64_instr = None, None
     tpath = os.path.join(ROOT, "profiles", "dalton_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            prof = json.load(open(tpath))
+            traffic, fp64_instr = prof.get("dram_bytes_per_launch"), prof.get("fp64_instr_per_theta_step")
         except Exception:
             traffic = None
     roofline = {
@@ -305,6 +306,12 @@ def run_ours(args):
         "peak_source": "DFMA micro-benchmark run in this process (rodeo_b200_fp64_peak_probe); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_theta_step": FLOPS_PER_THETA_STEP,
+        # hardware view: the kernel exploits the unit-triangular Q / unit-row W structure and executes fewer FP64
+        # instructions than the dense count (hence frac > 1); this is the share of the FP64 pipe's issue slots it fills
+        # (executed FP64 instructions per theta*step from the committed ncu source counters x measured rate / DFMA rate)
+        "fp64_pipe_frac": (fp64_instr * B * N / (kern_ms * 1e-3)) / (float(peak.value) * 1e12 / 2.0)
+                          if (fp64_instr and peak.value) else None,
+        "executed_fp64_instr_per_theta_step": fp64_instr,
         "hbm_view": {"algorithmic_bytes_per_launch": int(B * (6 + 3 + 1) * 8),
                      "hbm_gbs_measured": peaks.get("hbm_gbs")},
     }

@@ -81,6 +81,7 @@ def build():
         return np.stack([A(r) for r in res])
 
     def save_problem(tag, pr, ob=None):
+        out[f"{tag}_in_grid"] = np.array([pr["t_min"], pr["t_max"], pr["n_steps"]])
         for k in ("W", "X0", "theta", "Q", "R"):
             out[f"{tag}_in_{k}"] = pr[k]
         if ob is not None:
@@ -165,6 +166,32 @@ def build():
         key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs2), pr)
     out["fitzmid_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
         key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs2), pr)
+
+    # shortest solves the reference's scans support (the backward scan has length n_steps - 1 >= 1): n_steps = 2, 3,
+    # with observations on both end points
+    for Ns in (2, 3):
+        prs = P.fitz_problem(3, n_steps=Ns, t_max={2: 0.2, 3: 0.3}[Ns], seed=5)
+        obx = P.fitz_obs(prs, None, n_obs=2)
+        save_problem(f"fitzN{Ns}", prs, obx)
+        cs = dict(ode_fun=fitz_fun, ode_weight=jnp.array(prs["W"]), t_min=0.0, t_max=prs["t_max"], n_steps=Ns,
+                  prior_pars=(jnp.array(prs["Q"]), jnp.array(prs["R"])))
+        obj = {k: jnp.array(v) for k, v in obx.items()}
+        m, v = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **cs), prs)
+        out[f"fitzN{Ns}_mean"], out[f"fitzN{Ns}_var"] = m, v
+        out[f"fitzN{Ns}_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+            key=key, ode_init=X0, interrogate=kramer, theta=th, **cs, **obj), prs)
+        out[f"fitzN{Ns}_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+            key=key, ode_init=X0, interrogate=kramer, theta=th, **cs, **obj), prs)
+
+    # an observation time just past t_max: searchsorted gives n_steps + 1, an index no step ever equals
+    obp = {k: v[1:3].copy() for k, v in ob.items()}
+    obp["obs_times"] = np.array([1.0, 3.0 + 1e-9])
+    save_problem("fitzpast", pr, obp)
+    obsp = {k: jnp.array(v) for k, v in obp.items()}
+    out["fitzpast_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obsp), pr)
+    out["fitzpast_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obsp), pr)
 
     # square-root Kalman family (solve.py:236-241 with kalman_type="square-root"; docs/examples/higher_order.md:108-112)
     chol = jax.vmap(jnp.linalg.cholesky)(pp[1])

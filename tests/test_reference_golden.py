@@ -27,13 +27,17 @@ def ll_err(a, b):
     return float(np.max(np.abs(np.asarray(a) - b) / np.maximum(1.0, np.abs(b))))
 
 
-SETUPS = {"fitz": ("fitzhugh_nagumo", 3.0, 60), "fitzmid": ("fitzhugh_nagumo", 3.0, 60),
-          "readme": ("fitzhugh_nagumo", 40.0, 800), "lorenz": ("lorenz63", 0.5, 100),
-          "so": ("second_order_sin", 4.0, 80)}
+MODEL = {"fitz": "fitzhugh_nagumo", "fitzmid": "fitzhugh_nagumo", "readme": "fitzhugh_nagumo", "lorenz": "lorenz63",
+         "so": "second_order_sin", "fitzN2": "fitzhugh_nagumo", "fitzN3": "fitzhugh_nagumo", "fitzpast": "fitzhugh_nagumo"}
+
+
+def grid(tag):
+    _, t_max, n_steps = G[f"{tag}_in_grid"]
+    return MODEL[tag], float(t_max), int(n_steps)
 
 
 def oargs(tag, interr=orc.interrogate_kramer):
-    model, t_max, N = SETUPS[tag]
+    model, t_max, N = grid(tag)
     pr, ob = prob(tag)
     a = (orc.MODELS[model], pr["W"], pr["X0"], 0.0, t_max, N, interr, (pr["Q"], pr["R"]), pr["theta"])
     o = (ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"]) if ob else None
@@ -75,7 +79,7 @@ def test_oracle_solve_sim_same_normals_svd_factor():
     assert P.maxnorm_rel(x, G["fitz_sim_x"]) < 1e-10
 
 
-@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "readme", "so"])
+@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "fitzpast", "readme", "so", "fitzN2", "fitzN3"])
 def test_oracle_dalton_fenrir(tag):
     a, o = oargs(tag)
     assert ll_err(orc.fenrir(*a, *o), G[f"{tag}_fenrir"]) < 1e-11
@@ -105,7 +109,7 @@ def test_oracle_square_root_family():
     assert P.maxnorm_rel(L @ np.swapaxes(L, -1, -2), G["fitz_sqrt_var"]) < 1e-10
 
 
-@pytest.mark.parametrize("tag", ["readme", "lorenz", "so"])
+@pytest.mark.parametrize("tag", ["readme", "lorenz", "so", "fitzN2", "fitzN3"])
 def test_oracle_solve_mv_other_models(tag):
     a, _ = oargs(tag)
     m, v = orc.solve_mv(*a)
@@ -145,7 +149,7 @@ def _np(t):
 
 
 def gargs(rb, tag, interr=None):
-    model, t_max, N = SETUPS[tag]
+    model, t_max, N = grid(tag)
     pr, ob = prob(tag)
     interr = interr or rb.interrogate.interrogate_kramer
     a = (None, getattr(rb.models, model), pr["W"], pr["X0"], 0.0, t_max, N, interr)
@@ -171,7 +175,7 @@ def test_cuda_solve_mv_chkrebtii_same_normals(rb):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "readme", "so"])
+@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "fitzpast", "readme", "so", "fitzN2", "fitzN3"])
 def test_cuda_dalton_fenrir(rb, tag):
     a, kw, ob = gargs(rb, tag)
     assert ll_err(_np(rb.inference.fenrir(*a, **kw, **ob)), G[f"{tag}_fenrir"]) < TOL
@@ -209,7 +213,7 @@ def test_cuda_square_root_family(rb):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["readme", "lorenz", "so"])
+@pytest.mark.parametrize("tag", ["readme", "lorenz", "so", "fitzN2", "fitzN3"])
 def test_cuda_solve_mv_other_models(rb, tag):
     a, kw, _ = gargs(rb, tag)
     m, v = rb.solve_mv(*a, **kw)
