@@ -8,8 +8,9 @@
  * _smooth/smooth_mv (:160-217), multivariate_normal_logpdf with the 1e-8 cut-off (src/rodeo/utils.py:60-78),
  * interrogate_{kramer,schober,rodeo} (src/rodeo/interrogate.py:50-115), _solve_filter / solve_mv
  * (src/rodeo/solve.py:31-122,208-302) and dalton (src/rodeo/inference/dalton.py:39-235).
- * The reference's own JAX implementation cannot run in this image (no jax / jaxlib, no network): PARITY UNPINNED
- * against a live reference; tests/test_oracle_c.py pins this port to the NumPy oracle at 1e-11.
+ * Parity chain: real JAX cannot run in this image (no jax / jaxlib, no network), but the reference's own source runs
+ * over oracle/jaxshim and its outputs are committed (tests/golden/reference_vectors.npz); tests/test_reference_golden.py
+ * pins the NumPy oracle to them, and tests/test_oracle_c.py pins this port to the NumPy oracle at 1e-11.
  *
  * Nothing under rodeo_b200/ links or loads this file.
  *
