@@ -1,5 +1,7 @@
 // rodeo_b200_solve_sim_f64: batched rodeo.solve_sim
 // (reference src/rodeo/solve.py:125-302).
+#include <cstdlib>
+
 #include "rodeo_host.h"
 
 #ifndef RODEO_REAL
@@ -21,15 +23,26 @@ struct SolveSimRun {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
-    // (theta, block) lanes buy parallelism at the price of redundant right-hand-side / Philox work per lane: worth it
-    // only while one-theta warps cannot fill the SM sub-partitions (fewer than ~3 warps on each of the 592)
+    // (theta, block) lanes shorten the serial chain of a lane by n_block and multiply the warps by n_block, at the price
+    // of redundant right-hand-side / Philox work per lane (and 32 % n_block idle lanes).  They win while the launch is
+    // latency-bound, i.e. while all of its warps are resident at once; measured on B200 (N = 800 / 4,000):
+    //   FitzHugh-Nagumo (n_block 2)  B = 2,048 / 8,192 / 32,768: 1.11 / 1.13 / 2.23 ms against 2.00 / 2.12 / 2.53 ms
+    //   Lorenz63 (n_block 3)         B = 4,096 / 16,384 / 65,536: 5.9 / 23.9 / 89.8 ms against 15.0 / 15.0 / 39.1 ms
+    // so: block lanes iff their grid fits the resident slots (n_block 2), half of them (n_block >= 3: 30 of 32 lanes
+    // and three redundant Jacobians make its saturated throughput a quarter of the one-theta kernel's).
     bool block_lanes = false;
-    if constexpr (Model::NB >= 2) block_lanes = (p.B + 31) / 32 < 1776;
+    if constexpr (Model::NB >= 2) {
+      typedef BlockLane<real_t, Model, INTERR, QK> L;
+      constexpr int SMEM_BL = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
+      RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_bl_kernel<real_t, Model, INTERR, QK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BL));
+      const double slots = resident_slots(solve_sim_bl_kernel<real_t, Model, INTERR, QK>, 32, SMEM_BL);
+      block_lanes = (double)grid_for(p.B, L::TW) <= (Model::NB == 2 ? 1.0 : 0.5) * slots;
+      if (const char* e = getenv("RODEO_SIM_BLOCK_LANES")) block_lanes = e[0] == '1';      // tuning experiments
+    }
     if constexpr (Model::NB >= 2) if (block_lanes) {
       typedef BlockLane<real_t, Model, INTERR, QK> L;
       constexpr int SMEM = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
-      RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_bl_kernel<real_t, Model, INTERR, QK>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       solve_sim_bl_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, L::TW), 32, SMEM, s>>>(
           C, a, z_smooth, stash, stash_ldb(p.B), x_out);
     }

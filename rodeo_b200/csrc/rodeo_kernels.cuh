@@ -18,6 +18,10 @@
 #include "rodeo_models.cuh"
 
 
+#ifndef RODEO_SIM_BL_MINB
+#define RODEO_SIM_BL_MINB 14
+#endif
+
 namespace rodeo {
 
 typedef long long i64;
@@ -735,7 +739,7 @@ struct BlockLane {
   MT mu[P];
   T S[NS], rs;
   T Q[P][P], R[NS], W[M][P];     // this lane's block of the shared constants, in registers
-  int b, gb;                     // block index, first lane of this theta's lane group
+  int b, gb;                     // block index; this theta's slot tl in the warp (block c of it lives in lane c*TW + tl)
 
   RD_DEV void load_consts(const Consts& C) {
     RD_UNROLL for (int c = 0; c < NB; ++c)
@@ -788,7 +792,7 @@ struct BlockLane {
     // the right-hand side couples the blocks: gather every block's visible columns from the theta's lane group
     MT x[NB][JC];
     RD_UNROLL for (int c = 0; c < NB; ++c)
-      RD_UNROLL for (int j = 0; j < JC; ++j) x[c][j] = __shfl_sync(0xffffffffu, xo[j], gb + c);
+      RD_UNROLL for (int j = 0; j < JC; ++j) x[c][j] = __shfl_sync(0xffffffffu, xo[j], c * TW + gb);
     MT f[NB][M], jl[NB][M][JC];
     if constexpr (HAS_J) {
       eval_f_jac<Model, MT>(q, t, x, f, jl);
@@ -916,8 +920,11 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   typedef BlockLane<T, Model, INTERR, QK> L;
   constexpr int NB = L::NB, P = L::P, NS = L::NS, K = L::K, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
   const int lane = threadIdx.x;
-  int tl = lane / NB, b = lane - tl * NB;
-  const bool lane_ok = tl < TW;            // 32 % NB trailing lanes shadow the last group; their stores are masked
+  // block-major lanes: lane = b * TW + tl.  A half-warp then holds consecutive thetas of ONE block, so its 64-bit
+  // shared-memory accesses buf[(s * NSTATE + k(b, .)) * PITCH + tl] fall in 16 distinct bank pairs (theta-major lanes
+  // put two blocks' rows, 3 * PITCH apart, into each half-warp: every LDS / STS took 4 wavefronts instead of 2)
+  int b = lane / TW, tl = lane - b * TW;
+  const bool lane_ok = b < NB;             // 32 % NB trailing lanes shadow the last group; their stores are masked
   if (!lane_ok) { tl = TW - 1; b = NB - 1; }
   const i64 theta0 = (i64)blockIdx.x * TW;
   i64 idx = theta0 + tl;
@@ -927,7 +934,7 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
   const int N = a.n_steps;
   T* buf = reinterpret_cast<T*>(rodeo_dyn_smem);
   L f;
-  f.b = b; f.gb = tl * NB;
+  f.b = b; f.gb = tl;
   f.load_consts(C);
   f.rs = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
   const T* x0 = a.ode_init + idx * NB * P;
@@ -1157,8 +1164,12 @@ solve_mv_sqrt_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P
 // is kept in HBM (per-lane loads are 9 doubles, prefetched one step ahead in registers); shared memory only stages
 // the draws so that they leave as runs of K time rows per theta.
 
+// 14 resident one-warp CTAs per SM (what the 13 KB staging buffer allows): BASELINE configs[4] gives one GPU 32,768
+// particles = 2,048 warps = 13.8 per SM; at 12 CTAs per SM (148 registers) the launch was 1.15 waves.  With the bound
+// ptxas settles on 125 registers without spilling: 2.64 -> 2.23 ms on that configuration (a plain 144-register cap,
+// which also keeps everything resident, is no faster than before: the gain is the tighter schedule, not the residency)
 template <typename T, class Model, int INTERR, int QK, bool OBS = false>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, RODEO_SIM_BL_MINB)
 solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                     const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
                     T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>()) {
@@ -1167,8 +1178,8 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
   constexpr int NB = L::NB, P = L::P, NS = L::NS, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
   constexpr int K = 16, ROW = NB * P;                    // staged time rows: K * ROW * PITCH elements per warp
   const int lane = threadIdx.x;
-  int tl = lane / NB, b = lane - tl * NB;
-  const bool lane_ok = tl < TW;
+  int b = lane / TW, tl = lane - b * TW;   // block-major lanes, see solve_mv_bl_kernel
+  const bool lane_ok = b < NB;
   if (!lane_ok) { tl = TW - 1; b = NB - 1; }
   const i64 theta0 = (i64)blockIdx.x * TW;
   i64 idx = theta0 + tl;
@@ -1178,7 +1189,7 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
   const int N = a.n_steps;
   T* buf = reinterpret_cast<T*>(rodeo_dyn_smem);
   L f;
-  f.b = b; f.gb = tl * NB;
+  f.b = b; f.gb = tl;
   f.load_consts(C);
   f.rs = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
   const T* x0 = a.ode_init + idx * NB * P;
@@ -1377,8 +1388,11 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
 // fenrir: forward filter, then a Kalman filter on the backward Markov chain with the Gaussian observations
 // (reference src/rodeo/inference/fenrir.py:86-328)
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef RODEO_FENRIR_MINB
+#define RODEO_FENRIR_MINB 1
+#endif
 template <typename T, class Model, int INTERR, int QK, int NOBS>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, RODEO_FENRIR_MINB)
 fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ stash, i64 ldb,
               T* __restrict__ loglik) {
