@@ -694,55 +694,55 @@ struct Philox {
   }
 };
 
-// Two independent standard normals from 128 random bits: Box-Muller on a 53-bit uniform for the radius (so the tail
-// reaches 8.6 sigma) and a 24-bit uniform for the angle.
+// Four independent standard normals from the four 32-bit words of one Philox call: two Box-Muller pairs, each with a
+// 32-bit uniform u = (r + 1/2) 2^-32 for the radius (tail to 6.7 sigma; P(|z| > 6.7) = 2e-11, i.e. one draw in 5e10 is
+// clipped -- the same resolution as cuRAND's curand_normal) and a 24-bit uniform for the angle.
 //
-// Default (fast) variant: the transcendental part runs on the FP32 special-function unit -- ln u1 is split as
-// (exponent) ln 2 + ln(mantissa) with the exponent taken exactly from the double's bits, so only ln of a number in
-// [1, 2) and sin / cos of an angle in [0, 2 pi) are approximated -- and the result is widened to double.  The draws
+// Default (fast) variant: the transcendental part runs on the FP32 special-function unit -- ln u is split as
+// (exponent) ln 2 + ln(mantissa) with the exponent taken exactly from the integer's leading one, so only ln of a number
+// in [1, 2) and sin / cos of an angle in [0, 2 pi) are approximated -- and the result is widened to double.  The draws
 // are standard normal to ~2^-21 relative (total-variation distance ~1e-6 from the exact law: no sample-based test can
 // see it), at about a sixth of the instructions of the all-FP64 version, which matters because the sampling smoother
-// spends ~40% of its instructions on normals.  Define RODEO_EXACT_NORMALS for the all-FP64 Box-Muller.
+// spends a third of its instructions on random numbers.  Define RODEO_EXACT_NORMALS for the all-FP64 Box-Muller.
 // Bit parity with JAX's threefry / erfinv normals is not attainable either way; deterministic parity
 // tests inject the normals instead.
-RD_DEV void normal_pair_exact(const unsigned (&r)[4], double& z0, double& z1) {
-  unsigned long long a = ((unsigned long long)r[0] << 32) | r[1];
-  unsigned long long b = ((unsigned long long)r[2] << 32) | r[3];
-  double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);   // (0,1)
-  double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-  double rad = sqrt(-2.0 * log(u1));
+RD_DEV void normal_pair_exact(unsigned ru, unsigned ra, double& z0, double& z1) {
+  const double u1 = ((double)ru + 0.5) * (1.0 / 4294967296.0);   // (0,1)
+  const double u2 = ((double)ra + 0.5) * (1.0 / 4294967296.0);
+  const double rad = sqrt(-2.0 * log(u1));
   double s, c;
   sincospi(2.0 * u2, &s, &c);
   z0 = rad * c; z1 = rad * s;
 }
-RD_DEV void normal_pair_fast(const unsigned (&r)[4], float& z0, float& z1) {
-  // x = (a >> 11) + 0.5 in [0.5, 2^53): u1 = x 2^-53.  Its binary exponent is found from the leading one of the integer.
-  const unsigned hi = r[0], lo = r[1];
-  const unsigned long long k = (((unsigned long long)hi << 32) | lo) >> 11;          // 53-bit integer
-  const int lz = k ? __clzll((long long)k) : 64;                                      // leading zeros in 64 bits
-  const int e = 63 - lz;                                                              // floor(log2 k), -1 if k == 0
-  // mantissa of (k + 0.5) in [1, 2) to 24 bits: shift k so that its leading one sits at bit 23 (the +0.5 only matters
-  // for tiny k, where it is added explicitly)
+RD_DEV void normal_pair_fast(unsigned ru, unsigned ra, float& z0, float& z1) {
+  // x = ru + 0.5 in [0.5, 2^32): u = x 2^-32.  Its binary exponent is found from the leading one of the integer.
+  const int e = 31 - __clz((int)ru);                                                  // floor(log2 ru), -1 if ru == 0
   float mant;
   int ex;
-  if (e >= 24) { mant = (float)(unsigned)(k >> (e - 23)) * (1.0f / 8388608.0f); ex = e; }
-  else { const float xs = (float)(unsigned)k + 0.5f; ex = 0; mant = xs; }             // small k: exact in float
-  const float ln_u1 = ((float)(ex - 53) + __log2f(mant)) * 0.69314718056f;            // ln(x 2^-53), < 0
-  const float rad = sqrtf(-2.0f * ln_u1);
-  const float ang = (float)(r[2] >> 8) * (6.28318530718f / 16777216.0f);
+  if (e >= 24) { mant = (float)(ru >> (e - 23)) * (1.0f / 8388608.0f); ex = e; }      // mantissa in [1, 2) to 24 bits
+  else { mant = (float)ru + 0.5f; ex = 0; }                                           // small ru: exact in float
+  const float ln_u = ((float)(ex - 32) + __log2f(mant)) * 0.69314718056f;             // ln(x 2^-32), < 0
+  const float rad = sqrtf(-2.0f * ln_u);
+  const float ang = (float)(ra >> 8) * (6.28318530718f / 16777216.0f);
   float s, c;
   __sincosf(ang, &s, &c);
   z0 = rad * c; z1 = rad * s;
 }
-RD_DEV void normal_pair(const unsigned (&r)[4], double& z0, double& z1) {
+RD_DEV void normal_pair(unsigned ru, unsigned ra, double& z0, double& z1) {
 #ifdef RODEO_EXACT_NORMALS
-  normal_pair_exact(r, z0, z1);
+  normal_pair_exact(ru, ra, z0, z1);
 #else
   float a, b;
-  normal_pair_fast(r, a, b);
+  normal_pair_fast(ru, ra, a, b);
   z0 = (double)a; z1 = (double)b;
 #endif
 }
-RD_DEV void normal_pair(const unsigned (&r)[4], float& z0, float& z1) { normal_pair_fast(r, z0, z1); }
+RD_DEV void normal_pair(unsigned ru, unsigned ra, float& z0, float& z1) { normal_pair_fast(ru, ra, z0, z1); }
+// normals 0..3 of one Philox output; an unused pair costs nothing (dead code)
+template <typename T>
+RD_DEV void normal_quad(const unsigned (&r)[4], T (&q)[4]) {
+  normal_pair(r[0], r[1], q[0], q[1]);
+  normal_pair(r[2], r[3], q[2], q[3]);
+}
 
 }  // namespace rodeo

@@ -89,34 +89,57 @@ RD_DEV T step_time(T t_min, T t_max, int n, int n_steps) {
 // stream tags for the counter-based RNG
 enum : unsigned { TAG_INTERR_A = 0x100u, TAG_INTERR_B = 0x200u, TAG_SMOOTH = 0x300u };
 
-template <typename T, int COUNT>
-RD_DEV void philox_normals(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, T (&z)[COUNT]) {
+// Random-number layout: a stream is (key, particle, step, tag); Philox call c of a stream yields its normals 4c .. 4c+3.
+//   interrogation streams (TAG_INTERR_*): normal b * JC + j belongs to block b, visible column j;
+//   smoothing stream (TAG_SMOOTH):        block b owns calls b * CPB .. (b+1) * CPB - 1, CPB = ceil(P / 4), so that a
+//                                         lane that holds one block generates exactly its own calls.
+// Both lane mappings (one lane per theta, one lane per (theta, block)) read this layout, so a draw does not depend on
+// which kernel produced it.
+RD_DEV void philox_call(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, int call, unsigned (&r)[4]) {
   Philox ph{key0, key1};
-  RD_UNROLL for (int k = 0; k < COUNT; k += 2) {
+  ph((unsigned)particle, (unsigned)((unsigned long long)particle >> 32), (unsigned)step, tag + (unsigned)call, r);
+}
+
+// normals 4 * call0 .. 4 * call0 + COUNT - 1 of a stream
+template <typename T, int COUNT>
+RD_DEV void philox_normals(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, T (&z)[COUNT],
+                           int call0 = 0) {
+  RD_UNROLL for (int c = 0; c < (COUNT + 3) / 4; ++c) {
     unsigned r[4];
-    ph((unsigned)particle, (unsigned)((unsigned long long)particle >> 32), (unsigned)step, tag + (unsigned)(k >> 1), r);
-    T a, b;
-    normal_pair(r, a, b);
-    z[k] = a;
-    if (k + 1 < COUNT) z[k + 1] = b;
+    philox_call(key0, key1, particle, step, tag, call0 + c, r);
+    T q[4];
+    normal_quad(r, q);
+    RD_UNROLL for (int i = 0; i < 4; ++i)
+      if (4 * c + i < COUNT) z[4 * c + i] = q[i];
   }
 }
 
-// normals first .. first+COUNT-1 of the (theta, step, tag) stream (pairs g/2, component g&1), `first` a run-time value
+// normals first .. first+COUNT-1 of a stream, `first` a run-time value (selects instead of dynamic indexing)
 template <typename T, int COUNT>
 RD_DEV void philox_normal_range(unsigned key0, unsigned key1, i64 particle, int step, unsigned tag, int first,
                                 T (&z)[COUNT]) {
-  constexpr int NPAIR = COUNT / 2 + 1;
-  Philox ph{key0, key1};
-  T pr[2 * NPAIR];
-  const int p0 = first >> 1;
-  RD_UNROLL for (int k = 0; k < NPAIR; ++k) {
+  const int c0 = first >> 2, o = first & 3;
+  if constexpr (COUNT == 1) {
+    // one normal: pick its pair's two words first, so that a single Box-Muller pair is evaluated
     unsigned r[4];
-    ph((unsigned)particle, (unsigned)((unsigned long long)particle >> 32), (unsigned)step, tag + (unsigned)(p0 + k), r);
-    normal_pair(r, pr[2 * k], pr[2 * k + 1]);
+    philox_call(key0, key1, particle, step, tag, c0, r);
+    const unsigned ru = (o & 2) ? r[2] : r[0], ra = (o & 2) ? r[3] : r[1];
+    T a, b;
+    normal_pair(ru, ra, a, b);
+    z[0] = (o & 1) ? b : a;
+  } else {
+    constexpr int NCALL = (COUNT + 2) / 4 + 1;
+    T pr[4 * NCALL];
+    RD_UNROLL for (int k = 0; k < NCALL; ++k) {
+      unsigned r[4];
+      philox_call(key0, key1, particle, step, tag, c0 + k, r);
+      T q[4];
+      normal_quad(r, q);
+      RD_UNROLL for (int i = 0; i < 4; ++i) pr[4 * k + i] = q[i];
+    }
+    RD_UNROLL for (int k = 0; k < COUNT; ++k)
+      z[k] = o == 0 ? pr[k] : (o == 1 ? pr[k + 1] : (o == 2 ? pr[k + 2] : pr[k + 3]));
   }
-  const bool odd = (first & 1) != 0;
-  RD_UNROLL for (int k = 0; k < COUNT; ++k) z[k] = odd ? pr[k + 1] : pr[k];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1210,7 +1233,7 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
       const T* zp = z_smooth + (idx * (i64)(N + 1) + n) * (NB * P) + b * P;
       RD_UNROLL for (int k = 0; k < P; ++k) z[k] = zp[k];
     } else {
-      philox_normal_range<T, P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, b * P, z);
+      philox_normals<T, P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, z, b * ((P + 3) / 4));
     }
   };
   typedef typename L::MT MT;
@@ -1324,7 +1347,11 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
       const T* zp = z_smooth + (idx * (i64)(N + 1) + n) * (NB * P);
       RD_UNROLL for (int k = 0; k < NB * P; ++k) z[k] = zp[k];
     } else {
-      philox_normals<T, NB * P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, z);
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        T zb[P];
+        philox_normals<T, P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, zb, b * ((P + 3) / 4));
+        RD_UNROLL for (int k = 0; k < P; ++k) z[b * P + k] = zb[k];
+      }
     }
   };
   typedef typename F::MT MT;

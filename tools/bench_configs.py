@@ -66,7 +66,7 @@ def main():
         print(json.dumps(line), flush=True)
         res.append(line)
 
-    want = lambda k: (not args.only) or k in args.only.split(",")
+    want = lambda k: (k in args.only.split(",")) if args.only else not k.endswith("f32")
     sc = args.scale
 
     if want("C1"):
@@ -83,6 +83,22 @@ def main():
         f = lambda: rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], X0, 0.0, 40.0, 800, kr,
                                         prior_pars=(pr["Q"], pr["R"]), theta=th, **obd)
         report("C2 FN dalton kramer", B, 800, timeit(f, args.reps, flush), 963.0, 0.0)
+    if want("C1f32"):
+        B = int(65536 * sc); pr = P.fitz_problem(B, seed=0)
+        X0, th = D(pr["X0"].astype(np.float32)), D(pr["theta"].astype(np.float32))
+        f = lambda: rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], X0, 0.0, 40.0, 800, kr,
+                                prior_pars=(pr["Q"], pr["R"]), theta=th)
+        report("C1f32 FN solve_mv kramer, float32 storage / mixed arithmetic", B, 800, timeit(f, args.reps, flush),
+               1013.0, 96.0)
+        del X0, th; torch.cuda.empty_cache()
+    if want("C2f32"):
+        B = int(65536 * sc); pr = P.fitz_problem(B, seed=0); ob = P.fitz_obs(pr, None)
+        X0, th = D(pr["X0"].astype(np.float32)), D(pr["theta"].astype(np.float32))
+        obd = {k: D(v) if k != "obs_times" else v for k, v in ob.items()}
+        f = lambda: rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], X0, 0.0, 40.0, 800, kr,
+                                        prior_pars=(pr["Q"], pr["R"]), theta=th, **obd)
+        report("C2f32 FN dalton kramer, float32 storage / mixed arithmetic", B, 800, timeit(f, args.reps, flush),
+               963.0, 0.0)
     if want("C3"):
         B = int(65536 * sc); pr = P.lorenz_problem(B, seed=0)
         X0, th = D(pr["X0"]), D(pr["theta"])
