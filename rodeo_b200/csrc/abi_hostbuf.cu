@@ -15,10 +15,22 @@ struct Arena {
   char* base = nullptr;
   size_t cap = 0, used = 0;
   cudaStream_t stream = nullptr;
+  // chunked pipeline of the log-likelihood entry points: chunk c's inputs travel on `stream`, its kernel runs on
+  // lane[c] as soon as they have landed (ready[c]) and `stream` collects the results after done[c]
+  static constexpr int NCHUNK = 4;
+  cudaStream_t lane[NCHUNK] = {};
+  cudaEvent_t ready[NCHUNK] = {}, done[NCHUNK] = {};
 
   int reserve(size_t bytes) {
     used = 0;
-    if (!stream) RODEO_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!stream) {
+      RODEO_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      for (int c = 0; c < NCHUNK; ++c) {
+        RODEO_CUDA_OK(cudaStreamCreateWithFlags(&lane[c], cudaStreamNonBlocking));
+        RODEO_CUDA_OK(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
+        RODEO_CUDA_OK(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+      }
+    }
     if (bytes <= cap) return RODEO_OK;
     if (base) { RODEO_CUDA_OK(cudaFree(base)); base = nullptr; cap = 0; }
     RODEO_CUDA_OK(cudaMalloc((void**)&base, bytes));
@@ -32,7 +44,13 @@ struct Arena {
   }
   void release() {
     if (base) cudaFree(base);
-    if (stream) cudaStreamDestroy(stream);
+    if (stream) {
+      cudaStreamDestroy(stream);
+      for (int c = 0; c < NCHUNK; ++c) {
+        cudaStreamDestroy(lane[c]); cudaEventDestroy(ready[c]); cudaEventDestroy(done[c]);
+        lane[c] = nullptr; ready[c] = nullptr; done[c] = nullptr;
+      }
+    }
     base = nullptr; cap = used = 0; stream = nullptr;
   }
 };
@@ -67,15 +85,35 @@ extern "C" int rodeo_b200_dalton_f64_host(const RodeoProblem* p, const double* o
   double* d_D = (double*)g_arena.take(b_D);
   double* d_Om = (double*)g_arena.take(b_Om);
   cudaStream_t s = g_arena.stream;
-  RODEO_CUDA_OK(cudaMemcpyAsync(d_init, ode_init, b_init, cudaMemcpyHostToDevice, s));
-  RODEO_CUDA_OK(cudaMemcpyAsync(d_theta, theta, b_theta, cudaMemcpyHostToDevice, s));
   RODEO_CUDA_OK(cudaMemcpyAsync(d_ind, obs_ind, b_ind, cudaMemcpyHostToDevice, s));
   RODEO_CUDA_OK(cudaMemcpyAsync(d_y, obs_data, b_y, cudaMemcpyHostToDevice, s));
   RODEO_CUDA_OK(cudaMemcpyAsync(d_D, obs_weight, b_D, cudaMemcpyHostToDevice, s));
   RODEO_CUDA_OK(cudaMemcpyAsync(d_Om, obs_var, b_Om, cudaMemcpyHostToDevice, s));
-  if (int rc = rodeo_b200_dalton_f64(p, ode_weight, prior_weight, prior_var, d_init, d_theta, nullptr, d_ind, d_y,
-                                     d_D, d_Om, d_ll, nullptr, 0, s))
-    return rc;
+  // The theta batch is independent per theta, so it is cut into NCHUNK contiguous chunks: chunk c's kernel starts as
+  // soon as its own X0 / theta rows have landed, while the next chunk's rows are still crossing PCIe; the kernels run
+  // on separate streams so they share the GPU instead of queueing behind each other's tails.  Results are identical to
+  // one launch (per-theta arithmetic; random streams are keyed by the global particle index).
+  const int nchunk = B >= (size_t)Arena::NCHUNK * 8192 ? Arena::NCHUNK : 1;
+  const size_t per = (B + nchunk - 1) / nchunk;
+  const size_t row_init = nb * ps, row_theta = (size_t)p->n_theta;
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t b0 = (size_t)c * per, bn = b0 + per <= B ? per : B - b0;
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_init + b0 * row_init, ode_init + b0 * row_init, bn * row_init * 8,
+                                  cudaMemcpyHostToDevice, s));
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_theta + b0 * row_theta, theta + b0 * row_theta, bn * row_theta * 8,
+                                  cudaMemcpyHostToDevice, s));
+    RODEO_CUDA_OK(cudaEventRecord(g_arena.ready[c], s));
+    RODEO_CUDA_OK(cudaStreamWaitEvent(g_arena.lane[c], g_arena.ready[c], 0));
+    RodeoProblem pc = *p;
+    pc.B = (int64_t)bn;
+    pc.particle_offset = p->particle_offset + (int64_t)b0;
+    if (int rc = rodeo_b200_dalton_f64(&pc, ode_weight, prior_weight, prior_var, d_init + b0 * row_init,
+                                       d_theta + b0 * row_theta, nullptr, d_ind, d_y, d_D, d_Om, d_ll + b0, nullptr, 0,
+                                       g_arena.lane[c]))
+      return rc;
+    RODEO_CUDA_OK(cudaEventRecord(g_arena.done[c], g_arena.lane[c]));
+  }
+  for (int c = 0; c < nchunk; ++c) RODEO_CUDA_OK(cudaStreamWaitEvent(s, g_arena.done[c], 0));
   RODEO_CUDA_OK(cudaMemcpyAsync(loglik_out, d_ll, b_ll, cudaMemcpyDeviceToHost, s));
   RODEO_CUDA_OK(cudaStreamSynchronize(s));
   return RODEO_OK;

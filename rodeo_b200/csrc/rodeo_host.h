@@ -145,15 +145,20 @@ inline int dispatch_model(const RodeoProblem& p, const R* W, const R* Q, A&&... 
 
 inline unsigned grid_for(long long B, int block) { return (unsigned)((B + block - 1) / block); }
 
-// CTAs of `kernel` that are resident on the whole GPU at once (registers and dynamic shared memory taken into account)
-template <class K>
-inline double resident_slots(K kernel, int block, size_t smem) {
+inline int sm_count() {
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) n_sm = 148;
   }
+  return n_sm;
+}
+
+// CTAs of `kernel` that are resident on the whole GPU at once (registers and dynamic shared memory taken into account)
+template <class K>
+inline double resident_slots(K kernel, int block, size_t smem) {
+  const int n_sm = sm_count();
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1 || n_sm < 1)
     return 12.0 * 148.0;
