@@ -24,7 +24,7 @@ struct FenrirRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
+    constexpr int SMEM = 2 * SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;      // double-buffered history
     RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_kernel<real_t, Model, INTERR, QK, 1>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     fenrir_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, o, stash, stash_ldb(p.B), out);
@@ -59,7 +59,7 @@ extern "C" int RODEO_FN(rodeo_b200_fenrir)(const RodeoProblem* p, const real_t* 
     if (p->n_bobs != 1) { set_error("fenrir: n_bobs=%d is not supported for user models (only 1)", p->n_bobs); return RODEO_ERR_UNSUPPORTED; }
     real_t* stash = (real_t*)workspace;
     long long ldb = stash_ldb(p->B);
-    const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * (int)sizeof(real_t);
+    const int smem = 2 * seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * (int)sizeof(real_t);
     return user_launch(*p, "fenrir_kernel", ", 1", (const double*)ode_weight, (const double*)prior_weight, (const double*)prior_var, p->user_wcol, p->B, smem,
                        {&a, &o, &stash, &ldb, &loglik_out}, (cudaStream_t)stream);
   }

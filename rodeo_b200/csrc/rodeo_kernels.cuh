@@ -530,6 +530,32 @@ struct SegBuf {
   }
 };
 
+// asynchronous global -> shared copies of one element (LDGSTS: no register staging, completes in the background)
+template <typename T>
+RD_DEV void cp_async_elem(T* smem, const T* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
+}
+RD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+RD_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Every-state history (KC == 1): start copying filt[j*K .. j*K + cnt - 1] of theta idx into slots 0 .. cnt-1 of `buf`
+// (row 0 = (ode_init, 0) is not in the history: the caller fills that slot).  Each lane copies, and later reads, only
+// its own column of the buffer, so cp_async_wait_all() by the same lane is all the synchronisation needed.
+template <typename T, class F>
+RD_DEV void segment_fetch_async(const T* __restrict__ stash, i64 ldb, i64 idx, int j, int cnt, SegBuf<T, F>& buf) {
+  constexpr int NSTATE = SegBuf<T, F>::NSTATE, K = SegBuf<T, F>::K;
+  for (int s = 0; s < cnt; ++s) {
+    const int n = j * K + s;
+    if (n >= 1) {
+      const T* g = stash + (i64)(n - 1) * NSTATE * ldb + idx;
+      RD_UNROLL for (int k = 0; k < NSTATE; ++k) cp_async_elem(&buf.at(s, k), g + (i64)k * ldb);
+    }
+  }
+  cp_async_commit();
+}
+
 // checkpoint j (= filt[j*K], j >= 1) of theta idx:  stash[((j-1) * NSTATE + k) * ldb + idx]
 template <typename T, class F>
 RD_DEV void ckpt_store(T* __restrict__ stash, i64 ldb, i64 idx, int j, const F& f) {
@@ -1431,11 +1457,19 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   if (!live) idx = a.B - 1;
   const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
-  Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
+  // two history buffers: while segment j is processed out of one, segment j-1 travels HBM -> shared memory into the
+  // other (cp.async), so the serial chain of a theta never waits for its own history
+  Buf bufs[2] = {Buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x},
+                 Buf{reinterpret_cast<T*>(rodeo_dyn_smem) + Buf::BYTES / (int)sizeof(T), (int)threadIdx.x}};
   F f;
   f.init(a.ode_init + idx * NB * P);
   f.load_scale(a, idx);
   forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
+  __threadfence();                                        // the history stores above precede the asynchronous reads below
+  {
+    const int jt = (N - 1) / K;
+    segment_fetch_async<T, F>(stash, ldb, idx, jt, (N - jt * K) < K ? (N - jt * K) : K, bufs[jt & 1]);
+  }
 
   // backward-filter state starts at filt[N]
   F bk;
@@ -1456,8 +1490,10 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   for (int j = (N - 1) / K; j >= 0; --j) {
     const int n0 = j * K;
     const int cnt = (N - n0) < K ? (N - n0) : K;
-    if (j > 0) prefetch_segment<T, F, 1>(stash, ldb, idx, j - 1, K);
-    rebuild_segment<T, Model, INTERR, QK, 1>(C, a, q, idx, j, cnt, f, stash, ldb, buf);
+    Buf& buf = bufs[j & 1];
+    cp_async_wait_all();                                  // segment j has landed
+    if (j > 0) segment_fetch_async<T, F>(stash, ldb, idx, j - 1, K, bufs[(j - 1) & 1]);
+    else { f.init(a.ode_init + idx * NB * P); buf.put(0, f.mu, f.S); }      // filt[0] = (ode_init, 0)
     for (int s = cnt - 1; s >= 0; --s) {
       const int t = n0 + s;
       buf.get(s, f.mu, f.S);                              // filt[t]  (t = 0: (ode_init, 0))
