@@ -243,6 +243,61 @@ def build():
         key=key, ode_init=X0, interrogate=kramer, theta=th, **common2, **obs2), pr2)
 
     # ===============================================================================================================
+    # Hes1 (log scale) and SEIRAH, right-hand sides and settings of the reference's examples/timings.py:251-258, 339-352
+    # ===============================================================================================================
+    def hes1(X, t, theta):
+        P_, M_, H_ = jnp.exp(X[:, 0])
+        a, b, c, d, e, f, g = theta
+        logP = -a * H_ + b * M_ / P_ - c
+        logM = -d + e / (1 + P_ * P_) / M_
+        logH = -a * P_ + f / (1 + P_ * P_) / H_ - g
+        return jnp.array([[logP], [logM], [logH]])
+
+    def seirah(X, t, theta):
+        S, E, I, R, A_, H = X[:, 0]
+        N = S + E + I + R + A_ + H
+        b, r, alpha, D_e, D_I, D_q = theta
+        D_h = 30
+        dS = -b * S * (I + alpha * A_) / N
+        dE = b * S * (I + alpha * A_) / N - E / D_e
+        dI = r * E / D_e - I / D_q - I / D_I
+        dR = (I + A_) / D_I + H / D_h
+        dA = (1 - r) * E / D_e - A_ / D_I
+        dH = I / D_q - H / D_h
+        return jnp.array([[dS], [dE], [dI], [dR], [dA], [dH]])
+
+    for tag, fun, nv, x0v, th0, t_max_, n_st, seed in (
+            ("hes1", hes1, 3, np.log([1.439, 2.037, 17.904]), [0.022, 0.3, 0.031, 0.028, 0.5, 20, 0.3], 240.0, 120, 5),
+            ("seirah", seirah, 6, [63804435., 15492., 21752., 0., 618013., 93583.], [2.23, 0.034, 0.55, 5.1, 2.3, 1.13],
+             60.0, 80, 6)):
+        rng_ = np.random.default_rng(seed)
+        theta_ = np.asarray(th0) * np.exp(0.02 * rng_.standard_normal((2, len(th0))))
+        Wm, padm = rodeo.utils.first_order_pad(fun, nv, 3)
+        X0_ = np.stack([A(padm(jnp.array(np.asarray(x0v, dtype=float)), 0.0, theta=jnp.array(theta_[i]))) for i in range(2)])
+        Qm, Rm = rodeo.prior.ibm_init(dt=t_max_ / n_st, n_deriv=3, sigma=jnp.array([0.1] * nv))
+        prm = dict(W=A(Wm), X0=X0_, theta=theta_, Q=A(Qm), R=A(Rm), t_min=0.0, t_max=t_max_, n_steps=n_st)
+        save_problem(tag, prm)
+        cm = dict(ode_fun=fun, ode_weight=Wm, t_min=0.0, t_max=t_max_, n_steps=n_st, prior_pars=(Qm, Rm))
+        m, v = per_theta(lambda X0, th: rodeo.solve_mv(key=key, ode_init=X0, interrogate=kramer, theta=th, **cm), prm)
+        out[f"{tag}_mean"], out[f"{tag}_var"] = m, v
+
+    # ===============================================================================================================
+    # sigma as part of theta: the prior is rebuilt per theta with the reference's ibm_init (docs/examples/parameter.md:
+    # 218-222), here on FitzHugh-Nagumo with the dalton log-likelihood and solve_mv
+    # ===============================================================================================================
+    sig = 0.1 * np.exp(0.3 * np.random.default_rng(3).standard_normal((3, 2)))
+    out["fitzsig_in_sigma"] = sig
+    ms_, vs_, ll_ = [], [], []
+    for i in range(3):
+        Qi, Ri = rodeo.prior.ibm_init(dt=3.0 / 60, n_deriv=3, sigma=jnp.array(sig[i]))
+        ci = dict(common, prior_pars=(Qi, Ri))
+        m, v = rodeo.solve_mv(key=key, ode_init=jnp.array(pr["X0"][i]), interrogate=kramer, theta=jnp.array(pr["theta"][i]), **ci)
+        ll_.append(float(rodeo.inference.dalton(key=key, ode_init=jnp.array(pr["X0"][i]), interrogate=kramer,
+                                                theta=jnp.array(pr["theta"][i]), **ci, **obs)))
+        ms_.append(A(m)); vs_.append(A(v))
+    out["fitzsig_mean"], out["fitzsig_var"], out["fitzsig_dalton"] = np.stack(ms_), np.stack(vs_), np.array(ll_)
+
+    # ===============================================================================================================
     # Kalman primitives on random inputs (kalmantv/standard.py), incl. the log-pdf's 1e-8 eigenvalue cut-off
     # ===============================================================================================================
     rng = np.random.default_rng(99)

@@ -28,7 +28,7 @@ def ll_err(a, b):
 
 
 MODEL = {"fitz": "fitzhugh_nagumo", "fitzmid": "fitzhugh_nagumo", "readme": "fitzhugh_nagumo", "lorenz": "lorenz63",
-         "so": "second_order_sin", "fitzN2": "fitzhugh_nagumo", "fitzN3": "fitzhugh_nagumo", "fitzpast": "fitzhugh_nagumo"}
+         "so": "second_order_sin", "fitzN2": "fitzhugh_nagumo", "fitzN3": "fitzhugh_nagumo", "fitzpast": "fitzhugh_nagumo", "hes1": "hes1", "seirah": "seirah"}
 
 
 def grid(tag):
@@ -109,12 +109,22 @@ def test_oracle_square_root_family():
     assert P.maxnorm_rel(L @ np.swapaxes(L, -1, -2), G["fitz_sqrt_var"]) < 1e-10
 
 
-@pytest.mark.parametrize("tag", ["readme", "lorenz", "so", "fitzN2", "fitzN3"])
+@pytest.mark.parametrize("tag", ["readme", "lorenz", "so", "fitzN2", "fitzN3", "hes1", "seirah"])
 def test_oracle_solve_mv_other_models(tag):
     a, _ = oargs(tag)
     m, v = orc.solve_mv(*a)
     assert P.maxnorm_rel(m, G[f"{tag}_mean"]) < 1e-11
     assert P.maxnorm_rel(v, G[f"{tag}_var"]) < 1e-10
+
+
+def test_oracle_theta_dependent_prior():
+    a, o = oargs("fitz")
+    QR = [orc.ibm_init(3.0 / 60, 3, sg) for sg in G["fitzsig_in_sigma"]]
+    Q, R = QR[0][0], np.stack([r for _, r in QR])                       # Q shared, R (B, nb, p, p)
+    a = a[:7] + ((Q, R),) + a[8:]
+    m, v = orc.solve_mv(*a)
+    assert P.maxnorm_rel(m, G["fitzsig_mean"]) < 1e-12 and P.maxnorm_rel(v, G["fitzsig_var"]) < 1e-12
+    assert ll_err(orc.dalton(*a, *o), G["fitzsig_dalton"]) < 1e-11
 
 
 def test_oracle_kalman_primitives():
@@ -213,12 +223,23 @@ def test_cuda_square_root_family(rb):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["readme", "lorenz", "so", "fitzN2", "fitzN3"])
+@pytest.mark.parametrize("tag", ["readme", "lorenz", "so", "fitzN2", "fitzN3", "hes1", "seirah"])
 def test_cuda_solve_mv_other_models(rb, tag):
     a, kw, _ = gargs(rb, tag)
     m, v = rb.solve_mv(*a, **kw)
     assert P.maxnorm_rel(_np(m), G[f"{tag}_mean"]) < TOL
-    assert P.maxnorm_rel(_np(v), G[f"{tag}_var"]) < (1e-9 if tag == "lorenz" else TOL)
+    assert P.maxnorm_rel(_np(v), G[f"{tag}_var"]) < (1e-9 if tag in ("lorenz", "seirah") else TOL)
+
+
+@pytest.mark.gpu
+def test_cuda_theta_dependent_prior(rb):
+    """sigma part of theta: rb.prior.ibm_init with a (B, n_block) sigma (the kernels carry it as a per-(theta, block)
+    scale of the shared prior variance) against the reference's ibm_init called once per theta."""
+    a, kw, ob = gargs(rb, "fitz")
+    kw = dict(kw, prior_pars=rb.prior.ibm_init(3.0 / 60, 3, G["fitzsig_in_sigma"]))
+    m, v = rb.solve_mv(*a, **kw)
+    assert P.maxnorm_rel(_np(m), G["fitzsig_mean"]) < TOL and P.maxnorm_rel(_np(v), G["fitzsig_var"]) < TOL
+    assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G["fitzsig_dalton"]) < TOL
 
 
 @pytest.mark.gpu
