@@ -763,11 +763,16 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
 // theta exchange by shuffle once per forward step.  It also halves the work quantum per warp (finer load balance over
 // the SM sub-partitions) and the registers per lane.
 #ifndef RODEO_BL_SMEM
-#define RODEO_BL_SMEM 18432      // staging bytes per warp
+// staging bytes per warp.  FitzHugh-Nagumo (n_block 2, 18 states, 16 thetas per warp): 22,100 B -> K = 9 rows, 1.3 KB
+// covariance runs, 10 resident warps per SM.  Measured on B200 for 65,536 thetas x 800 steps after the shared-memory
+// accesses became conflict-free: K = 7 / 8 / 9 / 10 -> 3.09 / 3.02 / 2.84 / 3.03 ms (K = 5 / 6: 3.24): longer per-theta
+// runs buy HBM efficiency until too few warps are left to keep the FP64 pipe busy.
+#define RODEO_BL_SMEM 22100
 #endif
-__host__ __device__ constexpr int seg_len_bl(int nstate, int nb) {
-  return (RODEO_BL_SMEM / (nstate * (32 / nb + 1) * 8)) < 1 ? 1
-       : ((RODEO_BL_SMEM / (nstate * (32 / nb + 1) * 8)) > 12 ? 12 : (RODEO_BL_SMEM / (nstate * (32 / nb + 1) * 8)));
+__host__ __device__ constexpr int seg_len_bl(int nstate, int nb, int elem_bytes = 8) {
+  // float32 rows are half as long in bytes: allow up to 16 of them (same run length as 8 rows of doubles)
+  const int k = RODEO_BL_SMEM / (nstate * (32 / nb + 1) * elem_bytes), cap = elem_bytes == 8 ? 12 : 16;
+  return k < 1 ? 1 : (k > cap ? cap : k);
 }
 
 template <typename T, class Model, int INTERR, int QK>
@@ -779,7 +784,7 @@ struct BlockLane {
   static constexpr bool HAS_J = (INTERR == INTERR_KRAMER);
   static constexpr int TW = 32 / NB;                 // thetas per warp
   static constexpr int PITCH = TW + 1;
-  static constexpr int K = seg_len_bl(NSTATE, NB);
+  static constexpr int K = seg_len_bl(NSTATE, NB, (int)sizeof(T));
   static constexpr int BYTES = K * NSTATE * PITCH * (int)sizeof(T);
   typedef typename MeanOf<T>::type MT;      // means, ODE evaluation and residuals: always double (rodeo_core.cuh)
   typedef FilterConsts<T, NB, P, M> Consts;
@@ -930,6 +935,18 @@ struct BlockLane {
   }
 };
 
+// output stores: written once, never read back by the kernel
+template <typename T>
+RD_DEV void store_out(T* p, T v) {
+#if defined(RODEO_STORE_CS)
+  __stcs(p, v);
+#elif defined(RODEO_STORE_WT)
+  __stwt(p, v);
+#else
+  *p = v;
+#endif
+}
+
 // copy `rows` staged time rows of `nth` thetas (buffer [slot][state][theta], pitch PITCH) to a (B, N+1, ROW) output;
 // same scheme as SegBuf::copy_out
 template <typename T, int NB, int P, int K, int PITCH, bool VAR>
@@ -955,7 +972,7 @@ RD_DEV void seg_copy_out(const T* __restrict__ base, int lane, T* __restrict__ o
   T* dst = out + (theta0 * (i64)n_rows_total + n0) * ROW + lane;
   RD_UNROLL4 for (int th = 0; th < nth; ++th) {
     RD_UNROLL for (int it = 0; it < NIT; ++it)
-      if (src[it] >= 0) dst[32 * it] = base[src[it] + th];
+      if (src[it] >= 0) store_out(dst + 32 * it, base[src[it] + th]);
     dst += stride;
   }
 }
