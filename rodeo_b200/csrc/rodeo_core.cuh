@@ -203,9 +203,18 @@ struct LogPdfAcc {
   // one eigen-direction: eigenvalue w, projected residual z
   RD_DEV void term(T w, MT z, T rw /* = 1/w */) {
     const bool keep = !(fabs(w) <= T(1e-8));   // nan counts as kept, as ~isclose(nan, 0) does
+#ifdef RODEO_LOGPDF_SELECT
     quad = rd_fma(z * z, (MT)(keep ? rw : T(0)), quad);
     ld.add(keep ? w : T(1));
     cnt += keep ? 1 : 0;
+#else
+    // three predicated instructions instead of four 32-bit selects feeding unconditional ones
+    if (keep) {
+      quad = rd_fma(z * z, (MT)rw, quad);
+      ld.add(w);
+      ++cnt;
+    }
+#endif
   }
   RD_DEV MT value() const {
     return MT(-0.5) * (quad + (MT)ld.value()) - MT(0.5) * MT(1.8378770664093454836) * (MT)cnt;

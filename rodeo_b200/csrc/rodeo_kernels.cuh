@@ -1364,8 +1364,14 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
 // ------------------------------------------------------------------------------------------------------------------
 // z_smooth: optional injected normals (B, N+1, NB, P); row N feeds the terminal draw, rows 1..N-1 the backward
 // draws.  Without it the draws come from Philox keyed by (key, particle, step).
+// 14 resident CTAs per SM for models of up to 3 blocks (a thread holding more would spill heavily): Lorenz63 goes from
+// 166 registers to 128 with 116 B spilled and BASELINE configs[2] from 37.6 to 32.8 ms -- all 2,048 warps resident at once
+// and, as for solve_sim_bl_kernel, a tighter schedule
+#ifndef RODEO_SIM_T_MINB
+#define RODEO_SIM_T_MINB 14
+#endif
 template <typename T, class Model, int INTERR, int QK, bool OBS = false>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, Model::NB <= 3 ? RODEO_SIM_T_MINB : 1)
 solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                  const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
                  T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>()) {
