@@ -68,8 +68,18 @@ def cpu_problem(B):
     return pr, ob, ind
 
 
+def host_threads():
+    """every hardware thread this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    silently turn the CPU arm into a single-thread run"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_run(pr, ob, ind, B, threads=0):
     from oracle import c_port
+    threads = threads or host_threads()
     t0 = time.perf_counter()
     out = c_port.dalton("fitzhugh_nagumo", "kramer", pr["W"], pr["X0"][:B], 0.0, T_MAX, N_STEPS, pr["Q"], pr["R"],
                         pr["theta"][:B], ob["obs_data"], ind, ob["obs_weight"], ob["obs_var"], n_threads=threads)
@@ -78,8 +88,7 @@ def cpu_run(pr, ob, ind, B, threads=0):
 
 def cpu_baseline(target_seconds=10.0):
     """theta*steps/s of the C port with all host threads on a bounded sample (about `target_seconds` of CPU work)."""
-    from oracle import c_port
-    cores = c_port.max_threads()
+    cores = host_threads()
     pr, ob, ind = cpu_problem(B_PER_GPU)
     dt, _ = cpu_run(pr, ob, ind, 2048)                      # calibration (also warms the thread pool)
     rate = 2048 * N_STEPS / dt
@@ -94,8 +103,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import c_port
-    cores = c_port.max_threads()
+    cores = host_threads()
     pr, ob, ind = cpu_problem(B_PER_GPU)
     dt, _ = cpu_run(pr, ob, ind, 2048)
     rate = 2048 * N_STEPS / dt

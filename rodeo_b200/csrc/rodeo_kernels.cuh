@@ -977,8 +977,11 @@ RD_DEV void seg_copy_out(const T* __restrict__ base, int lane, T* __restrict__ o
   }
 }
 
+#ifndef RODEO_MV_BL_MINB
+#define RODEO_MV_BL_MINB 1
+#endif
 template <typename T, class Model, int INTERR, int QK, bool OBS = false>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, RODEO_MV_BL_MINB)
 solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                    const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
                    T* __restrict__ mean_out, T* __restrict__ var_out, const ObsHook<T> oh = ObsHook<T>()) {
