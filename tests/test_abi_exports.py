@@ -44,10 +44,10 @@ def test_workspace_sizing_needs_no_gpu():
     lib = _lib.load()
     c = _lib.RodeoProblem()
     c.B, c.n_steps, c.n_block, c.n_bstate = 65536, 800, 2, 3
-    # solve_mv ((theta, block)-lane kernel): one checkpoint of n_block*(p + p(p+1)/2) = 18 doubles per K = 7 steps
-    # (ceil(800/7) - 1 = 114 of them)
+    # solve_mv ((theta, block)-lane kernel): one checkpoint of n_block*(p + p(p+1)/2) = 18 doubles per K = 9 steps
+    # (ceil(800/9) - 1 = 88 of them)
     n = lib.rodeo_b200_workspace_bytes(_lib.OP_SOLVE_MV, ctypes.byref(c), 8)
-    assert n == 114 * 18 * 65536 * 8
+    assert n == 88 * 18 * 65536 * 8
     # solve_sim / fenrir: every filtered state filt[1..N-1]
     assert lib.rodeo_b200_workspace_bytes(_lib.OP_SOLVE_SIM, ctypes.byref(c), 8) == 799 * 18 * 65536 * 8
     assert lib.rodeo_b200_workspace_bytes(_lib.OP_FENRIR, ctypes.byref(c), 8) == 799 * 18 * 65536 * 8
