@@ -769,10 +769,14 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
 // runs buy HBM efficiency until too few warps are left to keep the FP64 pipe busy.
 #define RODEO_BL_SMEM 22100
 #endif
+// float32 (mixed arithmetic, half the output bytes) is bound by instruction issue rather than by HBM and prefers more
+// resident warps: K = 7 / 9 / 16 -> 2.27 / 2.44 / 3.15 ms on the same batch
+#ifndef RODEO_BL_SMEM_F32
+#define RODEO_BL_SMEM_F32 8700
+#endif
 __host__ __device__ constexpr int seg_len_bl(int nstate, int nb, int elem_bytes = 8) {
-  // float32 rows are half as long in bytes: allow up to 16 of them (same run length as 8 rows of doubles)
-  const int k = RODEO_BL_SMEM / (nstate * (32 / nb + 1) * elem_bytes), cap = elem_bytes == 8 ? 12 : 16;
-  return k < 1 ? 1 : (k > cap ? cap : k);
+  const int k = (elem_bytes == 8 ? RODEO_BL_SMEM : RODEO_BL_SMEM_F32) / (nstate * (32 / nb + 1) * elem_bytes);
+  return k < 1 ? 1 : (k > 12 ? 12 : k);
 }
 
 template <typename T, class Model, int INTERR, int QK>

@@ -407,6 +407,49 @@ def test_dalton_full_size_matches_c_oracle_on_a_subset(rb):
     assert np.array_equal(again, got[sub])
 
 
+def test_solve_mv_full_size_matches_c_oracle_on_a_subset(rb):
+    """BASELINE configs[0] at the throughput batch: 65,536 thetas x 800 steps = 10.1 GB of output."""
+    import torch
+    from oracle import c_port
+    B = 65536
+    pr = P.fitz_problem(B, seed=0)
+    m, v = rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 40.0, 800,
+                       rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"])
+    assert m.shape == (B, 801, 2, 3) and v.shape == (B, 801, 2, 3, 3)
+    assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
+    # row 0 is (ode_init, 0) verbatim (solve.py:295-301); variances are symmetric
+    assert torch.equal(m[:, 0], torch.as_tensor(pr["X0"], device=m.device)) and not bool(v[:, 0].any())
+    assert torch.equal(v, v.transpose(-1, -2))
+    sub = np.sort(np.random.default_rng(1).choice(B, 256, replace=False))
+    om, ov = c_port.solve_mv("fitzhugh_nagumo", "kramer", pr["W"], pr["X0"][sub], 0.0, 40.0, 800, pr["Q"], pr["R"],
+                             pr["theta"][sub])
+    idx = torch.as_tensor(sub, device=m.device)
+    assert P.maxnorm_rel(_np(m[idx]), om) < TOL and P.maxnorm_rel(_np(v[idx]), ov) < TOL
+    # batch-composition invariance: the same thetas alone give bitwise the same rows
+    m2, v2 = rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"][sub], 0.0, 40.0, 800,
+                         rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"][sub])
+    assert torch.equal(m2, m[idx]) and torch.equal(v2, v[idx])
+
+
+def test_solve_sim_full_size_shards_reproduce_the_whole(rb):
+    """BASELINE configs[4], one GPU's share: 32,768 particles x solve_sim.  The 8-GPU job cuts the particle axis into
+    contiguous shards; a shard run on its own (with its particle offset) must reproduce its rows of the whole."""
+    import torch
+    B = 32768
+    pr = P.fitz_problem(B, seed=0)
+    chk = functools.partial(rb.interrogate.interrogate_chkrebtii, kalman_type="standard")
+    key = np.array([11, 12], dtype=np.uint32)
+    args = (rb.models.fitzhugh_nagumo, pr["W"])
+    x = rb.solve_sim(key, *args, pr["X0"], 0.0, 40.0, 800, chk, prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"])
+    assert x.shape == (B, 801, 2, 3) and bool(torch.isfinite(x).all())
+    lo, hi = 3 * B // 8, 4 * B // 8                                  # rank 3 of 8
+    xs = rb.solve_sim(key, *args, pr["X0"][lo:hi], 0.0, 40.0, 800, chk, prior_pars=(pr["Q"], pr["R"]),
+                      theta=pr["theta"][lo:hi], _particle_offset=lo)
+    assert P.maxnorm_rel(_np(xs), _np(x[lo:hi])) < 1e-9             # the two batch sizes may pick different lane mappings
+    # FitzHugh-Nagumo trajectories live in a bounded limit cycle (|V| < 2.2, |R| < 1.3 for theta near (.2, .2, 3))
+    assert float(x[:, :, :, 0].abs().max()) < 10.0
+
+
 # ---- NVRTC user models ------------------------------------------------------------------------------------------------
 def test_nvrtc_user_model_matches_builtin_and_oracle(rb):
     """A user right-hand side given as a CUDA string (the device-side analogue of passing any Python `ode_fun`) runs
