@@ -245,6 +245,17 @@ int rodeo_b200_mvn_logpdf_f64(int64_t B, int n, const double* x, const double* m
                               void* stream);
 
 /*
+ * MAGI log-density p(U_{0:N}, Z = 0 | theta) of a given trajectory under the block-diagonal Markov prior.
+ * Replaces: rodeo.inference.magi_logdens (src/rodeo/inference/magi.py:6-99) AFTER its `ode_expand` call, i.e. it takes the
+ * expanded solution process.  prior_weight / prior_var (n_block, n_bstate, n_bstate) HOST; ode_state
+ * (B, n_steps + 1, n_block, n_bstate) device; logdens_out (B) device.  n_block <= 8, n_bstate in 2..4,
+ * n_active in 1..n_bstate; kalman_type "standard".
+ */
+int rodeo_b200_magi_logdens_f64(int64_t B, int n_steps, int n_block, int n_bstate, int n_active,
+                                const double* prior_weight, const double* prior_var, const double* ode_state,
+                                double* logdens_out, void* stream);
+
+/*
  * Register a user ODE right-hand side given as CUDA source defining `struct UserModel` with the functor interface
  * documented in rodeo_b200/csrc/rodeo_models.cuh (rodeo_b200.models.CudaOde generates it from a one-line rhs).  The
  * kernels are compiled for sm_100a with NVRTC on first use.  Replaces: an arbitrary `ode_fun` callable passed to

@@ -262,7 +262,10 @@ def _linalg_solve(a, b):
         return _wrap(_np.full(_np.broadcast_shapes(_np.shape(b)), _np.nan))
 
 
-def _cholesky(a):
+def _cholesky(a, symmetrize_input=True):
+    a = _np.asarray(a)
+    if symmetrize_input:                    # jnp.linalg.cholesky's default: factor (A + A^H) / 2
+        a = 0.5 * (a + _np.swapaxes(a, -1, -2))
     try:
         return _wrap(_np.linalg.cholesky(a))
     except _np.linalg.LinAlgError:          # jax returns NaN for a non-PD input instead of raising
@@ -304,7 +307,19 @@ _jsl = _module(
 )
 _jss = _module("jax.scipy.special", gammaln=_wrapping(_ssp.gammaln), erf=_wrapping(_ssp.erf),
                logsumexp=_wrapping(_ssp.logsumexp))
-_mvn = types.SimpleNamespace(logpdf=_wrapping(lambda x, mean, cov: _sst.multivariate_normal.logpdf(x, mean, cov)))
+def _mvn_logpdf(x, mean, cov, allow_singular=None):
+    """jax.scipy.stats.multivariate_normal.logpdf: Cholesky factor, triangular solve, no PSD screening (unlike SciPy's,
+    which eigendecomposes and rejects / truncates small eigenvalues)."""
+    x, mean, cov = _np.asarray(x, dtype=_np.float64), _np.asarray(mean, dtype=_np.float64), _np.asarray(cov)
+    n = mean.shape[-1]
+    if cov.ndim < 2:
+        return -0.5 * (n * _np.log(2 * _np.pi) + _np.log(cov) + (x - mean) ** 2 / cov)
+    L = _np.asarray(_cholesky(cov))
+    y = _sla.solve_triangular(L, x - mean, lower=True)
+    return -0.5 * _np.sum(y * y) - n / 2.0 * _np.log(2 * _np.pi) - _np.sum(_np.log(_np.diagonal(L)))
+
+
+_mvn = types.SimpleNamespace(logpdf=_wrapping(_mvn_logpdf))
 _norm = types.SimpleNamespace(logpdf=_wrapping(lambda x, loc=0, scale=1: _sst.norm.logpdf(x, loc, scale)))
 _jst = _module("jax.scipy.stats", multivariate_normal=_mvn, norm=_norm)
 scipy = _module("jax.scipy", linalg=_jsl, special=_jss, stats=_jst, cho_factor=_jsl.cho_factor,

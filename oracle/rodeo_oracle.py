@@ -680,6 +680,34 @@ def dalton_solve_sim(model, ode_weight, ode_init, t_min, t_max, n_steps, interro
     return xs
 
 
+def magi_logdens(ode_state, n_active, prior_pars):
+    """reference src/rodeo/inference/magi.py:6-99 after its ``ode_expand`` call: ``ode_state`` (B, N+1, nb, p) is the
+    expanded solution process.  Noise-free observation of the first ``n_active`` state entries of every block; the
+    log-density is the Cholesky-type one of jax.scipy.stats.multivariate_normal.logpdf (no eigenvalue cut-off)."""
+    X = np.asarray(ode_state, dtype=np.float64)
+    B, N1, nb, p = X.shape
+    Q, R = _bq(prior_pars[0], B), _bq(prior_pars[1], B)
+    W = np.broadcast_to(np.eye(n_active, p), (B, nb, n_active, p))
+    zero_m, zero_v = np.zeros((B, nb, n_active)), np.zeros((B, nb, n_active, n_active))
+    mean_state = np.zeros((B, nb, p))
+    m, v = X[:, 0], np.zeros((B, nb, p, p))
+    total = np.zeros(B)
+    for n in range(1, N1):
+        x_meas = X[:, n, :, :n_active]
+        mp, vp = predict(m, v, mean_state, Q, R)
+        mf, vf = forecast(mp, vp, zero_m, W, zero_v)
+        try:
+            L = np.linalg.cholesky(0.5 * (vf + _T(vf)))      # jnp.linalg.cholesky symmetrises its input
+        except np.linalg.LinAlgError:                        # ... and returns NaN where LAPACK reports failure
+            return np.full(B, np.nan)
+        z = np.linalg.solve(L, (x_meas - mf)[..., None])[..., 0]
+        logp = -0.5 * np.sum(z * z, -1) - np.sum(np.log(np.diagonal(L, axis1=-2, axis2=-1)), -1) \
+            - 0.5 * n_active * math.log(2 * math.pi)
+        total += logp.sum(-1)
+        m, v = update(mp, vp, x_meas, zero_m, W, zero_v)
+    return total
+
+
 # ----------------------------------------------------------------------------------------------------
 # square-root Kalman family  (reference src/rodeo/kalmantv/square_root.py, src/rodeo/utils.py:10-24)
 # variances are carried as lower-triangular factors L (var = L L^T); only L L^T is comparable across

@@ -10,3 +10,4 @@ from .basic import basic
 from . import fenrir as fenrir_module
 from .fenrir import fenrir, solve_mv as fenrir_solve_mv
 from .dalton import dalton, solve_mv as dalton_solve_mv, solve_sim as dalton_solve_sim
+from .magi import magi_logdens

@@ -298,6 +298,40 @@ def build():
     out["fitzsig_mean"], out["fitzsig_var"], out["fitzsig_dalton"] = np.stack(ms_), np.stack(vs_), np.array(ll_)
 
     # ===============================================================================================================
+    # MAGI log-density (inference/magi.py): trajectories = the kramer posterior means above plus noise, expanded as the
+    # ODE prescribes -- FitzHugh-Nagumo (x, f(x, theta), 0), second-order ODE (x, x', sin(w t) - k x, 0).
+    # n_active = 1 is the well-conditioned case.  With n_active >= 2 the reference's covariance-form recursion observes
+    # two or three entries of a block without noise, loses the symmetry of its variance within ~10 steps and becomes
+    # rounding-dominated (two float64 evaluations of the same formulas differ by ~1e-2): those values are stored as
+    # *_illcond and only checked loosely.
+    # ===============================================================================================================
+    rngm = np.random.default_rng(17)
+    U = out["fitz_kramer_mean"][:, :, :, 0:1] + 0.01 * rngm.standard_normal((3, 61, 2, 1))
+    out["magi_fitz_in_U"] = U
+
+    def fitz_expand(U_, **params):                     # (N+1, nb, 1) -> (N+1, nb, 3)
+        f = jax.vmap(lambda u: fitz_fun(u, 0.0, **params)[:, 0])(U_)
+        return jnp.concatenate([U_, f[:, :, None], jnp.zeros(U_.shape)], axis=2)
+
+    def magi(U_, expand, na, prior, th):
+        return float(rodeo.inference.magi_logdens(jnp.array(U_), expand, na, prior, "standard", theta=jnp.array(th)))
+    out["magi_fitz"] = np.array([magi(U[i], fitz_expand, 1, pp, pr["theta"][i]) for i in range(3)])
+    out["magi_fitz_illcond"] = np.array([magi(U[i], fitz_expand, 2, pp, pr["theta"][i]) for i in range(3)])
+    out["magi_fitz_state"] = np.stack([A(fitz_expand(jnp.array(U[i]), theta=jnp.array(pr["theta"][i]))) for i in range(3)])
+    U2 = out["so_mean"][:, :, :, 0:2] + 0.01 * rngm.standard_normal((2, 81, 1, 2))
+    out["magi_so_in_U"] = U2
+
+    def so_expand(U_, **params):                       # (x, x') -> (x, x', sin(w t) - k x, 0)
+        w, k = params["theta"]
+        t = jnp.linspace(0.0, 4.0, 81)
+        xdd = jnp.sin(w * t)[:, None] - k * U_[:, :, 0]
+        return jnp.concatenate([U_, xdd[:, :, None], jnp.zeros(U_[:, :, 0:1].shape)], axis=2)
+    pp2 = (jnp.array(pr2["Q"]), jnp.array(pr2["R"]))
+    out["magi_so"] = np.array([magi(U2[i], so_expand, 1, pp2, pr2["theta"][i]) for i in range(2)])
+    out["magi_so_illcond"] = np.array([magi(U2[i], so_expand, 3, pp2, pr2["theta"][i]) for i in range(2)])
+    out["magi_so_state"] = np.stack([A(so_expand(jnp.array(U2[i]), theta=jnp.array(pr2["theta"][i]))) for i in range(2)])
+
+    # ===============================================================================================================
     # Kalman primitives on random inputs (kalmantv/standard.py), incl. the log-pdf's 1e-8 eigenvalue cut-off
     # ===============================================================================================================
     rng = np.random.default_rng(99)

@@ -127,6 +127,18 @@ def test_oracle_theta_dependent_prior():
     assert ll_err(orc.dalton(*a, *o), G["fitzsig_dalton"]) < 1e-11
 
 
+def test_oracle_magi_logdens():
+    pr, _ = prob("fitz")
+    pr2, _ = prob("so")
+    assert ll_err(orc.magi_logdens(G["magi_fitz_state"], 1, (pr["Q"], pr["R"])), G["magi_fitz"]) / 1e8 < 1e-12
+    assert ll_err(orc.magi_logdens(G["magi_so_state"], 1, (pr2["Q"], pr2["R"])), G["magi_so"]) / 1e8 < 1e-12
+    assert np.max(np.abs(orc.magi_logdens(G["magi_fitz_state"], 1, (pr["Q"], pr["R"])) / G["magi_fitz"] - 1)) < 1e-12
+    # n_active >= 2: the reference's recursion is rounding-dominated (see make_reference_golden.py): two float64
+    # evaluations of its formulas differ by tens of percent -- same order of magnitude only
+    got = orc.magi_logdens(G["magi_so_state"], 3, (pr2["Q"], pr2["R"]))
+    assert np.all(np.isfinite(got)) and np.all((got / G["magi_so_illcond"] > 1 / 3) & (got / G["magi_so_illcond"] < 3))
+
+
 def test_oracle_kalman_primitives():
     k = {n[7:]: G[n] for n in G.files if n.startswith("kal_in_")}
     pm, pS = orc.predict(k["mu"], k["S"], k["c"], k["Qm"], k["Rm"])
@@ -240,6 +252,35 @@ def test_cuda_theta_dependent_prior(rb):
     m, v = rb.solve_mv(*a, **kw)
     assert P.maxnorm_rel(_np(m), G["fitzsig_mean"]) < TOL and P.maxnorm_rel(_np(v), G["fitzsig_var"]) < TOL
     assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G["fitzsig_dalton"]) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_magi_logdens(rb):
+    """rodeo.inference.magi_logdens with the user's own ode_expand (plain NumPy here), batched over trajectories and
+    un-batched, against the reference's values."""
+    pr, _ = prob("fitz")
+
+    def expand(U, theta):                                # (B, N+1, nb, 1) -> (B, N+1, nb, 3): (x, f(x, theta), 0)
+        x = U[..., 0]
+        f = np.stack([P.fitz_rhs(x[:, n], theta) for n in range(x.shape[1])], axis=1)
+        return np.concatenate([U, f[..., None], np.zeros_like(U)], axis=-1)
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) / b - 1)))
+    got = rb.inference.magi_logdens(G["magi_fitz_in_U"], expand, 1, (pr["Q"], pr["R"]), "standard", theta=pr["theta"])
+    assert got.shape == (3,) and rel(_np(got), G["magi_fitz"]) < TOL
+    one = rb.inference.magi_logdens(G["magi_fitz_in_U"][1], lambda U, theta: expand(U[None], theta[None])[0], 1,
+                                    (pr["Q"], pr["R"]), theta=pr["theta"][1])
+    assert one.dim() == 0 and rel(float(one), G["magi_fitz"][1]) < TOL
+    pr2, _ = prob("so")
+    got = rb.inference.magi_logdens(None, lambda U, **kw: G["magi_so_state"], 1, (pr2["Q"], pr2["R"]))
+    assert rel(_np(got), G["magi_so"]) < TOL
+    # n_active >= 2: rounding-dominated in the reference itself (float64 evaluations of the same formulas differ by a
+    # factor of 2..4 on these inputs); the kernel (packed symmetric variances) must stay finite
+    for na, state, want, prior in ((2, "magi_fitz_state", "magi_fitz_illcond", (pr["Q"], pr["R"])),
+                                  (3, "magi_so_state", "magi_so_illcond", (pr2["Q"], pr2["R"]))):
+        got = _np(rb.inference.magi_logdens(None, lambda U, **kw: G[state], na, prior))
+        assert np.all(np.isfinite(got)) and np.all(got < 0) and np.all(np.isfinite(G[want]))
+    with pytest.raises(NotImplementedError):
+        rb.inference.magi_logdens(None, lambda U, **kw: G["magi_so_state"], 3, (pr2["Q"], pr2["R"]), "square-root")
 
 
 @pytest.mark.gpu
