@@ -44,3 +44,14 @@ def ibm_init(dt, n_deriv, sigma):
     Q = np.repeat(Q1[None], len(sigma), axis=0)
     R = np.stack([sigma[b] ** 2 * R1 for b in range(len(sigma))])
     return Q, R
+
+
+def indep_init(prior_pars):
+    """Combine blocks of prior parameters into dense (1, n_block*p, n_block*p) matrices -- reference
+    src/rodeo/prior/indep_init.py:8-23.  Host-side helper for code that wants the non-blocked form (the reference's
+    examples/solve_nb.py); the kernels themselves run the blocked form and reject a model whose block shape differs
+    from the one it was compiled for."""
+    import scipy.linalg
+    prior_weight, prior_var = (np.asarray(a.detach().cpu().numpy() if hasattr(a, "detach") else a, dtype=np.float64)
+                               for a in prior_pars)
+    return scipy.linalg.block_diag(*prior_weight)[None, :], scipy.linalg.block_diag(*prior_var)[None, :]

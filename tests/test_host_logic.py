@@ -13,11 +13,16 @@ def test_public_names_mirror_the_reference():
     # reference src/rodeo/__init__.py:1-6 and src/rodeo/inference/__init__.py:1-3
     for name in ("solve_mv", "solve_sim", "interrogate", "prior", "inference", "utils"):
         assert hasattr(rodeo_b200, name)
-    for name in ("basic", "fenrir", "dalton"):
+    for name in ("basic", "fenrir", "dalton", "magi_logdens"):
         assert hasattr(rodeo_b200.inference, name)
     for name in ("interrogate_kramer", "interrogate_chkrebtii", "interrogate_schober", "interrogate_rodeo"):
         assert hasattr(rodeo_b200.interrogate, name)
     assert hasattr(rodeo_b200.prior, "ibm_init") and hasattr(rodeo_b200.utils, "first_order_pad")
+    # reference src/rodeo/prior/__init__.py:1-2
+    Q, R = rodeo_b200.prior.ibm_init(0.1, 3, [0.1, 0.2])
+    Qd, Rd = rodeo_b200.prior.indep_init((Q, R))
+    assert Qd.shape == (1, 6, 6) and np.array_equal(Qd[0, 3:, 3:], Q[1]) and not Qd[0, :3, 3:].any()
+    assert np.array_equal(Rd[0, :3, :3], R[0])
 
 
 def test_interrogation_objects_resolve_by_identity():
