@@ -375,8 +375,11 @@ struct Fwd {
 // warp); 65,536 thetas are 2,048 two-filter warps = 3.46 per sub-partition (rounds up to 4, 13.5% idle) but 4,096
 // one-filter warps of half the cost = 6.92 (rounds up to 7, 1.2% idle).  It also halves the live state per thread,
 // so the kernel fits 128 registers (4 resident warps per sub-partition) without spilling.
+#ifndef RODEO_DALTON_MINB
+#define RODEO_DALTON_MINB 16
+#endif
 template <typename T, class Model, int INTERR, int QK, int NOBS>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, RODEO_DALTON_MINB)
 dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ loglik) {
   typedef Fwd<T, Model, INTERR, QK> F;
