@@ -1239,6 +1239,9 @@ solve_mv_sqrt_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P
 // warps per SM sub-partition), so spreading the blocks over lanes is mainly about parallelism.  Every filtered state
 // is kept in HBM (per-lane loads are 9 doubles, prefetched one step ahead in registers); shared memory only stages
 // the draws so that they leave as runs of K time rows per theta.
+// (Checkpointing every second state and re-running the odd forward steps, which pays for the one-lane-per-theta kernel,
+// does not here: 2.09 -> 2.26 ms on BASELINE configs[4] -- at 3.5 warps per scheduler the extra instructions cost more
+// than the saved traffic.)
 
 // 14 resident one-warp CTAs per SM (what the 13 KB staging buffer allows): BASELINE configs[4] gives one GPU 32,768
 // particles = 2,048 warps = 13.8 per SM; at 12 CTAs per SM (148 registers) the launch was 1.15 waves.  With the bound
@@ -1377,6 +1380,9 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
 // 14 resident CTAs per SM for models of up to 3 blocks (a thread holding more would spill heavily): Lorenz63 goes from
 // 166 registers to 128 with 116 B spilled and BASELINE configs[2] from 37.6 to 32.8 ms -- all 2,048 warps resident at once
 // and, as for solve_sim_bl_kernel, a tighter schedule
+#ifndef RODEO_SIM_T_RECOMPUTE
+#define RODEO_SIM_T_RECOMPUTE 1
+#endif
 #ifndef RODEO_SIM_T_MINB
 #define RODEO_SIM_T_MINB 14
 #endif
@@ -1399,7 +1405,12 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   F f;
   f.init(a.ode_init + idx * NB * P);
   f.load_scale(a, idx);
-  forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb, hook);
+  // History: one checkpoint per shared-memory segment, the rest re-run (KC == K), as solve_mv does.  The sampling
+  // solvers are bound by HBM traffic too -- storing and re-loading every filtered state is 2 x 8 x NSTATE bytes per
+  // theta*step against 8 x NB x P of output -- and re-running a forward step reproduces its chkrebtii draw exactly
+  // because the random numbers are counter-based.
+  constexpr int KC = RODEO_SIM_T_RECOMPUTE ? K : 1;
+  forward_with_checkpoints<T, Model, INTERR, QK, KC>(C, a, q, idx, live, f, stash, ldb, hook);
 
   auto normals = [&](int n, T (&z)[NB * P]) {
     if (z_smooth != nullptr) {
@@ -1439,7 +1450,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   for (int j = (N - 1) / K; j >= 0; --j) {
     const int n0 = j * K;
     const int cnt = (N - n0) < K ? (N - n0) : K;
-    rebuild_segment<T, Model, INTERR, QK, 1>(C, a, q, idx, j, cnt, f, stash, ldb, buf);
+    rebuild_segment<T, Model, INTERR, QK, KC>(C, a, q, idx, j, cnt, f, stash, ldb, buf, hook);
     for (int s = cnt - 1; s >= 0; --s) {
       if (n0 + s == 0) break;                              // row 0 = ode_init: x0 is known, not sampled (solve.py:202-204)
       buf.get(s, f.mu, f.S);                               // filt[n]
@@ -1463,7 +1474,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
       RD_UNROLL for (int b = 0; b < NB; ++b)
         RD_UNROLL for (int i = 0; i < P; ++i) { x[b][i] = xn[b][i]; buf.at(s, b * P + i) = (T)xn[b][i]; }
     }
-    if (j > 0) prefetch_segment<T, F, 1>(stash, ldb, idx, j - 1, K);
+    if (j > 0) prefetch_segment<T, F, KC>(stash, ldb, idx, j - 1, K);
     __syncwarp();
     buf.template copy_out<false>(x_out, theta0, a.B, N + 1, n0, cnt);
     __syncwarp();
