@@ -984,11 +984,11 @@ RD_DEV void seg_copy_out(const T* __restrict__ base, int lane, T* __restrict__ o
   }
 }
 
-#ifndef RODEO_MV_BL_MINB
-#define RODEO_MV_BL_MINB 1
-#endif
+// (no minimum-blocks bound: an explicit 1 lets ptxas take 162 registers, which is harmless for float64 -- shared memory
+// caps the residency at 10 CTAs per SM -- but costs the float32 instantiation a third of its resident warps; caps of
+// 18 / 20 CTAs per SM (96 registers, spills) are 6 % / 12 % slower)
 template <typename T, class Model, int INTERR, int QK, bool OBS = false>
-__global__ void __launch_bounds__(32, RODEO_MV_BL_MINB)
+__global__ void __launch_bounds__(32)
 solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                    const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
                    T* __restrict__ mean_out, T* __restrict__ var_out, const ObsHook<T> oh = ObsHook<T>()) {
