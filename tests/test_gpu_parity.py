@@ -604,6 +604,20 @@ def test_ragged_batches_and_output_canaries(rb, B):
         assert torch.equal(b_.view(B), a[:B])
 
 
+def test_empty_batch(rb):
+    """B = 0: every entry point returns correctly shaped empty tensors and launches nothing out of bounds."""
+    pr = P.fitz_problem(4, n_steps=20, t_max=1.0, seed=2)
+    ob = P.fitz_obs(pr, None, n_obs=3)
+    kr = rb.interrogate.interrogate_kramer
+    a = (None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"][:0], 0.0, 1.0, 20, kr)
+    kw = dict(prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"][:0])
+    m, v = rb.solve_mv(*a, **kw)
+    assert m.shape == (0, 21, 2, 3) and v.shape == (0, 21, 2, 3, 3)
+    assert rb.solve_sim(1, *a[1:], **kw).shape == (0, 21, 2, 3)
+    assert rb.inference.dalton(*a, **kw, **ob).shape == (0,)
+    assert rb.inference.fenrir(*a, **kw, **ob).shape == (0,)
+
+
 # ---- data-adaptive solvers (SURVEY 8(f2)) ---------------------------------------------------------------------------------
 def test_dalton_data_adaptive_solvers(rb):
     """rodeo.inference.dalton.solve_mv / solve_sim (dalton.py:374-545): observations enter the forward filter."""
