@@ -24,7 +24,7 @@ struct DaltonRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    dalton_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(2 * p.B, 32), 32, 0, s>>>(C, a, o, out);
+    dalton_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 64, 0, s>>>(C, a, o, out);     // joint warp + marginal warp
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;

@@ -378,15 +378,24 @@ struct Fwd {
 #ifndef RODEO_DALTON_MINB
 #define RODEO_DALTON_MINB 16
 #endif
+// Two launch geometries.  64-thread CTAs (what the library launches): warp 0 runs the joint filters of 32 thetas, warp 1
+// their marginal filters, and the two meet through shared memory.  The filters differ only on the n_obs observation
+// steps, where the joint one takes the augmented (ODE row + observation row) update, about three times the plain one:
+// with both kinds interleaved in a warp every observation step executed BOTH paths for all 32 lanes (40 of 800 steps
+// cost 4 plain updates, 15 % of the run time); warp-uniform kinds pay 3 + 1 instead of 4 + 4.  32-thread CTAs (the NVRTC
+// launcher): lanes 2k / 2k+1 are the two filters of a theta and meet in a shuffle.
 template <typename T, class Model, int INTERR, int QK, int NOBS>
-__global__ void __launch_bounds__(32, RODEO_DALTON_MINB)
+__global__ void __launch_bounds__(64, RODEO_DALTON_MINB / 2)
 dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ loglik) {
   typedef Fwd<T, Model, INTERR, QK> F;
   constexpr int NB = F::NB, P = F::P, M = F::M, JC = F::JC, MS = F::MS;
-  const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool joint = (tid & 1) == 0;
-  i64 idx = tid >> 1;
+  __shared__ double marg[32];
+  const bool split = blockDim.x == 64;
+  const int lane = threadIdx.x & 31;
+  const i64 tid = (i64)blockIdx.x * 32 + lane;
+  const bool joint = split ? threadIdx.x < 32 : (tid & 1) == 0;
+  i64 idx = split ? tid : (tid >> 1);
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;                 // keep the whole warp in the loop for the final shuffle
   typedef typename F::MT MT;
@@ -438,7 +447,14 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     acc.ld.renorm();
   }
   const MT mine = acc.value();
-  const MT other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  MT other;
+  if (split) {
+    if (!joint) marg[lane] = mine;
+    __syncthreads();
+    other = marg[lane];
+  } else {
+    other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  }
   if (joint && live) loglik[idx] = (T)(mine - other);          // logdens_joint - logdens_marg (dalton.py:235)
 }
 
