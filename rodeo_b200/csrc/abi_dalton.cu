@@ -24,7 +24,16 @@ struct DaltonRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    dalton_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 64, 0, s>>>(C, a, o, out);     // joint warp + marginal warp
+    CommonArgs<real_t> ag = a;
+    if (sizeof(real_t) == 8) {
+      // joint CTAs, then marginal CTAs, each adding +/- its log-density to the zeroed output (rodeo_kernels.cuh)
+      ag.dalton_geometry = 2;
+      RODEO_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)p.B * sizeof(real_t), s));
+      dalton_kernel<real_t, Model, INTERR, QK, 1><<<2 * grid_for(p.B, 32), 32, 0, s>>>(C, ag, o, out);
+    } else {
+      ag.dalton_geometry = 1;      // joint warp + marginal warp per CTA: the difference is formed in double
+      dalton_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 64, 0, s>>>(C, ag, o, out);
+    }
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;

@@ -68,6 +68,7 @@ inline CommonArgs<T> make_common(const RodeoProblem& p, const T* ode_init, const
   a.t_min = (T)p.t_min; a.t_max = (T)p.t_max;
   a.theta = theta; a.ode_init = ode_init; a.key0 = p.key[0]; a.key1 = p.key[1]; a.z_interr = z_interr;
   a.r_scale = (const T*)p.prior_var_scale;
+  a.dalton_geometry = 0;
   return a;
 }
 

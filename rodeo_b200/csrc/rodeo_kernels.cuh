@@ -38,6 +38,7 @@ struct CommonArgs {
   unsigned key0, key1;    // PRNG key (the reference's uint32[2] jax key)
   const T* z_interr;      // optional injected normals for interrogate_chkrebtii, (B, n_steps, NSTREAM, NB, P)
   const T* r_scale;       // optional per-theta scale of the prior variance, (B, NB): R(theta, b) = r_scale * R[b]
+  int dalton_geometry;    // dalton_kernel only: how the joint and marginal filters of a theta are laid out (see there)
 };
 
 template <typename T>
@@ -378,12 +379,16 @@ struct Fwd {
 #ifndef RODEO_DALTON_MINB
 #define RODEO_DALTON_MINB 16
 #endif
-// Two launch geometries.  64-thread CTAs (what the library launches): warp 0 runs the joint filters of 32 thetas, warp 1
-// their marginal filters, and the two meet through shared memory.  The filters differ only on the n_obs observation
-// steps, where the joint one takes the augmented (ODE row + observation row) update, about three times the plain one:
-// with both kinds interleaved in a warp every observation step executed BOTH paths for all 32 lanes (40 of 800 steps
-// cost 4 plain updates, 15 % of the run time); warp-uniform kinds pay 3 + 1 instead of 4 + 4.  32-thread CTAs (the NVRTC
-// launcher): lanes 2k / 2k+1 are the two filters of a theta and meet in a shuffle.
+// Three launch geometries (CommonArgs::dalton_geometry).  The filters differ only on the n_obs observation steps, where
+// the joint one takes the augmented (ODE row + observation row) update, about three times the plain one; with both kinds
+// interleaved in a warp every observation step executes BOTH paths for all 32 lanes (8 % more FP64 instructions).
+//   0  32-thread CTAs, lanes 2k / 2k+1 are the two filters of a theta and meet in a shuffle (the NVRTC launcher);
+//   1  64-thread CTAs, warp 0 = joint filters of 32 thetas, warp 1 = their marginal filters, meeting in shared memory
+//      (float32 output: the difference must be formed in double before it is rounded).  The lighter marginal warp idles
+//      until its partner is done: 0.845 ms on BASELINE configs[1];
+//   2  32-thread CTAs, the first half of the grid runs joint filters, the second half marginal ones (heavier CTAs first),
+//      and each adds +/- its log-density to the zero-initialised output with one atomicAdd per theta.  0 + a - b and
+//      0 - b + a are both exactly fl(a - b), so the result is bitwise the one of the other geometries (float64 output).
 template <typename T, class Model, int INTERR, int QK, int NOBS>
 __global__ void __launch_bounds__(64, RODEO_DALTON_MINB / 2)
 dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
@@ -391,11 +396,12 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   typedef Fwd<T, Model, INTERR, QK> F;
   constexpr int NB = F::NB, P = F::P, M = F::M, JC = F::JC, MS = F::MS;
   __shared__ double marg[32];
-  const bool split = blockDim.x == 64;
+  const int geo = a.dalton_geometry;
   const int lane = threadIdx.x & 31;
-  const i64 tid = (i64)blockIdx.x * 32 + lane;
-  const bool joint = split ? threadIdx.x < 32 : (tid & 1) == 0;
-  i64 idx = split ? tid : (tid >> 1);
+  const i64 half = gridDim.x >> 1;
+  const i64 tid = (i64)(geo == 2 && (i64)blockIdx.x >= half ? (i64)blockIdx.x - half : (i64)blockIdx.x) * 32 + lane;
+  const bool joint = geo == 2 ? (i64)blockIdx.x < half : (geo == 1 ? threadIdx.x < 32 : (tid & 1) == 0);
+  i64 idx = geo == 0 ? (tid >> 1) : tid;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;                 // keep the whole warp in the loop for the final shuffle
   typedef typename F::MT MT;
@@ -447,15 +453,22 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     acc.ld.renorm();
   }
   const MT mine = acc.value();
+  // logdens_joint - logdens_marg (dalton.py:235)
+  if constexpr (sizeof(T) == 8) {
+    if (geo == 2) {
+      if (live) atomicAdd(loglik + idx, joint ? mine : -mine);
+      return;
+    }
+  }
   MT other;
-  if (split) {
+  if (geo == 1) {
     if (!joint) marg[lane] = mine;
     __syncthreads();
     other = marg[lane];
   } else {
     other = __shfl_xor_sync(0xffffffffu, mine, 1);
   }
-  if (joint && live) loglik[idx] = (T)(mine - other);          // logdens_joint - logdens_marg (dalton.py:235)
+  if (joint && live) loglik[idx] = (T)(mine - other);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
