@@ -1,6 +1,8 @@
 // Host-buffer convenience entry points (include/rodeo_b200.h: rodeo_b200_*_host): every pointer is HOST memory.
 // They stage inputs into a cached device arena, call the device-pointer entry point, copy the result back and
 // synchronise.  The arena only ever grows, so steady-state calls perform no allocation.
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "rodeo_host.h"
@@ -17,7 +19,10 @@ struct Arena {
   cudaStream_t stream = nullptr;
   // chunked pipeline of the log-likelihood entry points: chunk c's inputs travel on `stream`, its kernel runs on
   // lane[c] as soon as they have landed (ready[c]) and `stream` collects the results after done[c]
-  static constexpr int NCHUNK = 4;
+  static constexpr int NCHUNK = 8;
+  // pinned staging for the small per-call arrays (observation tables): one H2D copy instead of one per array
+  static constexpr size_t STAGE_BYTES = 256 << 10;
+  char* stage = nullptr;
   cudaStream_t lane[NCHUNK] = {};
   cudaEvent_t ready[NCHUNK] = {}, done[NCHUNK] = {};
 
@@ -25,6 +30,7 @@ struct Arena {
     used = 0;
     if (!stream) {
       RODEO_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      RODEO_CUDA_OK(cudaHostAlloc((void**)&stage, STAGE_BYTES, cudaHostAllocDefault));
       for (int c = 0; c < NCHUNK; ++c) {
         RODEO_CUDA_OK(cudaStreamCreateWithFlags(&lane[c], cudaStreamNonBlocking));
         RODEO_CUDA_OK(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
@@ -46,6 +52,8 @@ struct Arena {
     if (base) cudaFree(base);
     if (stream) {
       cudaStreamDestroy(stream);
+      if (stage) cudaFreeHost(stage);
+      stage = nullptr;
       for (int c = 0; c < NCHUNK; ++c) {
         cudaStreamDestroy(lane[c]); cudaEventDestroy(ready[c]); cudaEventDestroy(done[c]);
         lane[c] = nullptr; ready[c] = nullptr; done[c] = nullptr;
@@ -85,15 +93,33 @@ extern "C" int rodeo_b200_dalton_f64_host(const RodeoProblem* p, const double* o
   double* d_D = (double*)g_arena.take(b_D);
   double* d_Om = (double*)g_arena.take(b_Om);
   cudaStream_t s = g_arena.stream;
-  RODEO_CUDA_OK(cudaMemcpyAsync(d_ind, obs_ind, b_ind, cudaMemcpyHostToDevice, s));
-  RODEO_CUDA_OK(cudaMemcpyAsync(d_y, obs_data, b_y, cudaMemcpyHostToDevice, s));
-  RODEO_CUDA_OK(cudaMemcpyAsync(d_D, obs_weight, b_D, cudaMemcpyHostToDevice, s));
-  RODEO_CUDA_OK(cudaMemcpyAsync(d_Om, obs_var, b_Om, cudaMemcpyHostToDevice, s));
-  // The theta batch is independent per theta, so it is cut into NCHUNK contiguous chunks: chunk c's kernel starts as
+  // the four observation tables sit back to back in the arena (d_ind .. d_Om): stage them with the same layout in
+  // pinned memory and send them as one copy (the previous call has synchronised, so the staging buffer is free)
+  const size_t obs_span = (size_t)((char*)d_Om - (char*)d_ind) + b_Om;
+  if (obs_span <= Arena::STAGE_BYTES) {
+    char* st = g_arena.stage;
+    memcpy(st, obs_ind, b_ind);
+    memcpy(st + ((char*)d_y - (char*)d_ind), obs_data, b_y);
+    memcpy(st + ((char*)d_D - (char*)d_ind), obs_weight, b_D);
+    memcpy(st + ((char*)d_Om - (char*)d_ind), obs_var, b_Om);
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_ind, st, obs_span, cudaMemcpyHostToDevice, s));
+  } else {
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_ind, obs_ind, b_ind, cudaMemcpyHostToDevice, s));
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_y, obs_data, b_y, cudaMemcpyHostToDevice, s));
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_D, obs_weight, b_D, cudaMemcpyHostToDevice, s));
+    RODEO_CUDA_OK(cudaMemcpyAsync(d_Om, obs_var, b_Om, cudaMemcpyHostToDevice, s));
+  }
+  // The theta batch is independent per theta, so it is cut into two contiguous chunks (up to NCHUNK with RODEO_HOST_CHUNKS): chunk c's kernel starts as
   // soon as its own X0 / theta rows have landed, while the next chunk's rows are still crossing PCIe; the kernels run
   // on separate streams so they share the GPU instead of queueing behind each other's tails.  Results are identical to
   // one launch (per-theta arithmetic; random streams are keyed by the global particle index).
-  const int nchunk = B >= (size_t)Arena::NCHUNK * 8192 ? Arena::NCHUNK : 1;
+  // measured on B200 (65,536 thetas, FN dalton): 1 / 2 / 4 / 8 chunks -> 57.7 / 59.5 / 57.6 / 56.3 G theta*steps/s end to
+  // end: the kernel is FP64-bound, so every extra chunk costs a little tail; two hide half of the PCIe transfer
+  int nchunk = B >= 32768 ? 2 : 1;
+  if (const char* e = getenv("RODEO_HOST_CHUNKS")) {                       // tuning experiments
+    const int v = atoi(e);
+    if (v >= 1 && v <= Arena::NCHUNK && (size_t)v <= B) nchunk = v;
+  }
   const size_t per = (B + nchunk - 1) / nchunk;
   const size_t row_init = nb * ps, row_theta = (size_t)p->n_theta;
   for (int c = 0; c < nchunk; ++c) {
