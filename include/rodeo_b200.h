@@ -42,7 +42,8 @@ extern "C" {
 /* rodeo.interrogate.interrogate_*   (src/rodeo/interrogate.py) */
 enum { RODEO_INTERROGATE_KRAMER = 0, RODEO_INTERROGATE_CHKREBTII = 1, RODEO_INTERROGATE_SCHOBER = 2,
        RODEO_INTERROGATE_RODEO = 3 };
-/* kalman_type (src/rodeo/solve.py:236-241); only the covariance form is built so far */
+/* kalman_type (src/rodeo/solve.py:236-241).  RodeoProblem.kalman_type must be RODEO_KALMAN_STANDARD for the generic
+ * entry points; the square-root form has its own entry points (rodeo_b200_solve_mv_sqrt_*, rodeo_b200_sqrt_*) */
 enum { RODEO_KALMAN_STANDARD = 0, RODEO_KALMAN_SQUARE_ROOT = 1 };
 /* built-in ODE right-hand sides; ids >= RODEO_MODEL_USER_BASE come from rodeo_b200_register_model_nvrtc() */
 enum { RODEO_MODEL_FITZHUGH_NAGUMO = 0, RODEO_MODEL_LORENZ63 = 1, RODEO_MODEL_SECOND_ORDER_SIN = 2,
@@ -71,9 +72,10 @@ typedef struct RodeoProblem {
   double t_min, t_max;
   int32_t user_wcol;       /* user (NVRTC) models only: the ODE is X[:, user_wcol] = f(X, t), i.e. W = e_user_wcol  */
   int32_t reserved;
-  /* optional DEVICE pointer (B, n_block), same arithmetic type as the call, or NULL: per-theta scale of the prior
+  /* optional pointer (B, n_block), same arithmetic type as the call, or NULL: per-theta scale of the prior
    * variance, R(theta, b) = prior_var_scale[theta, b] * prior_var[b].  Covers an IBM prior whose sigma is part of
-   * theta (sigma^2 R_1, src/rodeo/prior/ibm.py:84-86) without a (B, n_block, p, p) array. */
+   * theta (sigma^2 R_1, src/rodeo/prior/ibm.py:84-86) without a (B, n_block, p, p) array.  A DEVICE pointer for the
+   * device-pointer entry points; a HOST pointer (float64) for the `*_host` wrappers, which stage it themselves. */
   const void* prior_var_scale;
 } RodeoProblem;
 
@@ -82,6 +84,8 @@ size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* prob, int elem_byt
 
 const char* rodeo_b200_last_error(void);
 int rodeo_b200_abi_version(void);
+/* sizeof(struct RodeoProblem) as this library was compiled: lets a binding check its own mirror of the struct */
+size_t rodeo_b200_problem_sizeof(void);
 
 /*
  * Common inputs:

@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "librodeo_oracle.so")
 MODEL_IDS = {"fitzhugh_nagumo": 0, "lorenz63": 1, "second_order_sin": 2, "hes1": 3, "seirah": 4}
 INTERR_IDS = {"kramer": 0, "chkrebtii": 1, "schober": 2, "rodeo": 3}
+_SO_LD = os.path.join(_HERE, "_build", "librodeo_oracle_ld.so")
 _lib = None
+_lib_ld = None
 
 
 def build():
@@ -41,9 +43,25 @@ def max_threads():
     return int(load().rodeo_oracle_max_threads())
 
 
+def load_ld():
+    """the same C source compiled with `long double` arithmetic (x87, 64-bit mantissa)"""
+    global _lib_ld
+    if _lib_ld is None:
+        if not os.path.exists(_SO_LD):
+            build()
+        _lib_ld = ctypes.CDLL(_SO_LD)
+    return _lib_ld
+
+
+def dalton_ld(*args, **kw):
+    """dalton evaluated in extended precision and rounded once to float64: the 'exact' value the float64 noise floor
+    of the log-likelihood is measured against (same recursion, ~2000x finer rounding)."""
+    return dalton(*args, _lib_override=load_ld(), **kw)
+
+
 def dalton(model, interr, W, X0, t_min, t_max, n_steps, Q, R, theta, obs_data, obs_ind, obs_weight, obs_var,
-           n_threads=0):
-    lib = load()
+           n_threads=0, _lib_override=None):
+    lib = _lib_override or load()
     W, X0, Q, R, theta = _c(W), _c(X0), _c(Q), _c(R), _c(theta)
     obs_data, obs_weight, obs_var, obs_ind = _c(obs_data), _c(obs_weight), _c(obs_var), _c(obs_ind, np.int32)
     B, nb, p = X0.shape

@@ -23,6 +23,25 @@
 #include <omp.h>
 #endif
 
+/* arithmetic type: double (the baseline / checker) or, with -DRODEO_LD, x87 long double (64-bit mantissa): the same
+ * recursion evaluated ~2000x more finely, used by the tests to measure the float64 noise floor of dalton per theta.
+ * The exported interface is double arrays either way. */
+#ifdef RODEO_LD
+typedef long double real;
+#define R_FABS fabsl
+#define R_SQRT sqrtl
+#define R_LOG logl
+#define R_EXP expl
+#define R_SIN sinl
+#else
+typedef double real;
+#define R_FABS fabs
+#define R_SQRT sqrt
+#define R_LOG log
+#define R_EXP exp
+#define R_SIN sin
+#endif
+
 #define NBMAX 6
 #define PMAX 4
 
@@ -30,37 +49,37 @@ enum { M_FITZ = 0, M_LORENZ = 1, M_SECOND = 2, M_HES1 = 3, M_SEIRAH = 4 };
 enum { I_KRAMER = 0, I_CHKREBTII = 1, I_SCHOBER = 2, I_RODEO = 3 };
 
 /* f (nb) and the block-diagonal Jacobian J (nb x p, own block only) at X (nb x p) */
-static void ode_eval(int model, int nb, int p, const double* X, double t, const double* th, double* f, double* J) {
-  memset(J, 0, sizeof(double) * nb * p);
+static void ode_eval(int model, int nb, int p, const real* X, real t, const real* th, real* f, real* J) {
+  memset(J, 0, sizeof(real) * nb * p);
   switch (model) {
     case M_FITZ: {
-      double a = th[0], b = th[1], c = th[2], V = X[0], R = X[p];
+      real a = th[0], b = th[1], c = th[2], V = X[0], R = X[p];
       f[0] = c * (V - V * V * V / 3 + R);
       f[1] = -1 / c * (V - a + b * R);
       J[0] = c * (1 - V * V);
       J[p] = -1 / c * b;
     } break;
     case M_LORENZ: {
-      double rho = th[0], sg = th[1], be = th[2], x = X[0], y = X[p], z = X[2 * p];
+      real rho = th[0], sg = th[1], be = th[2], x = X[0], y = X[p], z = X[2 * p];
       f[0] = -sg * x + sg * y; f[1] = rho * x - y - x * z; f[2] = -be * z + x * y;
       J[0] = -sg; J[p] = -1.0; J[2 * p] = -be;
     } break;
     case M_SECOND: {
-      f[0] = sin(th[0] * t) - th[1] * X[0];
+      f[0] = R_SIN(th[0] * t) - th[1] * X[0];
       J[0] = -th[1];
     } break;
     case M_HES1: {
-      double P = exp(X[0]), Mm = exp(X[p]), H = exp(X[2 * p]);
-      double a = th[0], b = th[1], c = th[2], d = th[3], e = th[4], ff = th[5], g = th[6];
+      real P = R_EXP(X[0]), Mm = R_EXP(X[p]), H = R_EXP(X[2 * p]);
+      real a = th[0], b = th[1], c = th[2], d = th[3], e = th[4], ff = th[5], g = th[6];
       f[0] = -a * H + b * Mm / P - c;
       f[1] = -d + e / (1 + P * P) / Mm;
       f[2] = -a * P + ff / (1 + P * P) / H - g;
       J[0] = -b * Mm / P; J[p] = -e / (1 + P * P) / Mm; J[2 * p] = -ff / (1 + P * P) / H;
     } break;
     case M_SEIRAH: {
-      double S = X[0], E = X[p], I = X[2 * p], R = X[3 * p], A = X[4 * p], H = X[5 * p];
-      double b = th[0], r = th[1], al = th[2], De = th[3], DI = th[4], Dq = th[5], Dh = 30.0;
-      double N = S + E + I + R + A + H, g = b * (I + al * A);
+      real S = X[0], E = X[p], I = X[2 * p], R = X[3 * p], A = X[4 * p], H = X[5 * p];
+      real b = th[0], r = th[1], al = th[2], De = th[3], DI = th[4], Dq = th[5], Dh = 30.0;
+      real N = S + E + I + R + A + H, g = b * (I + al * A);
       f[0] = -g * S / N; f[1] = g * S / N - E / De; f[2] = r * E / De - I / Dq - I / DI;
       f[3] = (I + A) / DI + H / Dh; f[4] = (1 - r) * E / De - A / DI; f[5] = I / Dq - H / Dh;
       J[0] = -g / N + g * S / (N * N); J[p] = -g * S / (N * N) - 1 / De; J[2 * p] = -1 / Dq - 1 / DI;
@@ -70,36 +89,36 @@ static void ode_eval(int model, int nb, int p, const double* X, double t, const 
 }
 
 /* ---- dense helpers on p x p row-major matrices -------------------------------------------------------------- */
-static void predict(int p, const double* Q, const double* R, const double* mu, const double* S, double* mp, double* Sp) {
-  double A[PMAX * PMAX];
+static void predict(int p, const real* Q, const real* R, const real* mu, const real* S, real* mp, real* Sp) {
+  real A[PMAX * PMAX];
   for (int i = 0; i < p; ++i) {
-    double m = 0;
+    real m = 0;
     for (int j = 0; j < p; ++j) m += Q[i * p + j] * mu[j];
     mp[i] = m;
     for (int k = 0; k < p; ++k) {
-      double a = 0;
+      real a = 0;
       for (int j = 0; j < p; ++j) a += Q[i * p + j] * S[j * p + k];
       A[i * p + k] = a;
     }
   }
   for (int i = 0; i < p; ++i)
     for (int j = 0; j < p; ++j) {
-      double a = 0;
+      real a = 0;
       for (int k = 0; k < p; ++k) a += A[i * p + k] * Q[j * p + k];
       Sp[i * p + j] = a + R[i * p + j];
     }
 }
 
 /* X = S^{-1} B, S mm x mm (mm <= 2), B mm x p; partial-pivot Gaussian elimination as LAPACK getrf/getrs */
-static void lu_solve(int mm, int p, const double* S, double* Bm) {
+static void lu_solve(int mm, int p, const real* S, real* Bm) {
   if (mm == 1) { for (int i = 0; i < p; ++i) Bm[i] /= S[0]; return; }
-  double A[4] = {S[0], S[1], S[2], S[3]};
-  if (fabs(A[2]) > fabs(A[0])) {
-    double t;
+  real A[4] = {S[0], S[1], S[2], S[3]};
+  if (R_FABS(A[2]) > R_FABS(A[0])) {
+    real t;
     t = A[0]; A[0] = A[2]; A[2] = t; t = A[1]; A[1] = A[3]; A[3] = t;
     for (int i = 0; i < p; ++i) { t = Bm[i]; Bm[i] = Bm[p + i]; Bm[p + i] = t; }
   }
-  double l = A[2] / A[0];
+  real l = A[2] / A[0];
   A[3] -= l * A[1];
   for (int i = 0; i < p; ++i) Bm[p + i] -= l * Bm[i];
   for (int i = 0; i < p; ++i) {
@@ -108,81 +127,81 @@ static void lu_solve(int mm, int p, const double* S, double* Bm) {
   }
 }
 
-static const double LOG2PI = 1.8378770664093454836;
+static const real LOG2PI = (real)1.8378770664093454835606594728112353L;
 
-static double logpdf_term(double w, double z) {
-  if (fabs(w) <= 1e-8) return 0.0;               /* ~isclose(w, 0, rtol=1e-300): default atol 1e-8 */
-  return -0.5 * (z * z / w + log(w)) - 0.5 * LOG2PI;
+static real logpdf_term(real w, real z) {
+  if (R_FABS(w) <= (real)1e-8) return 0.0;               /* ~isclose(w, 0, rtol=1e-300): default atol 1e-8 */
+  return -0.5 * (z * z / w + R_LOG(w)) - 0.5 * LOG2PI;
 }
 
 /* log N(res + mean; mean, S) for mm <= 2 via the symmetric eigen-decomposition */
-static double logpdf(int mm, const double* S, const double* res) {
+static real logpdf(int mm, const real* S, const real* res) {
   if (mm == 1) return logpdf_term(S[0], res[0]);
-  double a = S[0], b = S[1], c = S[3];
-  double tr = a + c, df = a - c, rt = sqrt(df * df + 4 * b * b);
-  double w1 = 0.5 * (tr + (tr >= 0 ? rt : -rt));  /* larger |.| root first, then the product for the other */
-  double w2 = (w1 != 0.0) ? (a * c - b * b) / w1 : 0.0;
-  double v0, v1;
-  if (fabs(w1 - a) + fabs(b) > fabs(w1 - c) + fabs(b)) { v0 = b; v1 = w1 - a; if (fabs(v0) + fabs(v1) == 0) { v0 = 1; v1 = 0; } }
-  else { v0 = w1 - c; v1 = b; if (fabs(v0) + fabs(v1) == 0) { v0 = 1; v1 = 0; } }
-  double nrm = sqrt(v0 * v0 + v1 * v1);
+  real a = S[0], b = S[1], c = S[3];
+  real tr = a + c, df = a - c, rt = R_SQRT(df * df + 4 * b * b);
+  real w1 = 0.5 * (tr + (tr >= 0 ? rt : -rt));  /* larger |.| root first, then the product for the other */
+  real w2 = (w1 != 0.0) ? (a * c - b * b) / w1 : 0.0;
+  real v0, v1;
+  if (R_FABS(w1 - a) + R_FABS(b) > R_FABS(w1 - c) + R_FABS(b)) { v0 = b; v1 = w1 - a; if (R_FABS(v0) + R_FABS(v1) == 0) { v0 = 1; v1 = 0; } }
+  else { v0 = w1 - c; v1 = b; if (R_FABS(v0) + R_FABS(v1) == 0) { v0 = 1; v1 = 0; } }
+  real nrm = R_SQRT(v0 * v0 + v1 * v1);
   v0 /= nrm; v1 /= nrm;
-  double z1 = v0 * res[0] + v1 * res[1], z2 = -v1 * res[0] + v0 * res[1];
+  real z1 = v0 * res[0] + v1 * res[1], z2 = -v1 * res[0] + v0 * res[1];
   return logpdf_term(w1, z1) + logpdf_term(w2, z2);
 }
 
 /* update with mm rows wm (mm x p), offsets d, noise V (mm x mm), observed x; returns the forecast log-pdf */
-static double update(int p, int mm, double* mu, double* S, const double* wm, const double* d, const double* V,
-                     const double* x, int want_lp) {
-  double wS[2 * PMAX], Sm[4], Kt[2 * PMAX], res[2];
+static real update(int p, int mm, real* mu, real* S, const real* wm, const real* d, const real* V,
+                     const real* x, int want_lp) {
+  real wS[2 * PMAX], Sm[4], Kt[2 * PMAX], res[2];
   for (int r = 0; r < mm; ++r) {
-    double mz = 0;
+    real mz = 0;
     for (int i = 0; i < p; ++i) mz += wm[r * p + i] * mu[i];
     res[r] = x[r] - (mz + d[r]);
     for (int j = 0; j < p; ++j) {
-      double a = 0;
+      real a = 0;
       for (int i = 0; i < p; ++i) a += wm[r * p + i] * S[i * p + j];
       wS[r * p + j] = a;                           /* var_meas_state_pred */
     }
   }
   for (int r = 0; r < mm; ++r)
     for (int s = 0; s < mm; ++s) {
-      double a = 0;
+      real a = 0;
       for (int j = 0; j < p; ++j) a += wS[r * p + j] * wm[s * p + j];
       Sm[r * mm + s] = a + V[r * mm + s];
     }
-  double lp = want_lp ? logpdf(mm, Sm, res) : 0.0;
+  real lp = want_lp ? logpdf(mm, Sm, res) : 0.0;
   for (int r = 0; r < mm; ++r)                      /* (S_p wm^T)^T = rows r: S_p wm[r] */
     for (int i = 0; i < p; ++i) {
-      double a = 0;
+      real a = 0;
       for (int j = 0; j < p; ++j) a += S[i * p + j] * wm[r * p + j];
       Kt[r * p + i] = a;
     }
   lu_solve(mm, p, Sm, Kt);
   for (int i = 0; i < p; ++i) {
-    double m = 0;
+    real m = 0;
     for (int r = 0; r < mm; ++r) m += Kt[r * p + i] * res[r];
     mu[i] += m;
   }
-  double Sn[PMAX * PMAX];
+  real Sn[PMAX * PMAX];
   for (int i = 0; i < p; ++i)
     for (int j = 0; j < p; ++j) {
-      double a = 0;
+      real a = 0;
       for (int r = 0; r < mm; ++r) a += Kt[r * p + i] * wS[r * p + j];
       Sn[i * p + j] = S[i * p + j] - a;
     }
-  memcpy(S, Sn, sizeof(double) * p * p);
+  memcpy(S, Sn, sizeof(real) * p * p);
   return lp;
 }
 
 /* interrogation for all blocks: wm (nb x p), d (nb), V (nb) */
-static void interrogate(int model, int interr, int nb, int p, const double* W, const double* mu, const double* S,
-                        double t, const double* th, double* wm, double* d, double* V) {
-  double f[NBMAX], J[NBMAX * PMAX];
+static void interrogate(int model, int interr, int nb, int p, const real* W, const real* mu, const real* S,
+                        real t, const real* th, real* wm, real* d, real* V) {
+  real f[NBMAX], J[NBMAX * PMAX];
   ode_eval(model, nb, p, mu, t, th, f, J);
   for (int b = 0; b < nb; ++b) {
     if (interr == I_KRAMER) {
-      double jm = 0;
+      real jm = 0;
       for (int j = 0; j < p; ++j) { wm[b * p + j] = W[b * p + j] + (-J[b * p + j]); jm += J[b * p + j] * mu[b * p + j]; }
       d[b] = -f[b] + jm; V[b] = 0.0;
     } else {
@@ -190,9 +209,9 @@ static void interrogate(int model, int interr, int nb, int p, const double* W, c
       d[b] = -f[b];
       V[b] = 0.0;
       if (interr == I_RODEO) {
-        double a = 0;
+        real a = 0;
         for (int i = 0; i < p; ++i) {
-          double u = 0;
+          real u = 0;
           for (int j = 0; j < p; ++j) u += W[b * p + j] * S[(b * p + j) * p + i];
           a += u * W[b * p + i];
         }
@@ -202,30 +221,30 @@ static void interrogate(int model, int interr, int nb, int p, const double* W, c
   }
 }
 
-static double step_time(double t_min, double t_max, int n, int N) { return t_min + (t_max - t_min) * (n + 1) / N; }
+static real step_time(real t_min, real t_max, int n, int N) { return t_min + (t_max - t_min) * (n + 1) / N; }
 
 /* one filter step for all blocks; obs_i >= 0 adds the observation rows (dalton zy_update); returns sum log-pdf */
-static double filter_step(int model, int interr, int nb, int p, const double* W, const double* Q, const double* R,
-                          double* mu, double* S, double t, const double* th, int obs_i, const double* obs_data,
-                          const double* obs_weight, const double* obs_var, int want_lp) {
-  double mp[NBMAX * PMAX], Sp[NBMAX * PMAX * PMAX], wm[NBMAX * PMAX], d[NBMAX], V[NBMAX];
+static real filter_step(int model, int interr, int nb, int p, const real* W, const real* Q, const real* R,
+                          real* mu, real* S, real t, const real* th, int obs_i, const real* obs_data,
+                          const real* obs_weight, const real* obs_var, int want_lp) {
+  real mp[NBMAX * PMAX], Sp[NBMAX * PMAX * PMAX], wm[NBMAX * PMAX], d[NBMAX], V[NBMAX];
   for (int b = 0; b < nb; ++b) predict(p, Q + b * p * p, R + b * p * p, mu + b * p, S + b * p * p, mp + b * p, Sp + b * p * p);
   interrogate(model, interr, nb, p, W, mp, Sp, t, th, wm, d, V);
-  double lp = 0.0;
+  real lp = 0.0;
   for (int b = 0; b < nb; ++b) {
     if (obs_i < 0) {
-      double x = 0.0;
+      real x = 0.0;
       lp += update(p, 1, mp + b * p, Sp + b * p * p, wm + b * p, d + b, V + b, &x, want_lp);
     } else {
-      double wa[2 * PMAX], da[2] = {d[b], 0.0}, Va[4] = {V[b], 0.0, 0.0, obs_var[obs_i * nb + b]};
-      double xa[2] = {0.0, obs_data[obs_i * nb + b]};
-      memcpy(wa, wm + b * p, sizeof(double) * p);
-      memcpy(wa + p, obs_weight + (obs_i * nb + b) * p, sizeof(double) * p);
+      real wa[2 * PMAX], da[2] = {d[b], 0.0}, Va[4] = {V[b], 0.0, 0.0, obs_var[obs_i * nb + b]};
+      real xa[2] = {0.0, obs_data[obs_i * nb + b]};
+      memcpy(wa, wm + b * p, sizeof(real) * p);
+      memcpy(wa + p, obs_weight + (obs_i * nb + b) * p, sizeof(real) * p);
       lp += update(p, 2, mp + b * p, Sp + b * p * p, wa, da, Va, xa, want_lp);
     }
   }
-  memcpy(mu, mp, sizeof(double) * nb * p);
-  memcpy(S, Sp, sizeof(double) * nb * p * p);
+  memcpy(mu, mp, sizeof(real) * nb * p);
+  memcpy(S, Sp, sizeof(real) * nb * p * p);
   return lp;
 }
 
@@ -238,35 +257,45 @@ int rodeo_oracle_max_threads(void) {
 }
 
 /* dalton log-likelihood per theta */
+static void to_real(real* dst, const double* src, long n) { for (long k = 0; k < n; ++k) dst[k] = (real)src[k]; }
+
 int rodeo_oracle_dalton(int model, int interr, long B, int N, int nb, int p, int n_theta, double t_min, double t_max,
-                        const double* W, const double* Q, const double* R, const double* X0, const double* theta,
-                        int n_obs, const int* obs_ind, const double* obs_data, const double* obs_weight,
-                        const double* obs_var, double* out, int n_threads) {
-  if (nb > NBMAX || p > PMAX || interr == I_CHKREBTII) return 1;
+                        const double* W_, const double* Q_, const double* R_, const double* X0, const double* theta,
+                        int n_obs, const int* obs_ind, const double* obs_data_, const double* obs_weight_,
+                        const double* obs_var_, double* out, int n_threads) {
+  if (nb > NBMAX || p > PMAX || n_theta > 16 || interr == I_CHKREBTII) return 1;
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
+  real W[NBMAX * PMAX], Q[NBMAX * PMAX * PMAX], R[NBMAX * PMAX * PMAX];
+  to_real(W, W_, (long)nb * p); to_real(Q, Q_, (long)nb * p * p); to_real(R, R_, (long)nb * p * p);
+  real* obs_data = (real*)malloc(sizeof(real) * (size_t)n_obs * nb);
+  real* obs_weight = (real*)malloc(sizeof(real) * (size_t)n_obs * nb * p);
+  real* obs_var = (real*)malloc(sizeof(real) * (size_t)n_obs * nb);
+  to_real(obs_data, obs_data_, (long)n_obs * nb); to_real(obs_weight, obs_weight_, (long)n_obs * nb * p);
+  to_real(obs_var, obs_var_, (long)n_obs * nb);
 #pragma omp parallel for schedule(static)
   for (long k = 0; k < B; ++k) {
-    const double* th = theta + k * n_theta;
-    double mzy[NBMAX * PMAX], Szy[NBMAX * PMAX * PMAX], mz[NBMAX * PMAX], Sz[NBMAX * PMAX * PMAX];
-    memcpy(mzy, X0 + k * nb * p, sizeof(double) * nb * p);
-    memcpy(mz, mzy, sizeof(double) * nb * p);
-    memset(Szy, 0, sizeof(double) * nb * p * p);
-    memset(Sz, 0, sizeof(double) * nb * p * p);
-    double ll_zy = 0.0, ll_z = 0.0;
+    real th[16];
+    to_real(th, theta + k * n_theta, n_theta);
+    real mzy[NBMAX * PMAX], Szy[NBMAX * PMAX * PMAX], mz[NBMAX * PMAX], Sz[NBMAX * PMAX * PMAX];
+    to_real(mzy, X0 + k * nb * p, (long)nb * p);
+    memcpy(mz, mzy, sizeof(real) * nb * p);
+    memset(Szy, 0, sizeof(real) * nb * p * p);
+    memset(Sz, 0, sizeof(real) * nb * p * p);
+    real ll_zy = 0.0, ll_z = 0.0;
     int i = 0;
     if (obs_ind[0] == 0) {
       for (int b = 0; b < nb; ++b) {
-        double m = 0;
+        real m = 0;
         for (int j = 0; j < p; ++j) m += obs_weight[b * p + j] * mzy[b * p + j];
-        double res = obs_data[b] - m;
+        real res = obs_data[b] - m;
         ll_zy += logpdf(1, obs_var + b, &res);
       }
       i = 1;
     }
     for (int n = 0; n < N; ++n) {
-      double t = step_time(t_min, t_max, n, N);
+      real t = step_time(t_min, t_max, n, N);
       int ic = i < n_obs ? i : n_obs - 1;
       if (n + 1 == obs_ind[ic]) {
         ll_zy += filter_step(model, interr, nb, p, W, Q, R, mzy, Szy, t, th, ic, obs_data, obs_weight, obs_var, 1);
@@ -276,11 +305,13 @@ int rodeo_oracle_dalton(int model, int interr, long B, int N, int nb, int p, int
       }
       ll_z += filter_step(model, interr, nb, p, W, Q, R, mz, Sz, t, th, -1, 0, 0, 0, 1);
     }
-    out[k] = ll_zy - ll_z;
+    out[k] = (double)(ll_zy - ll_z);
   }
+  free(obs_data); free(obs_weight); free(obs_var);
   return 0;
 }
 
+#ifndef RODEO_LD   /* the extended-precision build only serves the dalton noise-floor measurement */
 /* p x p LU solve with partial pivoting: X = A^{-1} Bm (Bm p x p row-major, columns are right-hand sides) */
 static void lu_solve_pp(int p, const double* Ain, double* Bm) {
   double A[PMAX * PMAX];
@@ -377,3 +408,4 @@ int rodeo_oracle_solve_mv(int model, int interr, long B, int N, int nb, int p, i
   }
   return 0;
 }
+#endif /* !RODEO_LD */

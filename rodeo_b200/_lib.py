@@ -52,6 +52,7 @@ SIGNATURES = {
     "rodeo_b200_workspace_bytes": (_sz, [_i, _P, _i]),
     "rodeo_b200_last_error": (ctypes.c_char_p, []),
     "rodeo_b200_abi_version": (_i, []),
+    "rodeo_b200_problem_sizeof": (_sz, []),
     "rodeo_b200_launch_count": (ctypes.c_int64, []),
     "rodeo_b200_solve_mv_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_solve_sim_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),

@@ -123,6 +123,7 @@ extern "C" {
 
 const char* rodeo_b200_last_error(void) { return g_err; }
 int rodeo_b200_abi_version(void) { return RODEO_B200_ABI_VERSION; }
+size_t rodeo_b200_problem_sizeof(void) { return sizeof(RodeoProblem); }
 int64_t rodeo_b200_launch_count(void) { return (int64_t)g_launches.load(); }
 
 size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes) {
@@ -150,30 +151,44 @@ size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes)
 
 // Measured FP64 FMA throughput of the current device in TFLOP/s (2 flop per DFMA), best of `reps` timed launches.
 // bench.py uses it as the roofline denominator for the FP64-bound kernels (MEASURED_PEAKS.json has no FP64 figure).
+namespace {
+struct ProbeResources {           // freed on every exit path
+  double* d = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t s = nullptr;
+  ~ProbeResources() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (s) cudaStreamDestroy(s);
+    if (d) cudaFree(d);
+  }
+};
+}  // namespace
+
 int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out) {
   if (!tflops_out) { set_error("tflops_out is NULL"); return RODEO_ERR_INVALID; }
   int dev = 0, sms = 0;
   RODEO_CUDA_OK(cudaGetDevice(&dev));
   RODEO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  double* d = nullptr;
-  RODEO_CUDA_OK(cudaMalloc((void**)&d, 8));
-  cudaEvent_t e0, e1;
-  RODEO_CUDA_OK(cudaEventCreate(&e0));
-  RODEO_CUDA_OK(cudaEventCreate(&e1));
+  ProbeResources r;
+  RODEO_CUDA_OK(cudaMalloc((void**)&r.d, 8));
+  RODEO_CUDA_OK(cudaEventCreate(&r.e0));
+  RODEO_CUDA_OK(cudaEventCreate(&r.e1));
+  RODEO_CUDA_OK(cudaStreamCreateWithFlags(&r.s, cudaStreamNonBlocking));   // private stream: no implicit joins
   const int iters = 4096, grid = sms * 8, block = 256;
   double best = 0.0;
-  for (int r = 0; r < reps + 2; ++r) {
-    RODEO_CUDA_OK(cudaEventRecord(e0, 0));
-    fp64_probe_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-9);
-    RODEO_CUDA_OK(cudaEventRecord(e1, 0));
-    RODEO_CUDA_OK(cudaEventSynchronize(e1));
+  for (int k = 0; k < reps + 2; ++k) {
+    RODEO_CUDA_OK(cudaEventRecord(r.e0, r.s));
+    fp64_probe_kernel<<<grid, block, 0, r.s>>>(r.d, iters, 0.999999, 1e-9);
+    RODEO_CUDA_OK(cudaGetLastError());
+    RODEO_CUDA_OK(cudaEventRecord(r.e1, r.s));
+    RODEO_CUDA_OK(cudaEventSynchronize(r.e1));
     float ms = 0.f;
-    RODEO_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    RODEO_CUDA_OK(cudaEventElapsedTime(&ms, r.e0, r.e1));
     const double flops = 2.0 * 64.0 * (double)iters * (double)grid * (double)block;
     const double tf = flops / (ms * 1e-3) / 1e12;
-    if (r >= 2 && tf > best) best = tf;
+    if (k >= 2 && tf > best) best = tf;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
   *tflops_out = best;
   return RODEO_OK;
 }

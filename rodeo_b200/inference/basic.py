@@ -20,7 +20,8 @@ def basic(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate
                        prior_weight, prior_var, kalman_type, params)
     pb.set_obs(obs_data, obs_times)
     Xt, _ = solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate,
-                     prior_pars=(pb.Q, pb.R), kalman_type=kalman_type, **params)
+                     prior_pars=prior_pars, prior_weight=prior_weight, prior_var=prior_var,
+                     kalman_type=kalman_type, **params)      # the caller's own prior (may be per theta)
     Xb = Xt if pb.batched else Xt[None]
     ode_data = pb.empty(pb.B, pb.c.n_obs, pb.nb, pb.p)
     rc = pb.fn("basic_gather")(ctypes.byref(pb.c), _host.ptr(Xb), _host.ptr(pb.obs_ind),

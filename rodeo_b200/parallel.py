@@ -23,28 +23,36 @@ def shard(x, rank, world):
     return x[lo:hi]
 
 
-def all_gather_loglik(local, B_total=None, group=None):
+def all_gather_loglik(local, B_total=None, group=None, out=None):
     """Concatenate every rank's per-theta log-likelihoods in rank order (NCCL on GPUs, gloo on CPU).
 
-    Shards may differ by one element (uneven split): they are padded to a common length for the collective.
+    With ``B_total`` (the global batch size) the shard sizes follow from :func:`shard_bounds`: no size exchange and
+    no host synchronisation -- one collective, enqueued on the current stream.  An even split is a single
+    ``all_gather_into_tensor`` (into ``out`` when given, so a steady-state caller allocates nothing); an uneven one
+    (shards differ by one element) pads to the common length.  Without ``B_total`` every rank must hold the same
+    number of elements.
     """
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
-    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    local = local.contiguous()
+    if B_total is None:
+        B_total = world * local.numel()
+    sizes = [hi - lo for lo, hi in (shard_bounds(B_total, r, world) for r in range(world))]
+    if local.numel() != sizes[dist.get_rank(group)]:
+        raise ValueError(f"rank holds {local.numel()} log-likelihoods, shard_bounds({B_total}) gives "
+                         f"{sizes[dist.get_rank(group)]}")
     m = max(sizes)
-    if all(s == m for s in sizes):
-        out = torch.empty(world * m, dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    if m == min(sizes):
+        if out is None:
+            out = torch.empty(world * m, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
         return out
     pad = torch.zeros(m, dtype=local.dtype, device=local.device)
     pad[:local.numel()] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+    buf = torch.empty(world * m, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    return torch.cat([buf[r * m:r * m + s] for r, s in enumerate(sizes)])
 
 
 def sharded_loglik(loglik_fn, theta, ode_init, group=None):

@@ -39,6 +39,22 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.RodeoProblem) == 16 + 40 + 8 + 16 + 8 + 8
 
 
+def test_struct_size_matches_the_library_and_the_documented_binding():
+    """sizeof(RodeoProblem) as compiled == the ctypes mirror in rodeo_b200/_lib.py == the struct INTEGRATION.md tells
+    a binding author to declare (a short struct would hand the library a garbage prior_var_scale pointer)."""
+    from rodeo_b200 import _lib
+    lib = _lib.load()
+    n = lib.rodeo_b200_problem_sizeof()
+    assert n == ctypes.sizeof(_lib.RodeoProblem)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class RodeoProblem\(ctypes\.Structure\):.*?\n\n", doc, flags=re.S)
+    assert m, "INTEGRATION.md no longer shows the ctypes struct"
+    ns = {"ctypes": ctypes}
+    exec(m.group(0), ns)
+    assert ctypes.sizeof(ns["RodeoProblem"]) == n
+    assert [f[0] for f in ns["RodeoProblem"]._fields_] == [f[0] for f in _lib.RodeoProblem._fields_]
+
+
 def test_workspace_sizing_needs_no_gpu():
     from rodeo_b200 import _lib
     lib = _lib.load()

@@ -84,8 +84,7 @@ def test_oracle_dalton_fenrir(tag):
     a, o = oargs(tag)
     assert ll_err(orc.fenrir(*a, *o), G[f"{tag}_fenrir"]) < 1e-11
     if f"{tag}_dalton" in G.files:
-        # the README-length dalton sum sits on its float64 noise floor
-        assert ll_err(orc.dalton(*a, *o), G[f"{tag}_dalton"]) < (1e-9 if tag == "readme" else 1e-11)
+        assert ll_err(orc.dalton(*a, *o), G[f"{tag}_dalton"]) < 1e-11
 
 
 def test_oracle_basic_and_data_adaptive_solvers():
@@ -201,9 +200,22 @@ def test_cuda_solve_mv_chkrebtii_same_normals(rb):
 def test_cuda_dalton_fenrir(rb, tag):
     a, kw, ob = gargs(rb, tag)
     assert ll_err(_np(rb.inference.fenrir(*a, **kw, **ob)), G[f"{tag}_fenrir"]) < TOL
-    # dalton's N = 800 sum sits on its float64 noise floor: the float64 oracle itself is
-    # ~1e-10 from the exact value there
-    assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G[f"{tag}_dalton"]) < (2e-9 if tag == "readme" else TOL)
+    got = _np(rb.inference.dalton(*a, **kw, **ob))
+    if tag != "readme":
+        assert ll_err(got, G[f"{tag}_dalton"]) < TOL
+        return
+    # README walkthrough (N = 800 = BASELINE configs[0]): the sum sits on its float64 noise floor, so the kernel and the
+    # reference's own value are both judged against the long-double evaluation (tests/noise_floor.py)
+    import noise_floor as NF
+    from oracle import c_port
+    model, t_max, N = grid(tag)
+    pr, _ = prob(tag)
+    ind = orc.obs_index(0.0, t_max, N, ob["obs_times"])
+    exact = c_port.dalton_ld(model, "kramer", pr["W"], pr["X0"], 0.0, t_max, N, pr["Q"], pr["R"], pr["theta"],
+                             ob["obs_data"], ind, ob["obs_weight"], ob["obs_var"])
+    st = NF.gate(got, G[f"{tag}_dalton"], exact)
+    NF.report("dalton README golden (reference source over the jax stand-in)", st)
+    assert st["ok"], st
 
 
 @pytest.mark.gpu
