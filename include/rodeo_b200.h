@@ -247,6 +247,11 @@ int rodeo_b200_ktv_smooth_f64(int64_t B, int n_state, int mode, const double* x_
                               double* out_mean, double* out_var, double* out_wgt, void* stream);
 int rodeo_b200_mvn_logpdf_f64(int64_t B, int n, const double* x, const double* mean, const double* cov, double* out,
                               void* stream);
+/* The factor the sampling paths draw with: lower-triangular A (B, n, n) with A A^T = cov, a Cholesky factorisation that
+ * zeroes the column of a non-positive pivot (positive SEMI-definite input, e.g. the singular smoothing covariances).
+ * Stands where the reference calls jax.random.multivariate_normal(method='svd' / 'cholesky') (src/rodeo/solve.py:179,
+ * 182-186; src/rodeo/interrogate.py:30-34): any factor with A A^T = cov gives the same distribution. */
+int rodeo_b200_psd_factor_f64(int64_t B, int n, const double* cov, double* factor_out, void* stream);
 
 /*
  * MAGI log-density p(U_{0:N}, Z = 0 | theta) of a given trajectory under the block-diagonal Markov prior.

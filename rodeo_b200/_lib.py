@@ -78,6 +78,7 @@ SIGNATURES = {
     "rodeo_b200_ktv_update_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
     "rodeo_b200_ktv_smooth_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
     "rodeo_b200_mvn_logpdf_f64": (_i, [ctypes.c_int64, _i] + [_vp] * 4 + [_vp]),
+    "rodeo_b200_psd_factor_f64": (_i, [ctypes.c_int64, _i, _vp, _vp, _vp]),
     "rodeo_b200_magi_logdens_f64": (_i, [ctypes.c_int64, _i, _i, _i, _i] + [_vp] * 4 + [_vp]),
     "rodeo_b200_dalton_f64_host": (_i, [_P] + [_vp] * 10),
     "rodeo_b200_solve_mv_f64_host": (_i, [_P] + [_vp] * 7),

@@ -1,5 +1,12 @@
 // rodeo_b200_dalton_f64: batched rodeo.inference.dalton (reference src/rodeo/inference/dalton.py:39-235).
+#include <cstdlib>
+
 #include "rodeo_host.h"
+
+// (theta, filter, block) lanes below this many (theta, filter) warps per SM sub-partition
+#ifndef RODEO_DALTON_BL_BELOW
+#define RODEO_DALTON_BL_BELOW 2.0
+#endif
 
 #ifndef RODEO_REAL
 #define RODEO_REAL double
@@ -25,11 +32,27 @@ struct DaltonRun {
     }
     if (p.B == 0) return RODEO_OK;
     CommonArgs<real_t> ag = a;
-    if (sizeof(real_t) == 8) {
-      // joint CTAs, then marginal CTAs, each adding +/- its log-density to the zeroed output (rodeo_kernels.cuh)
-      ag.dalton_geometry = 2;
+    if constexpr (sizeof(real_t) == 8) {
       RODEO_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)p.B * sizeof(real_t), s));
-      dalton_kernel<real_t, Model, INTERR, QK, 1><<<2 * grid_for(p.B, 32), 32, 0, s>>>(C, ag, o, out);
+      // Small batches cannot fill the FP64 pipes with one thread per (theta, filter): below about two such warps per SM
+      // sub-partition the run time is one thread's dependency chain, and spreading the blocks of a filter over lanes
+      // (dalton_bl_kernel) shortens that chain by n_block.  Both kernels return bitwise the same numbers.  Measured on
+      // B200, FitzHugh-Nagumo N = 800: see DESIGN.md section 4.1.
+      bool block_lanes = false;
+      if constexpr (Model::NB >= 2) {
+        const double warps_per_subpartition = 2.0 * grid_for(p.B, 32) / (4.0 * sm_count());
+        block_lanes = warps_per_subpartition < RODEO_DALTON_BL_BELOW;
+        if (const char* e = getenv("RODEO_DALTON_BLOCK_LANES")) block_lanes = e[0] == '1';      // tuning / tests
+        if (block_lanes) {
+          typedef BlockLane<real_t, Model, INTERR, QK> L;
+          dalton_bl_kernel<real_t, Model, INTERR, QK, 1><<<2 * grid_for(p.B, L::TW), 32, 0, s>>>(C, ag, o, out);
+        }
+      }
+      if (!block_lanes) {
+        // joint CTAs, then marginal CTAs, each adding +/- its log-density to the zeroed output (rodeo_kernels.cuh)
+        ag.dalton_geometry = 2;
+        dalton_kernel<real_t, Model, INTERR, QK, 1><<<2 * grid_for(p.B, 32), 32, 0, s>>>(C, ag, o, out);
+      }
     } else {
       ag.dalton_geometry = 1;      // joint warp + marginal warp per CTA: the difference is formed in double
       dalton_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 64, 0, s>>>(C, ag, o, out);

@@ -135,6 +135,20 @@ __global__ void ktv_logpdf(i64 B, const double* x, const double* mean, const dou
   out[k] = acc.value();
 }
 
+// the guarded Cholesky-type factor the sampling kernels draw with (rodeo_core.cuh psd_factor): A lower, A A^T = C
+template <int P>
+__global__ void ktv_psd_factor(i64 B, const double* cov, double* A_out) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  double c[P * (P + 1) / 2], A[P][P];
+  load_sym<P>(cov + k * P * P, c);
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int j = 0; j < P; ++j) A[i][j] = 0.0;
+  psd_factor<double, P>(c, A);
+  RD_UNROLL for (int i = 0; i < P; ++i)
+    RD_UNROLL for (int j = 0; j < P; ++j) A_out[(k * P + i) * P + j] = j <= i ? A[i][j] : 0.0;
+}
+
 template <int P, typename F>
 int for_m(int m, F&& f) {
   switch (m) {
@@ -209,6 +223,14 @@ int rodeo_b200_ktv_smooth_f64(int64_t B, int n_state, int mode, const double* x_
     ktv_smooth<decltype(Pc)::value><<<grid_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         B, mode, x_next, var_next, mean_state_filt, var_state_filt, mean_state_pred, var_state_pred, wgt_state, out_mean,
         out_var, out_wgt);
+    return launched();
+  });
+}
+
+int rodeo_b200_psd_factor_f64(int64_t B, int n, const double* cov, double* factor_out, void* stream) {
+  if (B <= 0) return RODEO_OK;
+  return for_p(n, [&](auto Pc) {
+    ktv_psd_factor<decltype(Pc)::value><<<grid_for(B, 128), 128, 0, (cudaStream_t)stream>>>(B, cov, factor_out);
     return launched();
   });
 }

@@ -221,6 +221,69 @@ struct LogPdfAcc {
   }
 };
 
+// The same accumulator split into per-block partial sums (quadratic form, mantissa product) and one set of integer
+// counters (exponent sum, kept-term count, sign bits).  dalton sums the log-densities of all blocks of a theta: keeping
+// one partial sum PER BLOCK and combining them in block order at the very end (combine_logpdf) makes the result
+// independent of how the blocks are laid out over threads -- a thread that owns every block of a theta and the lanes of
+// a (theta, block) warp add exactly the same numbers in exactly the same order, so both launch geometries return
+// bitwise the same log-likelihood.  The integer counters are exact, hence order-free, and can be shared.
+struct LogPdfCtl {
+  int esum, cnt, sgn;
+  RD_DEV void init() { esum = 0; cnt = 0; sgn = 0; }
+};
+template <typename T>
+struct LogPdfPart {
+  typedef typename MeanOf<T>::type MT;
+  MT quad; T prod;
+  RD_DEV void init() { quad = MT(0); prod = T(1); }
+  // fold the exponent of the running product into ctl.esum (once per time step)
+  RD_DEV void renorm(LogPdfCtl& c) {
+    LogAcc<T> l; l.prod = prod; l.esum = c.esum; l.sgn = 0;
+    l.renorm();
+    prod = l.prod; c.esum = l.esum;
+  }
+};
+// what update() / logpdf_terms() see: one block's partial sums plus the shared counters
+template <typename T>
+struct LogPdfPartRef {
+  typedef typename MeanOf<T>::type MT;
+  LogPdfPart<T>& p; LogPdfCtl& c;
+  RD_DEV void term(T w, MT z, T rw) {
+    const bool keep = !(fabs(w) <= T(1e-8));   // nan counts as kept, as ~isclose(nan, 0) does
+    if (keep) {
+      p.quad = rd_fma(z * z, (MT)rw, p.quad);
+      p.prod *= w;
+      c.sgn |= sizeof(T) == 8 ? __double2hiint((double)w) : __float_as_int((float)w);
+      ++c.cnt;
+    }
+  }
+};
+// log-density of all blocks: -1/2 (sum_b quad_b + log prod_b |prod_b| + ln2 esum) - 1/2 cnt log(2 pi), blocks in order
+template <typename T, int NB>
+RD_DEV typename MeanOf<T>::type combine_logpdf(const LogPdfPart<T> (&part)[NB], const LogPdfCtl& ctl) {
+  typedef typename MeanOf<T>::type MT;
+  MT quad = part[0].quad;
+  LogAcc<T> l; l.prod = part[0].prod; l.esum = ctl.esum; l.sgn = ctl.sgn;
+  RD_UNROLL for (int b = 1; b < NB; ++b) { quad += part[b].quad; l.prod *= part[b].prod; }
+  l.renorm();
+  return MT(-0.5) * (quad + (MT)l.value()) - MT(0.5) * MT(1.8378770664093454836) * (MT)ctl.cnt;
+}
+
+// all blocks of one theta held by one thread
+template <typename T, int NB>
+struct LogPdfParts {
+  typedef typename MeanOf<T>::type MT;
+  LogPdfPart<T> part[NB]; LogPdfCtl ctl;
+  RD_DEV void init() { ctl.init(); RD_UNROLL for (int b = 0; b < NB; ++b) part[b].init(); }
+  RD_DEV void renorm() { RD_UNROLL for (int b = 0; b < NB; ++b) part[b].renorm(ctl); }
+  RD_DEV MT value() const { return combine_logpdf<T, NB>(part, ctl); }
+};
+// accumulator of block b: the single accumulator itself, or a view of block b's partial sums
+template <typename T> RD_DEV LogPdfAcc<T>& acc_at(LogPdfAcc<T>& a, int) { return a; }
+template <typename T, int NB>
+RD_DEV LogPdfPartRef<T> acc_at(LogPdfParts<T, NB>& a, int b) { return LogPdfPartRef<T>{a.part[b], a.ctl}; }
+template <typename T> RD_DEV LogPdfPartRef<T>& acc_at(LogPdfPartRef<T>& a, int) { return a; }
+
 // ---- tiny dense solves -------------------------------------------------------------------------------------
 // Solve S X = Bm for X (MM x P right-hand sides stored as rows r of Bm[r][:]) by Gaussian elimination with
 // partial pivoting, the algorithm behind jnp.linalg.solve (LAPACK getrf/getrs) in rodeo.utils.solve_var.
@@ -324,8 +387,8 @@ RD_DEV void eig_jacobi(T (&A)[MM][MM], T (&V)[MM][MM]) {
 }
 
 // log N(x; mu, S) contribution(s) into `acc`, S symmetric MM x MM packed, res = x - mu.
-template <typename T, int MM>
-RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], LogPdfAcc<T>& acc) {
+template <typename T, int MM, class ACC>
+RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], ACC& acc) {
   if (MM == 1) {
     acc.term(Ss[0], res[0], rcp(Ss[0]));
   } else if (MM == 2) {
@@ -353,9 +416,9 @@ RD_DEV void logpdf_terms(const T (&Ss)[MM * (MM + 1) / 2], const T (&res)[MM], L
 //   S = wm S_p wm^T + V ;  K = S_p wm^T S^{-1} ;  mu_f = mu_p + K res ;  S_f = S_p - K (wm S_p)
 // WITH_LOGPDF adds log N(xm; mu_z, S) to `acc` (reference fenrir._forecast_update, fenrir.py:40-81).
 // In-place: mu, S hold the predicted moments on entry and the filtered moments on exit.
-template <typename T, int P, int MM, bool WITH_LOGPDF, typename MT>
+template <typename T, int P, int MM, bool WITH_LOGPDF, typename MT, class ACC>
 RD_DEV void update(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], const MT (&res)[MM],
-                   const T (&V)[MM * (MM + 1) / 2], LogPdfAcc<T>& acc) {
+                   const T (&V)[MM * (MM + 1) / 2], ACC& acc) {
   T v[MM][P];    // v[r] = S_p wm[r]^T   (== (wm S_p)[r] by symmetry)
   T Kt[MM][P];
   T Sm[MM * (MM + 1) / 2];
@@ -375,7 +438,7 @@ RD_DEV void update(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], c
   if (WITH_LOGPDF) {
     T rt[MM];
     RD_UNROLL for (int r = 0; r < MM; ++r) rt[r] = (T)res[r];
-    logpdf_terms<T, MM>(Sm, rt, acc);
+    logpdf_terms<T, MM, ACC>(Sm, rt, acc);
   }
   solve_small<T, MM, P>(Sm, Kt);
   RD_UNROLL for (int i = 0; i < P; ++i) {
@@ -395,8 +458,9 @@ RD_DEV void update(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&wm)[MM][P], c
 // produces for W = e_WK and a right-hand side that reads the leading JC state columns; jl == 0 for the other
 // interrogations).  Same arithmetic as update<T,P,1,...> with the multiplications by the structural 0 / 1 entries
 // removed (those are exact, so the results are bitwise those of the general row).
-template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J, bool HAS_V = true, typename MT = T>
-RD_DEV void update_unit_row(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[JC], MT res, T V, LogPdfAcc<T>& acc) {
+template <typename T, int P, int JC, int WK, bool WITH_LOGPDF, bool HAS_J, bool HAS_V = true, typename MT = T,
+          class ACC = LogPdfAcc<T>>
+RD_DEV void update_unit_row(MT (&mu)[P], T (&S)[P * (P + 1) / 2], const T (&jl)[JC], MT res, T V, ACC& acc) {
   T v[P];
   RD_UNROLL for (int i = 0; i < P; ++i) {
     T a = S[sym<P>(i, WK)];

@@ -299,26 +299,28 @@ struct Fwd {
   }
 
   // plain ODE-measurement update of every block, x_meas == 0 (solve.py:51, 81-88)
-  template <bool WITH_LOGPDF>
+  // `acc` is one accumulator for all blocks (LogPdfAcc) or per-block partial sums (LogPdfParts): see acc_at
+  template <bool WITH_LOGPDF, class ACCS>
   RD_DEV void update_z(const Consts& C, const T (&jl)[NB][M][JC], const MT (&res)[NB][M], const T (&V)[NB][MS],
-                       LogPdfAcc<T>& acc) {
+                       ACCS& acc) {
     RD_UNROLL for (int b = 0; b < NB; ++b) {
+      auto&& ab = acc_at(acc, b);
       if constexpr (UNITW) {
         update_unit_row<T, P, JC, WK, WITH_LOGPDF, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(
-            mu[b], S[b], jl[b][0], res[b][0], V[b][0], acc);
+            mu[b], S[b], jl[b][0], res[b][0], V[b][0], ab);
       } else {
         T wm[M][P];
         rows(C, b, jl[b], wm);
-        update<T, P, M, WITH_LOGPDF>(mu[b], S[b], wm, res[b], V[b], acc);
+        update<T, P, M, WITH_LOGPDF>(mu[b], S[b], wm, res[b], V[b], ab);
       }
     }
   }
 
   // observation-augmented update (dalton zy_update, dalton.py:136-149): rows [W~; D_i], offsets [d; 0],
   // noise blockdiag(V, Omega_i), observed value [0; y_i]  ->  residual [res; y_i - D_i mu_p]
-  template <int NOBS, bool WITH_LOGPDF>
+  template <int NOBS, bool WITH_LOGPDF, class ACCS>
   RD_DEV void update_zy(const Consts& C, const T (&jl)[NB][M][JC], const MT (&res)[NB][M], const T (&V)[NB][MS],
-                        const ObsArgs<T>& o, int i, LogPdfAcc<T>& acc) {
+                        const ObsArgs<T>& o, int i, ACCS& acc) {
     constexpr int MA = M + NOBS, MAS = MA * (MA + 1) / 2;
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       T wa[MA][P], Va[MAS], wm[M][P];
@@ -340,7 +342,8 @@ struct Fwd {
         RD_UNROLL for (int s = r; s < NOBS; ++s)
           Va[sidx<MA>(M + r, M + s)] = __ldg(o.obs_var + ((i * NB + b) * NOBS + r) * NOBS + s);
       }
-      update<T, P, MA, WITH_LOGPDF>(mu[b], S[b], wa, ra, Va, acc);
+      auto&& ab = acc_at(acc, b);
+      update<T, P, MA, WITH_LOGPDF>(mu[b], S[b], wa, ra, Va, ab);
     }
   }
 
@@ -409,7 +412,7 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   F f;
   f.init(a.ode_init + idx * NB * P);
   f.load_scale(a, idx);
-  LogPdfAcc<T> acc;
+  LogPdfParts<T, NB> acc;      // per-block partial sums: bitwise the result of dalton_bl_kernel (rodeo_core.cuh)
   acc.init();
 
   // log p(Y_0 | X_0) when the first observation sits on t_min (dalton.py:207-215); joint filter only
@@ -425,7 +428,8 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
           res[r] = (T)((MT)__ldg(o.obs_data + b * NOBS + r) - m);
           RD_UNROLL for (int s = r; s < NOBS; ++s) Om[sidx<NOBS>(r, s)] = __ldg(o.obs_var + (b * NOBS + r) * NOBS + s);
         }
-        logpdf_terms<T, NOBS>(Om, res, acc);
+        auto&& ab = acc_at(acc, b);
+        logpdf_terms<T, NOBS>(Om, res, ab);
       }
     }
     i = 1;
@@ -450,7 +454,7 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
     } else {
       f.template update_z<true>(C, jl, res, V, acc);
     }
-    acc.ld.renorm();
+    acc.renorm();
   }
   const MT mine = acc.value();
   // logdens_joint - logdens_marg (dalton.py:235)
@@ -850,6 +854,18 @@ struct BlockLane {
 
   // one forward step n -> n+1 of this lane's block (predict, interrogate, update); all 32 lanes must call it
   RD_DEV void step(const CommonArgs<T>& a, const Par& q, i64 idx, int n, const ObsHook<T>* hook = nullptr) {
+    LogPdfAcc<T> dummy;
+    int io = -1;
+    if (hook != nullptr) io = __ldg(hook->step_obs + n);
+    step_lp<false, 1>(a, q, idx, n, hook != nullptr ? &hook->o : nullptr, io, dummy, 0);
+  }
+
+  // The same with the forecast log-density of the update added to `acc` (WITH_LOGPDF) and, for io >= 0, the
+  // observation rows of observation io (dalton zy_update, dalton.py:136-149).  NSTREAM / stream: layout of the injected
+  // interrogation normals and the Philox stream (dalton: 2 streams, joint = 0, marginal = 1).
+  template <bool WITH_LOGPDF, int NSTREAM, class ACC>
+  RD_DEV void step_lp(const CommonArgs<T>& a, const Par& q, i64 idx, int n, const ObsArgs<T>* o, int io, ACC& acc,
+                      int stream) {
     {
       MT mp[P];
       T Sp[NS];
@@ -862,19 +878,20 @@ struct BlockLane {
     if constexpr (INTERR == INTERR_CHKREBTII) {
       T zc[JC];
       if (a.z_interr != nullptr) {
-        const T* z = a.z_interr + (idx * a.n_steps + n) * (NB * P) + b * P;
+        const T* z = a.z_interr + ((idx * a.n_steps + n) * NSTREAM + stream) * (NB * P) + b * P;
         RD_UNROLL for (int j = 0; j < JC; ++j) zc[j] = z[j];
       } else {
         // the same stream layout as the thread-per-theta kernels: normal k = b*JC + j of the step's vector; only
         // the Philox pair(s) that hold this block's normals are generated
-        philox_normal_range<T, JC>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, b * JC, zc);
+        philox_normal_range<T, JC>(a.key0, a.key1, a.particle_offset + idx, n,
+                                   stream == 0 ? TAG_INTERR_A : TAG_INTERR_B, b * JC, zc);
       }
       T A[P][P];
       psd_factor<T, P>(S, A);
       RD_UNROLL for (int j = 0; j < JC; ++j) {
-        MT acc = mu[j];
-        RD_UNROLL for (int k = 0; k <= j; ++k) acc = rd_fma((MT)A[j][k], (MT)zc[k], acc);
-        xo[j] = acc;
+        MT xa = mu[j];
+        RD_UNROLL for (int k = 0; k <= j; ++k) xa = rd_fma((MT)A[j][k], (MT)zc[k], xa);
+        xo[j] = xa;
       }
     } else {
       RD_UNROLL for (int j = 0; j < JC; ++j) xo[j] = mu[j];
@@ -902,23 +919,20 @@ struct BlockLane {
         RD_UNROLL for (int j = 0; j < JC; ++j) jo[r][j] = (b == c) ? (T)jl[c][r][j] : jo[r][j];
       }
     }
-    LogPdfAcc<T> dummy;
-    int io = -1;
-    if (hook != nullptr) io = __ldg(hook->step_obs + n);
     if (io >= 0) {
       // augmented update with the observation rows of this block (dalton.py:136-149), scalar ODE row + one obs row
       if constexpr (M == 1) {
         T wa[2][P], Va[3];
         MT ra[2];
-        MT acc = fo[0], ya = (MT)__ldg(hook->o.obs_data + (io * NB + b));
+        MT acc0 = fo[0], ya = (MT)__ldg(o->obs_data + (io * NB + b));
         RD_UNROLL for (int j = 0; j < P; ++j) {
           const T w = UNITW ? (j == WK ? T(1) : T(0)) : W[0][j];
           wa[0][j] = (HAS_J && j < JC) ? w - jo[0][j] : w;
-          acc = rd_fma(-(MT)w, mu[j], acc);
-          wa[1][j] = __ldg(hook->o.obs_weight + (io * NB + b) * P + j);
+          acc0 = rd_fma(-(MT)w, mu[j], acc0);
+          wa[1][j] = __ldg(o->obs_weight + (io * NB + b) * P + j);
           ya = rd_fma(-(MT)wa[1][j], mu[j], ya);
         }
-        ra[0] = acc; ra[1] = ya;
+        ra[0] = acc0; ra[1] = ya;
         T V0 = T(0);
         if constexpr (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) {
           if (UNITW) V0 = S[sidx<P>(WK, WK)];
@@ -930,46 +944,130 @@ struct BlockLane {
             }
           }
         }
-        Va[0] = V0; Va[1] = T(0); Va[2] = __ldg(hook->o.obs_var + (io * NB + b));
-        update<T, P, 2, false>(mu, S, wa, ra, Va, dummy);
+        Va[0] = V0; Va[1] = T(0); Va[2] = __ldg(o->obs_var + (io * NB + b));
+        update<T, P, 2, WITH_LOGPDF>(mu, S, wa, ra, Va, acc);
       }
     } else if constexpr (UNITW) {
       const MT res = fo[0] - mu[WK];
       const T V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) ? S[sidx<P>(WK, WK)] : T(0);
-      update_unit_row<T, P, JC, WK, false, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(mu, S, jo[0], res, V,
-                                                                                                         dummy);
+      update_unit_row<T, P, JC, WK, WITH_LOGPDF, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(
+          mu, S, jo[0], res, V, acc);
     } else {
       T wm[M][P], V[MS];
       MT res[M];
       RD_UNROLL for (int r = 0; r < M; ++r) {
-        MT acc = fo[r];
+        MT acc0 = fo[r];
         RD_UNROLL for (int j = 0; j < P; ++j) {
           wm[r][j] = (HAS_J && j < JC) ? W[r][j] - jo[r][j] : W[r][j];
-          acc = rd_fma(-(MT)W[r][j], mu[j], acc);
+          acc0 = rd_fma(-(MT)W[r][j], mu[j], acc0);
         }
-        res[r] = acc;
+        res[r] = acc0;
       }
       if constexpr (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) {
         T u[M][P];
         RD_UNROLL for (int r = 0; r < M; ++r)
           RD_UNROLL for (int i = 0; i < P; ++i) {
-            T acc = S[sym<P>(i, 0)] * W[r][0];
-            RD_UNROLL for (int j = 1; j < P; ++j) acc = rd_fma(S[sym<P>(i, j)], W[r][j], acc);
-            u[r][i] = acc;
+            T acc0 = S[sym<P>(i, 0)] * W[r][0];
+            RD_UNROLL for (int j = 1; j < P; ++j) acc0 = rd_fma(S[sym<P>(i, j)], W[r][j], acc0);
+            u[r][i] = acc0;
           }
         RD_UNROLL for (int r = 0; r < M; ++r)
           RD_UNROLL for (int s = r; s < M; ++s) {
-            T acc = W[r][0] * u[s][0];
-            RD_UNROLL for (int i = 1; i < P; ++i) acc = rd_fma(W[r][i], u[s][i], acc);
-            V[sidx<M>(r, s)] = acc;
+            T acc0 = W[r][0] * u[s][0];
+            RD_UNROLL for (int i = 1; i < P; ++i) acc0 = rd_fma(W[r][i], u[s][i], acc0);
+            V[sidx<M>(r, s)] = acc0;
           }
       } else {
         RD_UNROLL for (int k = 0; k < MS; ++k) V[k] = T(0);
       }
-      update<T, P, M, false>(mu, S, wm, res, V, dummy);
+      update<T, P, M, WITH_LOGPDF>(mu, S, wm, res, V, acc);
     }
   }
 };
+
+// ------------------------------------------------------------------------------------------------------------------
+// dalton with one lane per (theta, filter, block)
+// ------------------------------------------------------------------------------------------------------------------
+// dalton_kernel gives a thread one filter of one theta with all of its blocks.  When the batch is too small to fill the
+// GPU's FP64 pipes -- 8,192 thetas per GPU is what BASELINE configs[1] leaves each of 8 GPUs: 512 warps for 592 SM
+// sub-partitions -- its run time is the serial dependency chain of one thread (measured 474 cycles per step against 250
+// issue cycles), so the blocks of a filter are spread over lanes as in solve_mv_bl_kernel: a warp carries 32 / n_block
+// thetas, every lane runs the recursion of ONE block, and the lanes of a theta exchange the ODE-visible entries of
+// their predicted means by shuffle once per step.  Same grid split as geometry 2 of dalton_kernel (first half of the
+// grid joint filters, second half marginal ones, combined by atomicAdd into the zeroed output).  The per-block partial
+// sums are gathered by shuffle at the end and combined exactly as LogPdfParts::value() does, so the result is BITWISE
+// the one of dalton_kernel: which kernel the host picks (by batch size) never shows in the numbers.
+#ifndef RODEO_DALTON_BL_MINB
+#define RODEO_DALTON_BL_MINB 12
+#endif
+template <typename T, class Model, int INTERR, int QK, int NOBS>
+__global__ void __launch_bounds__(32, RODEO_DALTON_BL_MINB)
+dalton_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                 const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ loglik) {
+  static_assert(NOBS == 1, "block-lane dalton: one observation row per block");
+  typedef BlockLane<T, Model, INTERR, QK> L;
+  typedef typename L::MT MT;
+  constexpr int NB = L::NB, P = L::P, TW = L::TW;
+  const int lane = threadIdx.x;
+  int b = lane / TW, tl = lane - b * TW;            // block-major lanes, see solve_mv_bl_kernel
+  const bool lane_ok = b < NB;
+  if (!lane_ok) { tl = TW - 1; b = NB - 1; }
+  const i64 half = gridDim.x >> 1;
+  const bool joint = (i64)blockIdx.x < half;
+  const i64 theta0 = (joint ? (i64)blockIdx.x : (i64)blockIdx.x - half) * TW;
+  i64 idx = theta0 + tl;
+  const bool live = lane_ok && idx < a.B;
+  if (idx >= a.B) idx = a.B - 1;
+  const typename L::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
+  L f;
+  f.b = b; f.gb = tl;
+  f.load_consts(C);
+  f.rs = a.r_scale != nullptr ? a.r_scale[idx * NB + b] : T(1);
+  f.init(a.ode_init + idx * NB * P);
+  LogPdfPart<T> part;
+  LogPdfCtl ctl;
+  part.init(); ctl.init();
+  LogPdfPartRef<T> acc{part, ctl};
+
+  // log p(Y_0 | X_0) when the first observation sits on t_min (dalton.py:207-215); joint filter only
+  int i = 0;
+  if (__ldg(o.obs_ind) == 0) {
+    if (joint) {
+      T res[1], Om[1];
+      MT m = MT(0);
+      RD_UNROLL for (int j = 0; j < P; ++j) m = rd_fma((MT)__ldg(o.obs_weight + b * P + j), f.mu[j], m);
+      res[0] = (T)((MT)__ldg(o.obs_data + b) - m);
+      Om[0] = __ldg(o.obs_var + b);
+      logpdf_terms<T, 1>(Om, res, acc);
+    }
+    i = 1;
+  }
+  int next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
+  for (int n = 0; n < a.n_steps; ++n) {
+    int io = -1;
+    if (n + 1 == next_obs) {
+      if (joint) io = i < o.n_obs ? i : o.n_obs - 1;
+      ++i;
+      next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
+    }
+    f.template step_lp<true, 2>(a, q, idx, n, &o, io, acc, joint ? 0 : 1);
+    part.renorm(ctl);
+  }
+  // every block's partial sums, in block order, then the one formula both kernels share
+  LogPdfPart<T> all[NB];
+  LogPdfCtl tot;
+  tot.init();
+  RD_UNROLL for (int c = 0; c < NB; ++c) {
+    const int src = c * TW + tl;
+    all[c].quad = __shfl_sync(0xffffffffu, part.quad, src);
+    all[c].prod = __shfl_sync(0xffffffffu, part.prod, src);
+    tot.esum += __shfl_sync(0xffffffffu, ctl.esum, src);
+    tot.cnt += __shfl_sync(0xffffffffu, ctl.cnt, src);
+    tot.sgn |= __shfl_sync(0xffffffffu, ctl.sgn, src);
+  }
+  const MT mine = combine_logpdf<T, NB>(all, tot);
+  if (live && b == 0 && lane < TW) atomicAdd(loglik + idx, (T)(joint ? mine : -mine));
+}
 
 // output stores: written once, never read back by the kernel
 template <typename T>

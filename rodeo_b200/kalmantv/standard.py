@@ -131,3 +131,17 @@ def smooth_cond(mean_state_filt, var_state_filt, mean_state_pred, var_state_pred
     """reference src/rodeo/kalmantv/standard.py:339-371 -> (wgt_state_cond, mean_state_cond, var_state_cond)"""
     b, C, A = _smooth(2, None, None, mean_state_filt, var_state_filt, mean_state_pred, var_state_pred, wgt_state)
     return A, b, C
+
+
+def psd_factor(var):
+    """Lower-triangular ``A`` with ``A A^T = var`` for a positive semi-definite ``var`` (``[..., p, p]``): the factor
+    the sampling kernels draw with, where the reference uses ``jax.random.multivariate_normal`` with its SVD / Cholesky
+    factor (src/rodeo/solve.py:179; src/rodeo/interrogate.py:30-34)."""
+    V, = _prep(var)
+    p = V.shape[-1]
+    lead = _batch(V, 2)
+    Vf = _flat(V, lead, (p, p))
+    A = torch.empty_like(Vf)
+    rc = _lib.load().rodeo_b200_psd_factor_f64(Vf.shape[0], p, _host.ptr(Vf), _host.ptr(A), _stream())
+    _lib.check(rc, "kalmantv.psd_factor")
+    return A.reshape(*lead, p, p)

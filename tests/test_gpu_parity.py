@@ -894,3 +894,56 @@ def test_basic_forwards_a_theta_dependent_prior(rb):
     ind = orc.obs_index(0.0, 5.0, 100, ob["obs_times"])
     want = np.sum(-0.5 * (ob["obs_data"][None, :, :, 0] - om[:, ind][:, :, :, 0]) ** 2 / 0.005, axis=(1, 2))
     assert ll_err(_np(ll), want) < 1e-9
+
+
+# ---- dalton launch geometries ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("interr", ["kramer", "rodeo", "chkrebtii"])
+def test_dalton_block_lane_kernel_is_bitwise_the_thread_per_filter_kernel(rb, monkeypatch, interr):
+    """Small batches run dalton with one lane per (theta, filter, block) (dalton_bl_kernel), large ones with one thread
+    per (theta, filter): the host chooses by batch size, so the two must agree BITWISE (per-block partial sums combined
+    in block order by both), and each must match the oracle.  Ragged batch (not a multiple of the 16 thetas a warp
+    carries), observation at t_min and on ordinary steps."""
+    B, N = 203, 240
+    pr = P.fitz_problem(B, n_steps=N, t_max=12.0, seed=29)
+    ob = P.fitz_obs(pr, None, n_obs=13)
+    zi = np.random.default_rng(3).standard_normal((B, N, 2, 2, 3)) if interr == "chkrebtii" else None
+    out = {}
+    for lanes in ("0", "1"):
+        monkeypatch.setenv("RODEO_DALTON_BLOCK_LANES", lanes)
+        out[lanes] = _np(rb.inference.dalton(0, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 12.0, N,
+                                             _interr(rb, interr), prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"],
+                                             _z_interr=zi, **ob))
+    assert np.array_equal(out["0"], out["1"])
+    kw = dict(z_interrogate=zi) if zi is not None else {}
+    oi = functools.partial(orc.interrogate_chkrebtii, factor="ldl") if interr == "chkrebtii" else ORC_INTERR[interr]
+    want = orc.dalton(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 12.0, N, oi, (pr["Q"], pr["R"]),
+                      pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"], **kw)
+    e = ll_err(out["1"], want)
+    print(f"dalton block lanes [{interr}] vs oracle: {e:.2e}")
+    assert e < (1e-9 if interr == "chkrebtii" else TOL)
+
+
+def test_dalton_block_lanes_three_blocks_lorenz(rb, monkeypatch):
+    """n_block = 3: 10 thetas per warp, two idle lanes; a per-theta prior scale on top."""
+    B, N = 37, 120
+    pr = P.lorenz_problem(B, n_steps=N, t_max=0.6, sigma=50.0, seed=31)
+    rng = np.random.default_rng(5)
+    n_obs = 7
+    obs_times = np.linspace(0.0, 0.6, n_obs)
+    obs_data = (np.array([-12.0, -5.0, 38.0]) + rng.standard_normal((n_obs, 3)))[:, :, None]
+    obs_weight = np.zeros((n_obs, 3, 1, 3)); obs_weight[..., 0] = 1.0
+    obs_var = np.full((n_obs, 3, 1, 1), 0.5)
+    sig = 50.0 * np.exp(0.2 * rng.standard_normal((B, 3)))
+    Q, Rb = rb.prior.ibm_init(0.6 / N, 3, sig)
+    out = {}
+    for lanes in ("0", "1"):
+        monkeypatch.setenv("RODEO_DALTON_BLOCK_LANES", lanes)
+        out[lanes] = _np(rb.inference.dalton(None, rb.models.lorenz63, pr["W"], pr["X0"], 0.0, 0.6, N,
+                                             rb.interrogate.interrogate_kramer, prior_pars=(Q, Rb), theta=pr["theta"],
+                                             obs_data=obs_data, obs_times=obs_times, obs_weight=obs_weight,
+                                             obs_var=obs_var))
+    assert np.array_equal(out["0"], out["1"])
+    Ro = np.stack([orc.ibm_init(0.6 / N, 3, sig[k])[1] for k in range(B)])
+    want = orc.dalton(orc.MODELS["lorenz63"], pr["W"], pr["X0"], 0.0, 0.6, N, orc.interrogate_kramer, (Q, Ro),
+                      pr["theta"], obs_data, obs_times, obs_weight, obs_var)
+    assert ll_err(out["1"], want) < 1e-9

@@ -333,3 +333,33 @@ def test_cuda_kalman_primitives(rb):
     lp = [float(rb.utils.multivariate_normal_logpdf(G["lpcut_in_x"][i], np.zeros(2), G["lpcut_in_cov"][i]))
           for i in range(5)]
     assert np.allclose(lp, G["lpcut"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_cuda_sampling_factor_squares_to_the_smoothing_covariance(rb):
+    """The reference draws with the SVD factor U sqrt(s) of the (singular) smoothing covariance (src/rodeo/solve.py:179,
+    182-186), whose column signs are LAPACK's: its draw vector `fitz_sim_x` cannot be reproduced bit for bit by any other
+    factor, only in distribution.  What makes the CUDA draws equal in distribution is A A^T = V for the factor the
+    kernels use -- checked here on every smoothing covariance of the `fitz_sim_*` golden set-up (filtered moments of the
+    golden inputs, conditioned on the reference's own draws), to 1e-10 of max|V|; and the conditional means / covariances
+    the CUDA primitives produce on the way equal the oracle's to 1e-10."""
+    import torch
+    pr, _ = prob("fitz")
+    model, t_max, N = grid("fitz")
+    mp, vp, mf, vf = orc.solve_filter(orc.MODELS[model], pr["W"], pr["X0"], 0.0, t_max, N, orc.interrogate_kramer,
+                                      pr["Q"], pr["R"], pr["theta"])
+    x = G["fitz_sim_x"]                                                    # the reference's draws (B, N+1, nb, p)
+    B, _, nb, p = x.shape
+    Q = np.broadcast_to(pr["Q"], (B, N - 1, nb, p, p))
+    # smooth_sim at t = 1 .. N-1 conditions on x[t+1] with filt[t], pred[t+1]   (solve.py:170-178)
+    m, V = rb.kalmantv.standard.smooth_sim(x[:, 2:N + 1], mf[:, 1:N], vf[:, 1:N], mp[:, 2:N + 1], vp[:, 2:N + 1], Q)
+    om, oV = orc.smooth_sim(x[:, 2:N + 1], mf[:, 1:N], vf[:, 1:N], mp[:, 2:N + 1], vp[:, 2:N + 1], Q)
+    assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(V), oV) < TOL
+    Vall = torch.cat([V.reshape(-1, p, p), torch.as_tensor(vf[:, N].reshape(-1, p, p), device=V.device)])
+    A = rb.kalmantv.standard.psd_factor(Vall)
+    AAt = _np(A @ A.transpose(-1, -2))
+    Vn = _np(Vall)
+    scale = np.abs(Vn).max(axis=(1, 2), keepdims=True)
+    err = float(np.max(np.abs(AAt - Vn) / scale))
+    print(f"sampling factor: max |A A^T - V| / max|V| = {err:.2e} over {len(Vn)} covariances")
+    assert np.array_equal(np.triu(_np(A), 1), np.zeros_like(Vn)) and err < TOL
