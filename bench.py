@@ -86,17 +86,23 @@ def cpu_run(pr, ob, ind, B, threads=0):
     return time.perf_counter() - t0, out
 
 
-def cpu_baseline(target_seconds=10.0):
+def cpu_baseline(target_seconds=10.0, return_outputs=False):
     """theta*steps/s of the C port with all host threads on a bounded sample (about `target_seconds` of CPU work)."""
     cores = host_threads()
     pr, ob, ind = cpu_problem(B_PER_GPU)
     dt, _ = cpu_run(pr, ob, ind, 2048)                      # calibration (also warms the thread pool)
     rate = 2048 * N_STEPS / dt
     Bs = int(min(B_PER_GPU, max(2048, rate * target_seconds / N_STEPS)))
-    dt, _ = cpu_run(pr, ob, ind, Bs)
-    return {"value": Bs * N_STEPS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{Bs} of {B_PER_GPU} thetas x {N_STEPS} steps, FN dalton f64, C/OpenMP port of the reference "
-                      f"algorithm (reference JAX unavailable), {dt:.2f} s"}
+    dt, out = cpu_run(pr, ob, ind, Bs)
+    rec = {"value": Bs * N_STEPS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{Bs} of {B_PER_GPU} thetas x {N_STEPS} steps, FN dalton f64, C/OpenMP port of the reference "
+                     f"algorithm (scalar, dense, -ffp-contract=off; NOT the reference's JAX, which cannot run here), "
+                     f"{dt:.2f} s"}
+    if not return_outputs:
+        return rec
+    cargs = ("fitzhugh_nagumo", "kramer", pr["W"], pr["X0"][:Bs], 0.0, T_MAX, N_STEPS, pr["Q"], pr["R"],
+             pr["theta"][:Bs], ob["obs_data"], ind, ob["obs_weight"], ob["obs_var"])
+    return rec, out, cargs
 
 
 def run_reference(args):
@@ -136,8 +142,9 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.stop, self.ok = [], set(), threading.Event(), False
+    def __init__(self, index, period=0.004):
+        self.samples, self.power, self.reasons, self.stop, self.ok = [], [], set(), threading.Event(), False
+        self.period = period
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -154,13 +161,14 @@ class ClockSampler:
         while not self.stop.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if r & bit and name != "gpu_idle":
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(self.period)
 
     def __enter__(self):
         if self.ok:
@@ -176,16 +184,81 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "sm_mhz_min": float(np.min(self.samples)),
+                "power_w_median": float(np.median(self.power)) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
+N_COPIES = 64     # resident copies of a launch's inputs (X0, theta: 4.7 MB each); launches rotate over them
+
+
+class Dalton:
+    """one rank's dalton launcher: resident inputs, the C-ABI call, output into a caller-chosen buffer.
+
+    L2 hygiene: the inputs of a launch are 4.7 MB, far below the 126 MB L2, so consecutive launches rotate over N_COPIES
+    identical copies (300 MB in total): the copy a launch reads was last touched 64 launches and 300 MB of traffic
+    earlier.  (The kernel is FP64-bound: a cold read of its inputs is < 1 us of a 0.74 ms launch.)"""
+
+    def __init__(self, lib, pr, ob, lo, hi, offset, copies=N_COPIES):
+        import rodeo_b200
+        from rodeo_b200 import _host
+        self.lib, self._host = lib, _host
+        fn, kramer = rodeo_b200.models.fitzhugh_nagumo, rodeo_b200.interrogate.interrogate_kramer
+        self.pb = _host.Problem(None, fn, pr["W"], pr["X0"][lo:hi], 0.0, T_MAX, N_STEPS, kramer, (pr["Q"], pr["R"]), None,
+                                None, "standard", {"theta": pr["theta"][lo:hi]}, particle_offset=offset)
+        self.pb.set_obs(ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+        self.B = hi - lo
+        self.x0 = self.pb.x0.unsqueeze(0).repeat(copies, 1, 1, 1).contiguous()
+        self.theta = self.pb.theta.unsqueeze(0).repeat(copies, 1, 1).contiguous()
+        self.copies, self.k = copies, 0
+
+    def __call__(self, out):
+        import ctypes as C
+        from rodeo_b200 import _lib
+        pb, h = self.pb, self._host
+        c = self.k % self.copies
+        self.k += 1
+        rc = self.lib.rodeo_b200_dalton_f64(C.byref(pb.c), h.ptr(pb.W), h.ptr(pb.Q), h.ptr(pb.R), h.ptr(self.x0[c]),
+                                            h.ptr(self.theta[c]), None, h.ptr(pb.obs_ind), h.ptr(pb.obs_data),
+                                            h.ptr(pb.obs_weight), h.ptr(pb.obs_var), h.ptr(out), None, 0, pb.stream())
+        _lib.check(rc, "dalton")
+
+
+def timed_steps(torch, dist, world, dev, launcher, pipe, steps):
+    """K steps = K kernel launches, each followed (world > 1) by the all-gather of its log-likelihoods through the
+    product's GatherPipeline (the collective of step k overlaps the kernel of step k+1; the last one is drained inside
+    the timed region).  Returns (ms per step: wall of the whole region on the device, max over ranks; per-launch kernel
+    ms from events around each launch)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for e0, e1 in kev:
+        buf = pipe.local_buffer()
+        e0.record()
+        launcher(buf)
+        e1.record()
+        pipe.submit()
+    pipe.drain()
+    t1.record()
+    barrier()
+    total = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    return float(total.item()) / steps, np.array([e0.elapsed_time(e1) for e0, e1 in kev])
+
+
 def run_ours(args):
     import torch
     import rodeo_b200
-    from rodeo_b200 import _host, _lib
+    from rodeo_b200 import _host, _lib, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,66 +273,94 @@ def run_ours(args):
     lib = _lib.load()
     dev = torch.device("cuda", local)
     B, N = args.thetas, N_STEPS
+    steps, warm = args.steps, max(args.warmup, 3)
 
-    # ---- synthetic inputs: each rank owns its own contiguous shard of the global theta batch (weak scaling)
+    # ---- synthetic inputs.  Weak scaling: rank r owns thetas [r B, (r+1) B) of a world*B batch (its own seed).
     pr = workload(B, seed=rank)
     pr0 = P.fitz_problem(1, N, T_MAX, jitter=False)
     fn, kramer = rodeo_b200.models.fitzhugh_nagumo, rodeo_b200.interrogate.interrogate_kramer
     truth, _ = rodeo_b200.solve_mv(None, fn, pr0["W"], pr0["X0"][0], 0.0, T_MAX, N, kramer,
                                    prior_pars=(pr0["Q"], pr0["R"]), theta=pr0["theta"][0])
     ob = obs_for(pr, truth.cpu().numpy())
-
-    pb = _host.Problem(None, fn, pr["W"], pr["X0"], 0.0, T_MAX, N, kramer, (pr["Q"], pr["R"]), None, None,
-                       "standard", {"theta": pr["theta"]}, particle_offset=rank * B)
-    pb.set_obs(ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
-    out = torch.empty((B,), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * B,), dtype=torch.float64, device=dev) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-
-    def step():
-        rc = lib.rodeo_b200_dalton_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
-                                       _host.ptr(pb.x0), _host.ptr(pb.theta), None, _host.ptr(pb.obs_ind),
-                                       _host.ptr(pb.obs_data), _host.ptr(pb.obs_weight), _host.ptr(pb.obs_var),
-                                       _host.ptr(out), None, 0, pb.stream())
-        _lib.check(rc, "dalton")
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+    weak = Dalton(lib, pr, ob, 0, B, rank * B)
+    pipe = parallel.GatherPipeline(B, dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step()
+    for _ in range(warm):
+        weak(pipe.local_buffer())
+        pipe.submit()
+    pipe.drain()
     barrier()
 
-    # ---- device-resident timed region: K steps, CUDA events on the launching stream, L2 flushed between steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- device-resident timed region
     launches0 = lib.rodeo_b200_launch_count()
     with ClockSampler(local) as clk:
-        barrier()
         t_wall0 = time.perf_counter()
-        for e0, e1 in ev:
-            flush.zero_()
-            e0.record()
-            step()
-            e1.record()
-        barrier()
+        ms_per_step, kern_ms = timed_steps(torch, dist, world, dev, weak, pipe, steps)
         t_wall = time.perf_counter() - t_wall0
     launches = lib.rodeo_b200_launch_count() - launches0
-    step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
-    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
     value = world * B * N / (ms_per_step * 1e-3)
+    out = pipe.local[(pipe.k - 1) % pipe.depth].clone()                     # this rank's result of the last step
+    gather_ok = None
+    if world > 1:
+        # the gathered vector holds every rank's shard in rank order: this rank's slice is its own output, bitwise, and
+        # every rank holds the same vector (compare a position-weighted checksum across ranks)
+        full = pipe.result((pipe.k - 1) % pipe.depth)
+        own = bool(torch.equal(full[rank * B:(rank + 1) * B], out))
+        w = torch.arange(1, full.numel() + 1, dtype=torch.float64, device=dev)
+        cs = torch.stack([(full * w).sum(), -(full * w).sum()])
+        dist.all_reduce(cs, op=dist.ReduceOp.MAX)
+        same = bool((cs[0] == -cs[1]).item())
+        flag = torch.tensor([int(own and same and bool(torch.isfinite(full).all()))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
+        if not gather_ok:
+            raise SystemExit("bench.py: the gathered log-likelihoods do not match the per-rank outputs")
+
+    # ---- strong scaling at BASELINE configs[1]'s stated total: 65,536 thetas over `world` GPUs
+    strong = None
+    if args.thetas == B_PER_GPU:
+        prg = workload(B_PER_GPU, seed=0)                                    # the global batch, identical on every rank
+        obg = obs_for(prg, truth.cpu().numpy())
+        lo, hi = parallel.shard_bounds(B_PER_GPU, rank, world)
+        sh = Dalton(lib, prg, obg, lo, hi, lo)
+        spipe = parallel.GatherPipeline(hi - lo, dev)
+        for _ in range(warm):
+            sh(spipe.local_buffer()); spipe.submit()
+        spipe.drain()
+        s_ms, s_kern = timed_steps(torch, dist, world, dev, sh, spipe, steps)
+        rec = {"thetas_total": B_PER_GPU, "thetas_per_gpu": hi - lo, "ms_per_step": s_ms,
+               "value": B_PER_GPU * N / (s_ms * 1e-3), "unit": UNIT, "kernel_ms": float(np.mean(s_kern)),
+               "collective": "all-gather of the shard's log-likelihoods inside the step" if world > 1 else None}
+        if world > 1:
+            # one GPU doing the whole batch, measured in the same run (every rank times it; max over ranks)
+            one = Dalton(lib, prg, obg, 0, B_PER_GPU, 0)
+            opipe = parallel.GatherPipeline(B_PER_GPU, dev, collective=False)
+            for _ in range(warm):
+                one(opipe.local_buffer()); opipe.submit()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one(opipe.local_buffer()); opipe.submit()
+            e1.record(); barrier()
+            t1 = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            full1 = opipe.local[(opipe.k - 1) % opipe.depth]
+            fullN = spipe.result((spipe.k - 1) % spipe.depth)
+            rec.update({"one_gpu_ms_per_step": float(t1.item()), "speedup_vs_one_gpu": float(t1.item()) / s_ms,
+                        "sharded_equals_unsharded_bitwise": bool(torch.equal(full1, fullN))})
+        strong = rec
 
     # ---- end to end through the C ABI with host buffers (pinned), H2D + kernel + D2H inside the timed region
     h_x0 = torch.from_numpy(pr["X0"]).pin_memory()
     h_th = torch.from_numpy(pr["theta"]).pin_memory()
     h_out = torch.empty((B,), dtype=torch.float64).pin_memory()
+    pb = weak.pb
     h_ind = np.ascontiguousarray(pb.obs_ind_host)
     h_y, h_D, h_Om = (np.ascontiguousarray(ob[k]) for k in ("obs_data", "obs_weight", "obs_var"))
 
@@ -270,7 +371,7 @@ def run_ours(args):
                                             ctypes.c_void_p(h_out.data_ptr()))
         _lib.check(rc, "dalton_host")
 
-    n_e2e = 0 if args.skip_e2e else args.steps
+    n_e2e = 0 if args.skip_e2e else steps
     for _ in range(0 if args.skip_e2e else 3):
         e2e_step()
     barrier()
@@ -285,16 +386,58 @@ def run_ours(args):
     d2h = int(h_out.numel() * 8)
     same = bool(np.array_equal(h_out.numpy(), out.cpu().numpy(), equal_nan=True)) if n_e2e else None
 
+    # ---- the call a rodeo user makes: the Python drop-in with NumPy inputs (pageable H2D, per-call allocation), result
+    #      copied back to NumPy
+    e2e_py = None
+    if not args.skip_e2e:
+        kw = dict(prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"], **ob)
+
+        def py_step():
+            return rodeo_b200.inference.dalton(None, fn, pr["W"], pr["X0"], 0.0, T_MAX, N, kramer, **kw).cpu().numpy()
+        for _ in range(2):
+            r_py = py_step()
+        barrier()
+        n_py = max(3, min(steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_py):
+            r_py = py_step()
+        t_py = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_py, op=dist.ReduceOp.MAX)
+        e2e_py = {"value": world * B * N * n_py / float(t_py.item()), "unit": UNIT,
+                  "api": "rodeo_b200.inference.dalton(NumPy inputs) -> .cpu().numpy()",
+                  "matches_device_path": bool(np.array_equal(r_py, out.cpu().numpy(), equal_nan=True))}
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant (only) kernel: FP64-pipe bound, algorithmic flops / measured DFMA peak
+    # ---- sustained: >= 2 s of back-to-back launches (no flush, no host work in between), clocks sampled throughout
+    sustained = None
+    if world == 1 and not args.skip_sustained:
+        buf = pipe.local_buffer()
+        n_sus = int(2.2 / (float(np.mean(kern_ms)) * 1e-3)) + 1
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        with ClockSampler(local, period=0.05) as sclk:
+            e0.record()
+            for _ in range(n_sus):
+                weak(buf)
+            e1.record()
+            torch.cuda.synchronize()
+        sus_ms = e0.elapsed_time(e1) / n_sus
+        sustained = {"launches": n_sus, "seconds": e0.elapsed_time(e1) * 1e-3, "ms_per_step": sus_ms,
+                     "value": B * N / (sus_ms * 1e-3), "unit": UNIT, "clocks": sclk.summary(),
+                     "note": "back-to-back launches for >= 2 s with no host work in between (inputs rotate over the 64 "
+                             "copies as in the burst figure)"}
+
+    # ---- roofline of the dominant (only) kernel: FP64-pipe bound
     peak = ctypes.c_double(0.0)
     _lib.check(lib.rodeo_b200_fp64_peak_probe(5, ctypes.byref(peak)), "fp64 probe")
-    kern_ms = float(np.mean(step_ms)) if world == 1 else ms_per_step
-    achieved = FLOPS_PER_THETA_STEP * B * N / (kern_ms * 1e-3) / 1e12
+    k_ms = float(np.mean(kern_ms))
+    achieved = FLOPS_PER_THETA_STEP * B * N / (k_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,39 +451,76 @@ def run_ours(args):
             traffic, fp64_instr = prof.get("dram_bytes_per_launch"), prof.get("fp64_instr_per_theta_step")
         except Exception:
             traffic = None
+    pipe_frac = ((fp64_instr * B * N / (k_ms * 1e-3)) / (float(peak.value) * 1e12 / 2.0)
+                 if (fp64_instr and peak.value) else None)
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
         "frac": achieved / float(peak.value) if peak.value else None, "traffic": traffic,
-        "peak_source": "DFMA micro-benchmark run in this process (rodeo_b200_fp64_peak_probe); "
-                       "MEASURED_PEAKS.json has no FP64 figure",
+        # two named views of the same measurement.  frac_dense (= frac) follows SURVEY 8(d): DENSE algorithmic flops
+        # (963 per theta*step, no structure exploited) / kernel time / measured DFMA peak; it exceeds 1 because the
+        # kernel skips the multiplications by the exact 0/1 entries of the unit-triangular Q and the unit-row W and
+        # conditions on an observation by two scalar updates.  frac_fp64_pipe is the hardware view: FP64 instructions
+        # the kernel actually executes (ncu source counters, profiles/) x measured launch rate / DFMA issue rate.
+        "frac_dense": achieved / float(peak.value) if peak.value else None,
+        "frac_fp64_pipe": pipe_frac,
+        "kernel_ms": k_ms,
+        "peak_source": "DFMA micro-benchmark run in this process (rodeo_b200_fp64_peak_probe, private stream); "
+                       "MEASURED_PEAKS.json has no FP64 figure; spec estimate 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
         "algorithmic_flops_per_theta_step": FLOPS_PER_THETA_STEP,
-        # hardware view: the kernel exploits the unit-triangular Q / unit-row W structure and executes fewer FP64
-        # instructions than the dense count (hence frac > 1); this is the share of the FP64 pipe's issue slots it fills
-        # (executed FP64 instructions per theta*step from the committed ncu source counters x measured rate / DFMA rate)
-        "fp64_pipe_frac": (fp64_instr * B * N / (kern_ms * 1e-3)) / (float(peak.value) * 1e12 / 2.0)
-                          if (fp64_instr and peak.value) else None,
         "executed_fp64_instr_per_theta_step": fp64_instr,
         "hbm_view": {"algorithmic_bytes_per_launch": int(B * (6 + 3 + 1) * 8),
                      "hbm_gbs_measured": peaks.get("hbm_gbs")},
     }
 
-    cpu = cpu_baseline() if (world == 1 and not args.skip_cpu) else None
+    # ---- CPU baseline and parity of the TIMED launch: every theta against the C port (float64) of the cpu_baseline
+    #      leg, judged against the same port in long double (tests/noise_floor.py)
+    cpu, parity = None, None
+    if world == 1 and not args.skip_cpu:
+        cpu, cpu_out, cpu_args = cpu_baseline(return_outputs=True)
+        nb_ = min(len(cpu_out), B)
+        if nb_ > 0:
+            import noise_floor as NF
+            from oracle import c_port
+            exact = c_port.dalton_ld(*cpu_args, n_threads=host_threads())
+            parity = NF.gate(out.cpu().numpy()[:nb_], cpu_out[:nb_], exact[:nb_])
+            parity["against"] = ("%d of the %d thetas of the timed launch; oracle = C port of the reference algorithm "
+                                 "(float64), exact = the same port in x87 long double" % (nb_, B))
+
+    configs = None
+    if world == 1 and not args.skip_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        torch.cuda.empty_cache()
+        configs = bench_configs.run("C1,C3,C4,C5", reps=3, quiet=True)
+        cpath = os.path.join(ROOT, "profiles", "config_traffic.json")
+        if os.path.exists(cpath):
+            extra = json.load(open(cpath))
+            for c in configs:
+                c.update(extra.get(c["config"].split()[0], {}))
+
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "FitzHugh-Nagumo dalton log-likelihood (BASELINE configs[1]): 65,536 thetas per GPU, "
                                "n_steps=800, t in [0,40], n_obs=41, interrogate_kramer, IBM sigma=0.1, float64",
                    "thetas_per_gpu": B, "n_steps": N, "n_obs": N_OBS, "parallelism": f"theta-sharded x{world}",
-                   "l2": "256 MiB memset between timed steps (outside the event brackets)"},
-        "roofline": roofline, "cpu_baseline": cpu,
+                   "l2": "inputs larger than L2: launches rotate over 64 resident copies of (X0, theta), 300 MB in total",
+                   "step": "one dalton launch over the rank's batch" + (
+                       " + NCCL all-gather of its log-likelihoods through rodeo_b200.parallel.GatherPipeline "
+                       "(the collective of step k overlaps the kernel of step k+1; drained inside the timed region)"
+                       if world > 1 else "")},
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "rodeo_b200_dalton_f64_host (C ABI, pinned host buffers)", "matches_device_path": same},
+        "e2e_python": e2e_py, "strong": strong, "sustained": sustained, "configs": configs,
+        "gather_matches_rank_outputs": gather_ok,
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -354,6 +534,8 @@ def main():
                     help="thetas per GPU (tuning experiments only; the benchmark configuration is the default)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer e2e leg")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the C1/C3/C4/C5 records")
+    ap.add_argument("--skip-sustained", action="store_true", help="skip the >= 2 s back-to-back run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

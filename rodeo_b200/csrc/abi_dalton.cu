@@ -3,9 +3,9 @@
 
 #include "rodeo_host.h"
 
-// (theta, filter, block) lanes below this many (theta, filter) warps per SM sub-partition
+// (theta, filter, block) lanes while their grid has at most this many warps per SM sub-partition
 #ifndef RODEO_DALTON_BL_BELOW
-#define RODEO_DALTON_BL_BELOW 2.0
+#define RODEO_DALTON_BL_BELOW 1.0
 #endif
 
 #ifndef RODEO_REAL
@@ -34,14 +34,16 @@ struct DaltonRun {
     CommonArgs<real_t> ag = a;
     if constexpr (sizeof(real_t) == 8) {
       RODEO_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)p.B * sizeof(real_t), s));
-      // Small batches cannot fill the FP64 pipes with one thread per (theta, filter): below about two such warps per SM
-      // sub-partition the run time is one thread's dependency chain, and spreading the blocks of a filter over lanes
-      // (dalton_bl_kernel) shortens that chain by n_block.  Both kernels return bitwise the same numbers.  Measured on
-      // B200, FitzHugh-Nagumo N = 800: see DESIGN.md section 4.1.
+      // A lone warp per SM sub-partition is bound by its own FP64 issue cadence (one DFMA per 2 cycles): spreading the
+      // blocks of a filter over lanes (dalton_bl_kernel) halves the instructions per lane, which pays only while every
+      // such warp still has a sub-partition to itself.  Measured on B200, FitzHugh-Nagumo N = 800, thread-per-filter /
+      // block lanes: 2,048 thetas 0.146 / 0.138 ms, 4,096: 0.162 / 0.138, 8,192: 0.147 / 0.176, 16,384: 0.243 / 0.310,
+      // 65,536: 0.733 / 0.976.  Both kernels return bitwise the same numbers.
       bool block_lanes = false;
       if constexpr (Model::NB >= 2) {
-        const double warps_per_subpartition = 2.0 * grid_for(p.B, 32) / (4.0 * sm_count());
-        block_lanes = warps_per_subpartition < RODEO_DALTON_BL_BELOW;
+        // (theta, filter, block) lanes while every warp of theirs still gets an SM sub-partition to itself
+        typedef BlockLane<real_t, Model, INTERR, QK> L0;
+        block_lanes = 2.0 * grid_for(p.B, L0::TW) <= RODEO_DALTON_BL_BELOW * 4.0 * sm_count();
         if (const char* e = getenv("RODEO_DALTON_BLOCK_LANES")) block_lanes = e[0] == '1';      // tuning / tests
         if (block_lanes) {
           typedef BlockLane<real_t, Model, INTERR, QK> L;

@@ -142,6 +142,7 @@ static int dalton_host_body(const RodeoProblem* p, const double* ode_weight, con
   }
   const size_t per = (B + nchunk - 1) / nchunk;
   const size_t row_init = nb * ps, row_theta = (size_t)p->n_theta;
+  int launched = 0;
   for (int c = 0; c < nchunk; ++c) {
     const size_t b0 = (size_t)c * per;
     if (b0 >= B) break;
@@ -163,8 +164,10 @@ static int dalton_host_body(const RodeoProblem* p, const double* ode_weight, con
                                        g_arena.lane[c]))
       return rc;
     RODEO_CUDA_OK(cudaEventRecord(g_arena.done[c], g_arena.lane[c]));
-    RODEO_CUDA_OK(cudaStreamWaitEvent(s, g_arena.done[c], 0));
+    ++launched;
   }
+  // only now does the copy stream wait for the kernels: waiting inside the loop would hold back the next chunk's copies
+  for (int c = 0; c < launched; ++c) RODEO_CUDA_OK(cudaStreamWaitEvent(s, g_arena.done[c], 0));
   RODEO_CUDA_OK(cudaMemcpyAsync(loglik_out, d_ll, b_ll, cudaMemcpyDeviceToHost, s));
   RODEO_CUDA_OK(cudaStreamSynchronize(s));
   return RODEO_OK;

@@ -235,7 +235,7 @@ struct Fwd {
     RD_UNROLL for (int b = 0; b < NB; ++b)
       RD_UNROLL for (int r = 0; r < M; ++r) {
         if (UNITW) {
-          res[b][r] = f[b][r] - mu[b][WK];
+          res[b][r] = sub_exact(f[b][r], mu[b][WK]);
         } else {
           MT a = f[b][r];
           RD_UNROLL for (int j = 0; j < P; ++j) a = rd_fma(-(MT)C.W[b][r][j], mu[b][j], a);
@@ -322,28 +322,49 @@ struct Fwd {
   RD_DEV void update_zy(const Consts& C, const T (&jl)[NB][M][JC], const MT (&res)[NB][M], const T (&V)[NB][MS],
                         const ObsArgs<T>& o, int i, ACCS& acc) {
     constexpr int MA = M + NOBS, MAS = MA * (MA + 1) / 2;
+    constexpr bool HAS_V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII);
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T wa[MA][P], Va[MAS], wm[M][P];
-      MT ra[MA];
-      rows(C, b, jl[b], wm);
-      RD_UNROLL for (int k = 0; k < MAS; ++k) Va[k] = T(0);
-      RD_UNROLL for (int r = 0; r < M; ++r) {
-        RD_UNROLL for (int j = 0; j < P; ++j) wa[r][j] = wm[r][j];
-        ra[r] = res[b][r];
-        RD_UNROLL for (int s = r; s < M; ++s) Va[sidx<MA>(r, s)] = V[b][sidx<M>(r, s)];
-      }
-      RD_UNROLL for (int r = 0; r < NOBS; ++r) {
-        MT a = (MT)__ldg(o.obs_data + (i * NB + b) * NOBS + r);
-        RD_UNROLL for (int j = 0; j < P; ++j) {
-          wa[M + r][j] = __ldg(o.obs_weight + ((i * NB + b) * NOBS + r) * P + j);
-          a = rd_fma(-(MT)wa[M + r][j], mu[b][j], a);
-        }
-        ra[M + r] = a;
-        RD_UNROLL for (int s = r; s < NOBS; ++s)
-          Va[sidx<MA>(M + r, M + s)] = __ldg(o.obs_var + ((i * NB + b) * NOBS + r) * NOBS + s);
-      }
       auto&& ab = acc_at(acc, b);
-      update<T, P, MA, WITH_LOGPDF>(mu[b], S[b], wa, ra, Va, ab);
+      if constexpr (M == 1 && NOBS == 1 && sizeof(T) == 8) {
+        // one ODE row + one observation row with uncorrelated noises: two scalar updates (rodeo_core.cuh).  float64
+        // only: in float32 the Schur complement formed through the downdated covariance costs accuracy the float32
+        // instantiation does not have to spare (dalton 1.2e-5 against 7.5e-6 with the stacked update; gate 1e-5)
+        T D[P];
+        const MT ry = (MT)__ldg(o.obs_data + (i * NB + b));
+        RD_UNROLL for (int j = 0; j < P; ++j) D[j] = __ldg(o.obs_weight + (i * NB + b) * P + j);
+        const T Om = __ldg(o.obs_var + (i * NB + b));
+        const DenseRow<T, P> row2{D};
+        if constexpr (UNITW) {
+          const UnitRow<T, P, JC, WK, HAS_J> row1{jl[b][0]};
+          update_two_rows<T, P, WITH_LOGPDF, HAS_V>(mu[b], S[b], row1, res[b][0], V[b][0], row2, ry, Om, ab);
+        } else {
+          T wm[M][P];
+          rows(C, b, jl[b], wm);
+          const DenseRow<T, P> row1{wm[0]};
+          update_two_rows<T, P, WITH_LOGPDF, HAS_V>(mu[b], S[b], row1, res[b][0], V[b][0], row2, ry, Om, ab);
+        }
+      } else {
+        T wa[MA][P], Va[MAS], wm[M][P];
+        MT ra[MA];
+        rows(C, b, jl[b], wm);
+        RD_UNROLL for (int k = 0; k < MAS; ++k) Va[k] = T(0);
+        RD_UNROLL for (int r = 0; r < M; ++r) {
+          RD_UNROLL for (int j = 0; j < P; ++j) wa[r][j] = wm[r][j];
+          ra[r] = res[b][r];
+          RD_UNROLL for (int s = r; s < M; ++s) Va[sidx<MA>(r, s)] = V[b][sidx<M>(r, s)];
+        }
+        RD_UNROLL for (int r = 0; r < NOBS; ++r) {
+          MT a = (MT)__ldg(o.obs_data + (i * NB + b) * NOBS + r);
+          RD_UNROLL for (int j = 0; j < P; ++j) {
+            wa[M + r][j] = __ldg(o.obs_weight + ((i * NB + b) * NOBS + r) * P + j);
+            a = rd_fma(-(MT)wa[M + r][j], mu[b][j], a);
+          }
+          ra[M + r] = a;
+          RD_UNROLL for (int s = r; s < NOBS; ++s)
+            Va[sidx<MA>(M + r, M + s)] = __ldg(o.obs_var + ((i * NB + b) * NOBS + r) * NOBS + s);
+        }
+        update<T, P, MA, WITH_LOGPDF>(mu[b], S[b], wa, ra, Va, ab);
+      }
     }
   }
 
@@ -437,24 +458,35 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   // traced out-of-range gathers clamp: obs_ind[min(i, n_obs-1)]
   int next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
 
-  for (int n = 0; n < a.n_steps; ++n) {
+  // One step n -> n+1; io >= 0: the joint filter's step that also conditions on observation io (dalton.py:136-149).
+  // Each filter is linearised at its own prediction (dalton.py:116-132, 168-184).
+  auto step = [&](int n, int io) {
     const MT t = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, n, a.n_steps) : MT(0);
     T jl[NB][M][JC], V[NB][MS], zc[NB][JC];
     MT res[NB][M];
-    // each filter is linearised at its own prediction (dalton.py:116-132, 168-184)
     f.predict_all(C);
     f.template interr_normals<2>(a, idx, n, joint ? 0 : 1, zc);
     f.interrogate(C, q, t, zc, jl, res, V);
-    if (n + 1 == next_obs) {
-      const int ic = i < o.n_obs ? i : o.n_obs - 1;
-      if (joint) f.template update_zy<NOBS, true>(C, jl, res, V, o, ic, acc);
-      else f.template update_z<true>(C, jl, res, V, acc);
-      ++i;
-      next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
-    } else {
-      f.template update_z<true>(C, jl, res, V, acc);
-    }
-    acc.renorm();
+    if (io >= 0) f.template update_zy<NOBS, true>(C, jl, res, V, o, io, acc);
+    else f.template update_z<true>(C, jl, res, V, acc);
+    if ((n & 3) == 3) acc.renorm();       // fold the exponents of the running products every 4th step
+  };
+  // The reference's scan tests t + 1 == obs_ind[i] at every step (dalton.py:163).  Here the steps between two
+  // observations run in an inner loop without that test (the loop body is then branch-free: no observation bookkeeping,
+  // no reconvergence point on the dependency chain of a lone warp).  Same semantics, including the corner cases: an
+  // observation index that is not ahead of the current step (duplicates, obs_ind[0] == 0 consumed above, the clamped
+  // index after the last observation) never matches again.
+  int n = 0;
+  const int N = a.n_steps;
+  for (;;) {
+    const int stop = next_obs - 1;                         // the step with n + 1 == next_obs
+    const bool has_obs = stop >= n && stop < N;
+    const int end = has_obs ? stop : N;
+    for (; n < end; ++n) step(n, -1);
+    if (!has_obs) break;
+    step(n, joint ? (i < o.n_obs ? i : o.n_obs - 1) : -1);
+    ++n; ++i;
+    next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
   }
   const MT mine = acc.value();
   // logdens_joint - logdens_marg (dalton.py:235)
@@ -920,35 +952,41 @@ struct BlockLane {
       }
     }
     if (io >= 0) {
-      // augmented update with the observation rows of this block (dalton.py:136-149), scalar ODE row + one obs row
+      // augmented update with the observation row of this block (dalton.py:136-149): scalar ODE row + one obs row with
+      // uncorrelated noises = two scalar updates (rodeo_core.cuh update_two_rows; the same call as Fwd::update_zy)
       if constexpr (M == 1) {
-        T wa[2][P], Va[3];
-        MT ra[2];
-        MT acc0 = fo[0], ya = (MT)__ldg(o->obs_data + (io * NB + b));
-        RD_UNROLL for (int j = 0; j < P; ++j) {
-          const T w = UNITW ? (j == WK ? T(1) : T(0)) : W[0][j];
-          wa[0][j] = (HAS_J && j < JC) ? w - jo[0][j] : w;
-          acc0 = rd_fma(-(MT)w, mu[j], acc0);
-          wa[1][j] = __ldg(o->obs_weight + (io * NB + b) * P + j);
-          ya = rd_fma(-(MT)wa[1][j], mu[j], ya);
-        }
-        ra[0] = acc0; ra[1] = ya;
-        T V0 = T(0);
-        if constexpr (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) {
-          if (UNITW) V0 = S[sidx<P>(WK, WK)];
-          else {
+        constexpr bool HAS_V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII);
+        T D[P];
+        const MT ry = (MT)__ldg(o->obs_data + (io * NB + b));
+        RD_UNROLL for (int j = 0; j < P; ++j) D[j] = __ldg(o->obs_weight + (io * NB + b) * P + j);
+        const T Om = __ldg(o->obs_var + (io * NB + b));
+        const DenseRow<T, P> row2{D};
+        if constexpr (UNITW) {
+          const MT res = sub_exact(fo[0], mu[WK]);
+          const T V0 = HAS_V ? S[sidx<P>(WK, WK)] : T(0);
+          const UnitRow<T, P, JC, WK, HAS_J> row1{jo[0]};
+          update_two_rows<T, P, WITH_LOGPDF, HAS_V>(mu, S, row1, res, V0, row2, ry, Om, acc);
+        } else {
+          T wm[P];
+          MT res = fo[0];
+          RD_UNROLL for (int j = 0; j < P; ++j) {
+            wm[j] = (HAS_J && j < JC) ? W[0][j] - jo[0][j] : W[0][j];
+            res = rd_fma(-(MT)W[0][j], mu[j], res);
+          }
+          T V0 = T(0);
+          if constexpr (HAS_V) {
             RD_UNROLL for (int i = 0; i < P; ++i) {
-              T u = T(0);
-              RD_UNROLL for (int j = 0; j < P; ++j) u = rd_fma(S[sym<P>(i, j)], W[0][j], u);
-              V0 = rd_fma(W[0][i], u, V0);
+              T u = S[sym<P>(i, 0)] * W[0][0];
+              RD_UNROLL for (int j = 1; j < P; ++j) u = rd_fma(S[sym<P>(i, j)], W[0][j], u);
+              V0 = i == 0 ? W[0][0] * u : rd_fma(W[0][i], u, V0);
             }
           }
+          const DenseRow<T, P> row1{wm};
+          update_two_rows<T, P, WITH_LOGPDF, HAS_V>(mu, S, row1, res, V0, row2, ry, Om, acc);
         }
-        Va[0] = V0; Va[1] = T(0); Va[2] = __ldg(o->obs_var + (io * NB + b));
-        update<T, P, 2, WITH_LOGPDF>(mu, S, wa, ra, Va, acc);
       }
     } else if constexpr (UNITW) {
-      const MT res = fo[0] - mu[WK];
+      const MT res = sub_exact(fo[0], mu[WK]);
       const T V = (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII) ? S[sidx<P>(WK, WK)] : T(0);
       update_unit_row<T, P, JC, WK, WITH_LOGPDF, HAS_J, (INTERR == INTERR_RODEO || INTERR == INTERR_CHKREBTII)>(
           mu, S, jo[0], res, V, acc);
@@ -1043,15 +1081,22 @@ dalton_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
     i = 1;
   }
   int next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
-  for (int n = 0; n < a.n_steps; ++n) {
-    int io = -1;
-    if (n + 1 == next_obs) {
-      if (joint) io = i < o.n_obs ? i : o.n_obs - 1;
-      ++i;
-      next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
+  // steps between two observations run in a branch-free inner loop: see dalton_kernel
+  int n = 0;
+  const int N = a.n_steps;
+  for (;;) {
+    const int stop = next_obs - 1;
+    const bool has_obs = stop >= n && stop < N;
+    const int end = has_obs ? stop : N;
+    for (; n < end; ++n) {
+      f.template step_lp<true, 2>(a, q, idx, n, &o, -1, acc, joint ? 0 : 1);
+      if ((n & 3) == 3) part.renorm(ctl);
     }
-    f.template step_lp<true, 2>(a, q, idx, n, &o, io, acc, joint ? 0 : 1);
-    part.renorm(ctl);
+    if (!has_obs) break;
+    f.template step_lp<true, 2>(a, q, idx, n, &o, joint ? (i < o.n_obs ? i : o.n_obs - 1) : -1, acc, joint ? 0 : 1);
+    if ((n & 3) == 3) part.renorm(ctl);
+    ++n; ++i;
+    next_obs = __ldg(o.obs_ind + (i < o.n_obs ? i : o.n_obs - 1));
   }
   // every block's partial sums, in block order, then the one formula both kernels share
   LogPdfPart<T> all[NB];

@@ -55,6 +55,75 @@ def all_gather_loglik(local, B_total=None, group=None, out=None):
     return torch.cat([buf[r * m:r * m + s] for r, s in enumerate(sizes)])
 
 
+class GatherPipeline:
+    """Keeps the all-gather of the log-likelihoods off the critical path of a stream of batches.
+
+    The collective of batch k runs on a side stream while the kernel of batch k+1 already runs on the compute stream
+    (``depth`` local / gathered buffer pairs, reused round-robin).  Per batch:
+
+        buf = pipe.local_buffer()      # (B_local,) tensor the kernel writes; waits, on the compute stream, for the
+                                       # collective that last read this buffer
+        ... launch the log-likelihood kernel into buf on the current stream ...
+        slot = pipe.submit()           # enqueue the all-gather of buf behind the kernel, on the side stream
+        ...
+        full = pipe.result(slot)       # (world * B_local,) in rank order; the current stream waits for the collective
+
+    Without an initialised process group (or world size 1) no collective is issued and ``result`` returns the local
+    buffer.  Equal shard sizes only (pad with :func:`all_gather_loglik` otherwise).
+    """
+
+    def __init__(self, B_local, device, dtype=torch.float64, group=None, depth=2, collective=True):
+        self.group = group
+        self.world = (dist.get_world_size(group)
+                      if (collective and dist.is_available() and dist.is_initialized()) else 1)
+        self.depth, self.k = depth, 0
+        self.local = [torch.zeros(B_local, dtype=dtype, device=device) for _ in range(depth)]
+        self.cuda = torch.device(device).type == "cuda"
+        if self.world > 1:
+            self.gathered = [torch.empty(self.world * B_local, dtype=dtype, device=device) for _ in range(depth)]
+            if self.cuda:
+                self.comm = torch.cuda.Stream(device=device)
+                self.ready = [torch.cuda.Event() for _ in range(depth)]
+                self.done = [torch.cuda.Event() for _ in range(depth)]
+                self.pending = [False] * depth
+
+    def local_buffer(self):
+        slot = self.k % self.depth
+        if self.world > 1 and self.cuda and self.pending[slot]:
+            torch.cuda.current_stream().wait_event(self.done[slot])      # its previous gather has read it
+        return self.local[slot]
+
+    def submit(self):
+        slot = self.k % self.depth
+        self.k += 1
+        if self.world == 1:
+            return slot
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group)
+            return slot
+        self.ready[slot].record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[slot])
+            dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group)
+            self.done[slot].record(self.comm)
+        self.pending[slot] = True
+        return slot
+
+    def result(self, slot):
+        if self.world == 1:
+            return self.local[slot]
+        if self.cuda and self.pending[slot]:
+            torch.cuda.current_stream().wait_event(self.done[slot])
+        return self.gathered[slot]
+
+    def drain(self):
+        """the current stream waits for every collective issued so far"""
+        if self.world > 1 and self.cuda:
+            for slot in range(self.depth):
+                if self.pending[slot]:
+                    torch.cuda.current_stream().wait_event(self.done[slot])
+
+
 def sharded_loglik(loglik_fn, theta, ode_init, group=None):
     """Run ``loglik_fn(theta_shard, ode_init_shard, particle_offset) -> (B_local,) tensor`` on this rank's shard
     and all-gather.  ``loglik_fn`` is typically a closure over ``rodeo_b200.inference.dalton`` / ``fenrir``."""

@@ -36,13 +36,13 @@ def timeit(fn, reps, flush):
     return float(np.median(ts))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="")
-    ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes (debugging)")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+def run(only="", reps=5, scale=1.0, quiet=False):
+    """time the configs named in `only` (comma separated; empty = all float64 ones); returns the list of records"""
+    class A:
+        pass
+    args = A()
+    args.only, args.reps, args.scale = only, reps, scale
+    dev = torch.device("cuda", torch.cuda.current_device())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _lib.load()
     peak = ctypes.c_double(0.0)
@@ -63,7 +63,8 @@ def main():
                 "roofline_frac": max(t_f, t_b) / (ms * 1e-3), "fp64_peak_tflops": peak.value, "hbm_gbs": hbm}
         if extra:
             line.update(extra)
-        print(json.dumps(line), flush=True)
+        if not quiet:
+            print(json.dumps(line), flush=True)
         res.append(line)
 
     want = lambda k: (k in args.only.split(",")) if args.only else not k.endswith("f32")
@@ -122,6 +123,18 @@ def main():
                                  800, chk, prior_pars=(pr["Q"], pr["R"]), theta=th)
         report("C5 FN solve_sim chkrebtii (one GPU's 32,768 of 262,144 particles)", B, 800,
                timeit(f, args.reps, flush), 1035.0, 48.0)
+    del flush
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes (debugging)")
+    args = ap.parse_args()
+    res = run(args.only, args.reps, args.scale)
     out = os.path.join(ROOT, "gpurun_out", "bench_configs.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     json.dump(res, open(out, "w"), indent=1)
