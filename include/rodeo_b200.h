@@ -144,6 +144,37 @@ int rodeo_b200_basic_gather_f64(const RodeoProblem* prob, const double* Xt /* (B
 int rodeo_b200_gauss_obs_loglik_f64(const RodeoProblem* prob, const double* Xt, const int32_t* obs_ind,
                                     const double* obs_data, double noise_sd, double* loglik_out, void* stream);
 
+/* The two calls above fused: one draw of the solution posterior per theta (solve_sim) and, accumulated inside the
+ * backward sweep, loglik[b] = sum_{i,k} log N(obs_data[i, k]; X[b, obs_ind[i], k, 0], noise_sd^2) -- the whole
+ * `logdensity_fn` of the reference's pseudo-marginal MCMC walkthrough (docs/examples/parameter.md:333-354:
+ * rodeo.solve_sim, Xt[obs_ind], Gaussian log-density).  x_out may be NULL: the trajectories are then never written
+ * (BASELINE configs[4]: 262,144 particles x 38 KB per iteration stay on chip).  obs_ind (n_obs) int32 device,
+ * non-decreasing; obs_data (n_obs, n_block) device.  Same workspace as rodeo_b200_solve_sim_f64. */
+int rodeo_b200_solve_sim_loglik_f64(const RodeoProblem* prob, const double* ode_weight, const double* prior_weight,
+                                    const double* prior_var, const double* ode_init, const double* theta,
+                                    const double* z_interr, const double* z_smooth, const int32_t* obs_ind,
+                                    const double* obs_data, double noise_sd, double* loglik_out,
+                                    double* x_out /* (B, N+1, n_block, n_bstate) or NULL */,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Random-walk Metropolis-Hastings bookkeeping for many chains at once (one chain = one theta of the batched kernels):
+ * the proposal and the accept / reject of the reference's pseudo-marginal step (src/rodeo/inference/pseudo_marginal.py:
+ * 175-189 Gaussian proposal, :452-483 rmh_proposal.generate) around its `logdensity_fn`, which is
+ * rodeo_b200_solve_sim_loglik_f64 plus the caller's prior.  position / proposal (n_chains, dim), sigma (dim): device.
+ * key: HOST uint32[2] (the step's PRNG key); z (n_chains, dim) / u (n_chains) optional device arrays of injected
+ * standard normals / uniforms (NULL: Philox streams keyed by (key, chain_offset + chain)).
+ *   propose:  proposal = position + sigma * z
+ *   accept:   log_p = new_logdensity - logdensity (NaN -> -inf); p_accept = min(1, exp(log_p)); accepted = u < p_accept;
+ *             accepted chains take proposal / new_logdensity IN PLACE.
+ */
+int rodeo_b200_rwmh_propose_f64(int64_t n_chains, int dim, const double* position, const double* sigma,
+                                const double* z, const uint32_t* key, int64_t chain_offset, double* proposal,
+                                void* stream);
+int rodeo_b200_rwmh_accept_f64(int64_t n_chains, int dim, double* position, double* logdensity, const double* proposal,
+                               const double* new_logdensity, const double* u, const uint32_t* key, int64_t chain_offset,
+                               int32_t* accepted_out, double* p_accept_out, void* stream);
+
 /* X0[b] = [x0[b], f(x0[b], t, theta[b]), 0, ...]   x0: (B, n_block) device; X0: (B, n_block, n_bstate) device */
 int rodeo_b200_ode_init_pad_f64(const RodeoProblem* prob, double t, const double* theta, const double* x0,
                                 double* X0, void* stream);
@@ -252,6 +283,26 @@ int rodeo_b200_mvn_logpdf_f64(int64_t B, int n, const double* x, const double* m
  * Stands where the reference calls jax.random.multivariate_normal(method='svd' / 'cholesky') (src/rodeo/solve.py:179,
  * 182-186; src/rodeo/interrogate.py:30-34): any factor with A A^T = cov gives the same distribution. */
 int rodeo_b200_psd_factor_f64(int64_t B, int n, const double* cov, double* factor_out, void* stream);
+
+/*
+ * Batched square-root Kalman primitives: rodeo.kalmantv.square_root.{predict, update, forecast, smooth_mv, smooth_sim,
+ * smooth_cond} (src/rodeo/kalmantv/square_root.py:30-385; rodeo.utils.add_sqrt, src/rodeo/utils.py:10-24).  Same
+ * argument order as the rodeo_b200_ktv_* calls, with every variance a lower-triangular factor L (var = L L^T; full
+ * row-major matrices, zero upper triangle) and the extra `var_state` = R^{1/2} the reference's smoothers take.
+ * var_fore is returned as a covariance (square_root.py:343-344).  Only L L^T is comparable across implementations.
+ */
+int rodeo_b200_sqrt_predict_f64(int64_t B, int n_state, const double* mean_state_past, const double* var_state_past,
+                                const double* mean_state, const double* wgt_state, const double* var_state,
+                                double* mean_state_pred, double* var_state_pred, void* stream);
+int rodeo_b200_sqrt_update_f64(int64_t B, int n_state, int n_meas, const double* mean_state_pred,
+                               const double* var_state_pred, const double* x_meas, const double* mean_meas,
+                               const double* wgt_meas, const double* var_meas, double* mean_state_filt,
+                               double* var_state_filt, double* mean_fore, double* var_fore, void* stream);
+int rodeo_b200_sqrt_smooth_f64(int64_t B, int n_state, int mode, const double* x_next, const double* var_next,
+                               const double* mean_state_filt, const double* var_state_filt,
+                               const double* mean_state_pred, const double* var_state_pred, const double* wgt_state,
+                               const double* var_state, double* out_mean, double* out_var, double* out_wgt,
+                               void* stream);
 
 /*
  * MAGI log-density p(U_{0:N}, Z = 0 | theta) of a given trajectory under the block-diagonal Markov prior.

@@ -859,3 +859,30 @@ def fenrir_solve_mv(model, ode_weight, ode_init, t_min, t_max, n_steps, interrog
         ms[:, k + 2], vs[:, k + 2] = smooth_mv(ms[:, k + 1], vs[:, k + 1], bmf[:, k + 2], bvf[:, k + 2],
                                                bmp[:, k + 1], bvp[:, k + 1], A_all[:, k + 1])
     return ms, vs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pseudo-marginal random-walk Metropolis-Hastings, many chains  (reference src/rodeo/inference/pseudo_marginal.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def gauss_obs_loglik(Xt, obs_ind, obs_data, noise_sd):
+    """sum_{i,k} log N(obs_data[i,k]; Xt[:, obs_ind[i], k, 0], noise_sd^2): the `fitz_loglik` of the reference's
+    parameter-inference walkthrough (docs/examples/parameter.md:192-205) applied to Xt[obs_ind]"""
+    ind = np.clip(np.asarray(obs_ind), 0, Xt.shape[1] - 1)
+    d = np.asarray(obs_data)[None] - Xt[..., 0][:, ind]
+    return np.sum(-0.5 * np.log(2 * np.pi) - np.log(noise_sd) - 0.5 * d * d / noise_sd ** 2, axis=(1, 2))
+
+
+def rwmh_step(position, logdensity, logdensity_fn, sigma, z, u):
+    """One RW-MH step for every chain with injected proposal normals z (C, d) and acceptance uniforms u (C,):
+    new_position = position + sigma z (pseudo_marginal.py:175-189, diagonal sigma); proposed log-density from
+    `logdensity_fn(new_position)` (:473); log_p = new - old for the symmetric proposal with NaN -> -inf, p_accept =
+    min(1, exp(log_p)), accept iff u < p_accept (blackjax compute_asymmetric_acceptance_ratio /
+    static_binomial_sampling, as called at :476-479).  Returns (position, logdensity, accepted, p_accept)."""
+    prop = position + np.asarray(sigma) * z
+    new_ld = logdensity_fn(prop)
+    lp = new_ld - logdensity
+    lp = np.where(np.isnan(lp), -np.inf, lp)
+    with np.errstate(over="ignore"):
+        pa = np.minimum(np.exp(lp), 1.0)
+    acc = u < pa
+    return np.where(acc[:, None], prop, position), np.where(acc, new_ld, logdensity), acc, pa

@@ -7,4 +7,4 @@ __version__ = "0.1.0"
 
 from . import interrogate, prior, utils, models, inference, kalmantv  # noqa: F401
 from .prior import ibm_init  # noqa: F401
-from .solve import solve_sim, solve_mv  # noqa: F401
+from .solve import solve_sim, solve_mv, solve_sim_loglik  # noqa: F401

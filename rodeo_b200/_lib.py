@@ -60,6 +60,10 @@ SIGNATURES = {
     "rodeo_b200_fenrir_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),
     "rodeo_b200_basic_gather_f64": (_i, [_P, _vp, _vp, _vp, _vp]),
     "rodeo_b200_gauss_obs_loglik_f64": (_i, [_P, _vp, _vp, _vp, _d, _vp, _vp]),
+    "rodeo_b200_solve_sim_loglik_f64": (_i, [_P] + [_vp] * 9 + [_d, _vp, _vp] + [_vp, _sz, _vp]),
+    "rodeo_b200_rwmh_propose_f64": (_i, [ctypes.c_int64, _i, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp, _vp]),
+    "rodeo_b200_rwmh_accept_f64": (_i, [ctypes.c_int64, _i, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp, _vp,
+                                        _vp]),
     "rodeo_b200_ode_init_pad_f64": (_i, [_P, _d, _vp, _vp, _vp, _vp]),
     "rodeo_b200_solve_mv_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_solve_sim_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
@@ -78,6 +82,9 @@ SIGNATURES = {
     "rodeo_b200_ktv_update_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
     "rodeo_b200_ktv_smooth_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
     "rodeo_b200_mvn_logpdf_f64": (_i, [ctypes.c_int64, _i] + [_vp] * 4 + [_vp]),
+    "rodeo_b200_sqrt_predict_f64": (_i, [ctypes.c_int64, _i] + [_vp] * 7 + [_vp]),
+    "rodeo_b200_sqrt_update_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 10 + [_vp]),
+    "rodeo_b200_sqrt_smooth_f64": (_i, [ctypes.c_int64, _i, _i] + [_vp] * 11 + [_vp]),
     "rodeo_b200_psd_factor_f64": (_i, [ctypes.c_int64, _i, _vp, _vp, _vp]),
     "rodeo_b200_magi_logdens_f64": (_i, [ctypes.c_int64, _i, _i, _i, _i] + [_vp] * 4 + [_vp]),
     "rodeo_b200_dalton_f64_host": (_i, [_P] + [_vp] * 10),

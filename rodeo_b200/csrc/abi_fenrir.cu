@@ -1,4 +1,6 @@
 // rodeo_b200_fenrir_f64: batched rodeo.inference.fenrir (reference src/rodeo/inference/fenrir.py:86-328).
+#include <cstdlib>
+
 #include "rodeo_host.h"
 
 #ifndef RODEO_REAL
@@ -24,10 +26,25 @@ struct FenrirRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    constexpr int SMEM = 2 * SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;      // double-buffered history
-    RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_kernel<real_t, Model, INTERR, QK, 1>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    fenrir_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, o, stash, stash_ldb(p.B), out);
+    bool ws = sizeof(real_t) == 8;                         // warp-specialised backward sweep (rodeo_kernels.cuh)
+    if (const char* e = getenv("RODEO_FENRIR_WS")) ws = ws && e[0] == '1';      // tuning / tests
+    if constexpr (sizeof(real_t) == 8) {
+      if (ws) {
+        constexpr int NSP = Model::P * (Model::P + 1) / 2;
+        constexpr int SMEM_WS = 2 * RODEO_FENRIR_NP * Model::NB * (Model::P * Model::P + 2 * Model::P + NSP) * 32 *
+                                (int)sizeof(real_t);
+        RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_ws_kernel<real_t, Model, INTERR, QK, 1>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WS));
+        fenrir_ws_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32 * (1 + RODEO_FENRIR_NP), SMEM_WS, s>>>(C, a, o, stash,
+                                                                                               stash_ldb(p.B), out);
+      }
+    }
+    if (!ws) {
+      constexpr int SMEM = 2 * SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;      // double-buffered history
+      RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_kernel<real_t, Model, INTERR, QK, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      fenrir_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, o, stash, stash_ldb(p.B), out);
+    }
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
     return RODEO_OK;

@@ -7,6 +7,7 @@
 #ifndef RODEO_REAL
 #define RODEO_REAL double
 #define RODEO_SUFFIX _f64
+#define RODEO_SOLVE_SIM_LOGLIK
 #endif
 #define RODEO_CAT2(a, b) a##b
 #define RODEO_CAT(a, b) RODEO_CAT2(a, b)
@@ -19,7 +20,8 @@ namespace host {
 template <class Model, int INTERR, int QK>
 struct SolveSimRun {
   static int run(const RodeoProblem& p, const real_t* W, const real_t* Q, const real_t* R,
-                 const CommonArgs<real_t>& a, const real_t* z_smooth, real_t* stash, real_t* x_out, cudaStream_t s) {
+                 const CommonArgs<real_t>& a, const real_t* z_smooth, real_t* stash, real_t* x_out,
+                 const SimLoglik<real_t>& sl, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
@@ -44,14 +46,14 @@ struct SolveSimRun {
       typedef BlockLane<real_t, Model, INTERR, QK> L;
       constexpr int SMEM = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
       solve_sim_bl_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, L::TW), 32, SMEM, s>>>(
-          C, a, z_smooth, stash, stash_ldb(p.B), x_out);
+          C, a, z_smooth, stash, stash_ldb(p.B), x_out, ObsHook<real_t>(), sl);
     }
     if (!block_lanes) {
       constexpr int SMEM = SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
       RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_kernel<real_t, Model, INTERR, QK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-      solve_sim_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(C, a, z_smooth, stash,
-                                                                                  stash_ldb(p.B), x_out);
+      solve_sim_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, 32), 32, SMEM, s>>>(
+          C, a, z_smooth, stash, stash_ldb(p.B), x_out, ObsHook<real_t>(), sl);
     }
     g_launches++;
     RODEO_CUDA_OK(cudaGetLastError());
@@ -74,10 +76,10 @@ static int check_ws(int op, const RodeoProblem* p, void* ws, size_t ws_bytes) {
   return RODEO_OK;
 }
 
-extern "C" int RODEO_FN(rodeo_b200_solve_sim)(const RodeoProblem* p, const real_t* ode_weight, const real_t* prior_weight,
-                                        const real_t* prior_var, const real_t* ode_init, const real_t* theta,
-                                        const real_t* z_interr, const real_t* z_smooth, real_t* x_out,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
+static int solve_sim_impl(const RodeoProblem* p, const real_t* ode_weight, const real_t* prior_weight,
+                          const real_t* prior_var, const real_t* ode_init, const real_t* theta, const real_t* z_interr,
+                          const real_t* z_smooth, real_t* x_out, const SimLoglik<real_t>& sl, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   if (int rc = check_common(p)) return rc;
   if (int rc = check_ws(RODEO_OP_SOLVE_SIM, p, workspace, workspace_bytes)) return rc;
   CommonArgs<real_t> a = make_common<real_t>(*p, ode_init, theta, z_interr);
@@ -85,11 +87,38 @@ extern "C" int RODEO_FN(rodeo_b200_solve_sim)(const RodeoProblem* p, const real_
     if (sizeof(real_t) != 8) { set_error("user (NVRTC) models are float64 only"); return RODEO_ERR_UNSUPPORTED; }
     real_t* stash = (real_t*)workspace;
     long long ldb = stash_ldb(p->B);
-    ObsHook<real_t> no_obs{};        // trailing kernel parameter of the solver kernels (unused: OBS = false)
+    ObsHook<real_t> no_obs{};        // trailing kernel parameters of the solver kernels (OBS = false)
+    SimLoglik<real_t> slv = sl;
     const int smem = seg_len(nstate_of(p->n_block, p->n_bstate)) * nstate_of(p->n_block, p->n_bstate) * SEG_PITCH * (int)sizeof(real_t);
     return user_launch(*p, "solve_sim_kernel", "", (const double*)ode_weight, (const double*)prior_weight, (const double*)prior_var, p->user_wcol, p->B, smem,
-                       {&a, &z_smooth, &stash, &ldb, &x_out, &no_obs}, (cudaStream_t)stream);
+                       {&a, &z_smooth, &stash, &ldb, &x_out, &no_obs, &slv}, (cudaStream_t)stream);
   }
   return dispatch_model<SolveSimRun>(*p, ode_weight, prior_weight, *p, ode_weight, prior_weight, prior_var, a, z_smooth,
-                                     (real_t*)workspace, x_out, (cudaStream_t)stream);
+                                     (real_t*)workspace, x_out, sl, (cudaStream_t)stream);
 }
+
+extern "C" int RODEO_FN(rodeo_b200_solve_sim)(const RodeoProblem* p, const real_t* ode_weight, const real_t* prior_weight,
+                                        const real_t* prior_var, const real_t* ode_init, const real_t* theta,
+                                        const real_t* z_interr, const real_t* z_smooth, real_t* x_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  return solve_sim_impl(p, ode_weight, prior_weight, prior_var, ode_init, theta, z_interr, z_smooth, x_out,
+                        SimLoglik<real_t>(), workspace, workspace_bytes, stream);
+}
+
+#ifdef RODEO_SOLVE_SIM_LOGLIK     /* float64 translation unit only */
+extern "C" int rodeo_b200_solve_sim_loglik_f64(const RodeoProblem* p, const double* ode_weight,
+                                               const double* prior_weight, const double* prior_var,
+                                               const double* ode_init, const double* theta, const double* z_interr,
+                                               const double* z_smooth, const int32_t* obs_ind, const double* obs_data,
+                                               double noise_sd, double* loglik_out, double* x_out, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  if (!p || p->n_obs < 1 || !(noise_sd > 0.0) || !loglik_out) {
+    set_error("solve_sim_loglik needs n_obs >= 1, noise_sd > 0 and an output buffer");
+    return RODEO_ERR_INVALID;
+  }
+  SimLoglik<double> sl;
+  sl.obs_ind = obs_ind; sl.obs_data = obs_data; sl.n_obs = p->n_obs; sl.noise_sd = noise_sd; sl.out = loglik_out;
+  return solve_sim_impl(p, ode_weight, prior_weight, prior_var, ode_init, theta, z_interr, z_smooth, x_out, sl, workspace,
+                        workspace_bytes, stream);
+}
+#endif

@@ -60,6 +60,45 @@ struct ObsHook {
   const int* step_obs;   // (n_steps) or nullptr
 };
 
+// Fused Gaussian observation log-likelihood of a solve_sim draw (the inner call of a pseudo-marginal MCMC step,
+// reference docs/examples/parameter.md:333-354: solve_sim, then sum_i,k log N(obs_data[i, k]; Xt[obs_ind[i], k, 0], sd^2)):
+// accumulated while the backward sweep produces the draw, so that Xt need not be written at all (x_out == nullptr).
+// obs_ind must be non-decreasing (searchsorted of sorted observation times); out-of-range indices clamp like the
+// reference's traced gather.
+template <typename T>
+struct SimLoglik {
+  const int* obs_ind;     // (n_obs)
+  const T* obs_data;      // (n_obs, NB)
+  int n_obs;
+  T noise_sd;
+  T* out;                 // (B) or nullptr: no log-likelihood
+};
+// walks the observations backwards in time alongside the sweep
+template <typename T, typename MT>
+struct SimLoglikAcc {
+  MT ll, rvar, cst;
+  int oi, next_t, n_rows;
+  RD_DEV void init(const SimLoglik<T>& sl, int n_rows_) {
+    ll = MT(0); n_rows = n_rows_; oi = sl.out != nullptr ? sl.n_obs - 1 : -1;
+    rvar = MT(1) / ((MT)sl.noise_sd * (MT)sl.noise_sd);
+    cst = MT(-0.5) * MT(1.8378770664093454836) - log((MT)sl.noise_sd);
+    next_t = oi >= 0 ? clampi(__ldg(sl.obs_ind + oi)) : -1;
+  }
+  RD_DEV int clampi(int r) const { return r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r); }
+  // row t of the draw is known: xv(b) returns x_t[b][0]; blocks b0 .. b1-1 are this thread's
+  template <class XV>
+  RD_DEV void row(const SimLoglik<T>& sl, int t, int nb, int b0, int b1, XV xv) {
+    while (next_t == t) {
+      for (int b = b0; b < b1; ++b) {
+        const MT d = (MT)__ldg(sl.obs_data + oi * nb + b) - xv(b);
+        ll += cst - MT(0.5) * d * d * rvar;
+      }
+      --oi;
+      next_t = oi >= 0 ? clampi(__ldg(sl.obs_ind + oi)) : -1;
+    }
+  }
+};
+
 // step_obs[n] = i if the reference's scan (dalton.py:313-350) applies observation i at step n (t+1 == obs_ind[i],
 // i clamped, starting at 1 when obs_ind[0] == 0), else -1
 template <int UNUSED = 0>
@@ -656,12 +695,13 @@ RD_DEV void ckpt_prefetch(const T* __restrict__ stash, i64 ldb, i64 idx, int j) 
 template <typename T, class Model, int INTERR, int QK>
 RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
                          const typename Fwd<T, Model, INTERR, QK>::Par& q, i64 idx, int n,
-                         Fwd<T, Model, INTERR, QK>& f, const ObsHook<T>* hook = nullptr) {
+                         Fwd<T, Model, INTERR, QK>& f, const ObsHook<T>* hook = nullptr,
+                         const typename Fwd<T, Model, INTERR, QK>::MT* t_given = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
   typedef typename F::MT MT;
   constexpr int NB = F::NB, M = F::M, JC = F::JC, MS = F::MS;
   LogPdfAcc<T> dummy;
-  const MT t = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, n, a.n_steps) : MT(0);
+  const MT t = Model::USES_TIME ? (t_given != nullptr ? *t_given : step_time<MT>(a.t_min, a.t_max, n, a.n_steps)) : MT(0);
   T jl[NB][M][JC], V[NB][MS], zc[NB][JC];
   MT res[NB][M];
   f.predict_all(C);
@@ -681,9 +721,14 @@ RD_DEV void forward_with_checkpoints(const FilterConsts<T, Model::NB, Model::P, 
                                      Fwd<T, Model, INTERR, QK>& f, T* __restrict__ stash, i64 ldb,
                                      const ObsHook<T>* hook = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
+  typedef typename F::MT MT;
   int to_ckpt = KC, j = 0;
+  // the time stamp of step n+1 (an IEEE division, solve.py:74) is formed while step n runs, off its dependency chain
+  MT t_next = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, 0, a.n_steps) : MT(0);
   for (int n = 0; n < a.n_steps; ++n) {
-    forward_step<T, Model, INTERR, QK>(C, a, q, idx, n, f, hook);
+    const MT t_now = t_next;
+    if (Model::USES_TIME) t_next = step_time<MT>(a.t_min, a.t_max, n + 1, a.n_steps);
+    forward_step<T, Model, INTERR, QK>(C, a, q, idx, n, f, hook, &t_now);
     if (--to_ckpt == 0) {
       to_ckpt = KC;
       ++j;
@@ -1423,7 +1468,8 @@ template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32, RODEO_SIM_BL_MINB)
 solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                     const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
-                    T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>()) {
+                    T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>(),
+                    const SimLoglik<T> sl = SimLoglik<T>()) {
   const ObsHook<T>* hook = OBS ? &oh : nullptr;
   typedef BlockLane<T, Model, INTERR, QK> L;
   constexpr int NB = L::NB, P = L::P, NS = L::NS, TW = L::TW, NSTATE = L::NSTATE, PITCH = L::PITCH;
@@ -1477,13 +1523,17 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
 
   // terminal draw from N(mu_f[N], S_f[N])  (solve.py:182-186)
   MT x[P];
+  SimLoglikAcc<T, MT> la;
+  la.init(sl, N + 1);
   {
     T z[P];
     MT xn[P];
     normals(N, z);
     draw(f.mu, f.S, z, xn);
     RD_UNROLL for (int i = 0; i < P; ++i) x[i] = xn[i];
-    if (live) RD_UNROLL for (int i = 0; i < P; ++i) x_out[(idx * (i64)(N + 1) + N) * ROW + b * P + i] = (T)x[i];
+    if (live && x_out != nullptr)
+      RD_UNROLL for (int i = 0; i < P; ++i) x_out[(idx * (i64)(N + 1) + N) * ROW + b * P + i] = (T)x[i];
+    la.row(sl, N, NB, b, b + 1, [&](int) { return x[0]; });
   }
 
   const int nth = (a.B - theta0) < TW ? (int)(a.B - theta0) : TW;
@@ -1502,7 +1552,9 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
     for (int s = cnt - 1; s >= 0; --s) {
       const int n = n0 + s;
       if (n == 0) {                                        // row 0 = ode_init: x0 is known, not sampled
-        RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * ROW + b * P + i) * PITCH + tl] = x0[b * P + i];
+        if (x_out != nullptr)
+          RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * ROW + b * P + i) * PITCH + tl] = x0[b * P + i];
+        la.row(sl, 0, NB, b, b + 1, [&](int) { return (MT)x0[b * P]; });
         break;
       }
       RD_UNROLL for (int i = 0; i < P; ++i) f.mu[i] = (MT)nmu[i];
@@ -1523,10 +1575,13 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
       }
       cond_var<T, P>(f.S, G, Ct, Cv);
       draw(m, Cv, z, xn);
-      RD_UNROLL for (int i = 0; i < P; ++i) { x[i] = xn[i]; buf[(s * ROW + b * P + i) * PITCH + tl] = (T)xn[i]; }
+      RD_UNROLL for (int i = 0; i < P; ++i) x[i] = xn[i];
+      if (x_out != nullptr)
+        RD_UNROLL for (int i = 0; i < P; ++i) buf[(s * ROW + b * P + i) * PITCH + tl] = (T)xn[i];
+      la.row(sl, n, NB, b, b + 1, [&](int) { return x[0]; });
     }
-    __syncwarp();
-    {
+    if (x_out != nullptr) {
+      __syncwarp();
       // copy rows n0 .. n0+cnt-1: per theta one contiguous run of cnt*ROW elements
       constexpr int NIT = (K * ROW + 31) / 32;
       const int run = cnt * ROW;
@@ -1539,8 +1594,14 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
         }
         dst += stride;
       }
+      __syncwarp();
     }
-    __syncwarp();
+  }
+  if (sl.out != nullptr) {
+    // sum the blocks of a theta in block order (lane c * TW + tl holds block c)
+    MT tot = MT(0);
+    RD_UNROLL for (int c = 0; c < NB; ++c) tot += __shfl_sync(0xffffffffu, la.ll, c * TW + tl);
+    if (live && b == 0 && lane < TW) sl.out[idx] = (T)tot;
   }
 }
 
@@ -1562,7 +1623,7 @@ template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32, Model::NB <= 3 ? RODEO_SIM_T_MINB : 1)
 solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                  const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
-                 T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>()) {
+                 T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>(), const SimLoglik<T> sl = SimLoglik<T>()) {
   const ObsHook<T>* hook = OBS ? &oh : nullptr;
   typedef Fwd<T, Model, INTERR, QK> F;
   typedef SegBuf<T, F> Buf;
@@ -1616,15 +1677,26 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
     RD_UNROLL for (int b = 0; b < NB; ++b) draw(b, f.mu[b], f.S[b], z, xn);
     RD_UNROLL for (int b = 0; b < NB; ++b)
       RD_UNROLL for (int i = 0; i < P; ++i) x[b][i] = xn[b][i];
-    if (live) store_mean_row<T, NB, P>(x_out + (idx * (i64)(N + 1) + N) * (NB * P), x);
+    if (live && x_out != nullptr) store_mean_row<T, NB, P>(x_out + (idx * (i64)(N + 1) + N) * (NB * P), x);
   }
+  SimLoglikAcc<T, MT> la;
+  la.init(sl, N + 1);
+  auto x_of = [&](int bb) {                                // x_t[bb][0] with bb a run-time block index
+    MT v = x[0][0];
+    RD_UNROLL for (int c = 1; c < NB; ++c) v = bb == c ? x[c][0] : v;
+    return v;
+  };
+  la.row(sl, N, NB, 0, NB, x_of);
 
   for (int j = (N - 1) / K; j >= 0; --j) {
     const int n0 = j * K;
     const int cnt = (N - n0) < K ? (N - n0) : K;
     rebuild_segment<T, Model, INTERR, QK, KC>(C, a, q, idx, j, cnt, f, stash, ldb, buf, hook);
     for (int s = cnt - 1; s >= 0; --s) {
-      if (n0 + s == 0) break;                              // row 0 = ode_init: x0 is known, not sampled (solve.py:202-204)
+      if (n0 + s == 0) {                                   // row 0 = ode_init: x0 is known, not sampled (solve.py:202-204)
+        la.row(sl, 0, NB, 0, NB, [&](int bb) { return (MT)a.ode_init[idx * NB * P + bb * P]; });
+        break;
+      }
       buf.get(s, f.mu, f.S);                               // filt[n]
       T z[NB * P];
       normals(n0 + s, z);
@@ -1645,12 +1717,14 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
       }
       RD_UNROLL for (int b = 0; b < NB; ++b)
         RD_UNROLL for (int i = 0; i < P; ++i) { x[b][i] = xn[b][i]; buf.at(s, b * P + i) = (T)xn[b][i]; }
+      la.row(sl, n0 + s, NB, 0, NB, x_of);
     }
     if (j > 0) prefetch_segment<T, F, KC>(stash, ldb, idx, j - 1, K);
     __syncwarp();
-    buf.template copy_out<false>(x_out, theta0, a.B, N + 1, n0, cnt);
+    if (x_out != nullptr) buf.template copy_out<false>(x_out, theta0, a.B, N + 1, n0, cnt);
     __syncwarp();
   }
+  if (sl.out != nullptr && live) sl.out[idx] = (T)la.ll;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1743,6 +1817,166 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   if (live) loglik[idx] = (T)acc.value();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// fenrir, warp-specialised backward sweep
+// ------------------------------------------------------------------------------------------------------------------
+// BASELINE configs[3] (p = 4, 16,384 thetas = 512 warps for 592 SM sub-partitions) runs fenrir_kernel as ONE warp per
+// sub-partition: its time is the serial chain of a theta.  ncu (profiles/r02_fenrir_before_ncu.txt): a backward step
+// issues ~300 FP64 instructions (2 cycles each) behind a 4-pivot LDL^T whose reciprocals depend on one another, and 23 %
+// of the samples sit in the history fetch.  But only a small part of a backward step is sequential in t: the parameters
+// of the backward Markov chain  X_t = A_t X_{t+1} + b_t + N(0, C_t)  (smooth_cond, standard.py:366-370) depend on
+// filt[t] alone, which the forward sweep has already written.  So the CTA is three warps over the same 32 thetas:
+//   warp 0      forward filter (history to HBM), then the CONSUMER of the backward sweep: predicts the backward filter
+//               through (A_t, b_t, C_t), applies the observations, accumulates the log-density (fenrir.py:151-179);
+//   warps 1..NP PRODUCERS: producer p takes the steps t = N-1-p, N-1-p-NP, ...: load filt[t] (two of its steps ahead),
+//               predict, LDL^T gain, conditional variance -> (A_t, mu_f, mu_p, C_t) into a 2 NP-slot shared-memory ring.
+// Hand-over by named barriers (bar.arrive / bar.sync with 64 participants: one producer warp + the consumer), the
+// producer / consumer pattern of the PTX manual.  NP = 3: measured on BASELINE configs[3], a produced step costs ~1,750
+// cycles (476 issue cycles + history latency + FP64-pipe contention with the neighbouring warps) against ~300 for the
+// consumer's.  The arithmetic is the same __device__ functions in the same order as
+// fenrir_kernel: the log-likelihoods are bitwise identical.
+#ifndef RODEO_FENRIR_NP
+#define RODEO_FENRIR_NP 3
+#endif
+template <typename T, class Model, int INTERR, int QK, int NOBS>
+__global__ void __launch_bounds__(32 * (1 + RODEO_FENRIR_NP))
+fenrir_ws_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                 const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ stash, i64 ldb,
+                 T* __restrict__ loglik) {
+  typedef Fwd<T, Model, INTERR, QK> F;
+  typedef typename F::MT MT;
+  constexpr int NB = F::NB, P = F::P, NS = F::NS, NSTATE = NB * (P + NS);
+  static_assert(sizeof(T) == 8, "the ring stages the means as T: float64 only");
+  constexpr int NCH = NB * (P * P + P + NS);             // per theta and step in the ring: A_t, mu_f, C_t per block ...
+  constexpr int NP = RODEO_FENRIR_NP, RING = 2 * NP;     // ... followed by a second region with mu_p: RING * NB * P
+  static_assert(2 * RING + 1 <= 16, "named barriers");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  i64 idx = (i64)blockIdx.x * 32 + lane;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;
+  const int N = a.n_steps;
+  T* ring = reinterpret_cast<T*>(rodeo_dyn_smem);        // [slot][k][lane]
+  auto slot_of = [&](int t) { return (N - 1 - t) % RING; };
+  auto bar_sync = [](int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); };
+  auto bar_arrive = [](int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); };
+  // barrier ids: 1 + slot = "slot is full", 1 + RING + slot = "slot is empty"
+
+  F f;
+  F bk;                                                   // backward-filter state (consumer)
+  f.load_scale(a, idx);
+  if (warp == 0) {
+    const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
+    f.init(a.ode_init + idx * NB * P);
+    forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      RD_UNROLL for (int i = 0; i < P; ++i) bk.mu[b][i] = f.mu[b][i];
+      RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = f.S[b][k];
+    }
+  }
+  __syncthreads();                                        // the history of this CTA's thetas is complete and visible
+
+  if (warp > 0) {
+    // ---- producers
+    const int pid = warp - 1;
+    auto load_filt = [&](int t, MT (&mu)[NB][P], T (&S)[NB][NS]) {
+      if (t >= 1) {
+        const T* s = stash + (i64)(t - 1) * NSTATE * ldb + idx;
+        RD_UNROLL for (int b = 0; b < NB; ++b) {
+          RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = (MT)s[(i64)(b * P + i) * ldb];
+          RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = s[(i64)(NB * P + b * NS + k) * ldb];
+        }
+      } else {                                            // filt[0] = (ode_init, 0)
+        RD_UNROLL for (int b = 0; b < NB; ++b) {
+          RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = (MT)a.ode_init[idx * NB * P + b * P + i];
+          RD_UNROLL for (int k = 0; k < NS; ++k) S[b][k] = T(0);
+        }
+      }
+    };
+    // software pipeline over this producer's steps: two loads in flight ahead of the step being computed
+    MT nmu[2][NB][P];
+    T nS[2][NB][NS];
+    int t = N - 1 - pid;
+    if (t >= 0) load_filt(t, nmu[0], nS[0]);
+    if (t - NP >= 0) load_filt(t - NP, nmu[1], nS[1]);
+    int produced = 0;
+    for (; t >= 0; t -= NP) {
+      const int cur = produced & 1;
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        RD_UNROLL for (int i = 0; i < P; ++i) f.mu[b][i] = cur ? nmu[1][b][i] : nmu[0][b][i];
+        RD_UNROLL for (int k = 0; k < NS; ++k) f.S[b][k] = cur ? nS[1][b][k] : nS[0][b][k];
+      }
+      if (t - 2 * NP >= 0) {                               // refill the buffer just consumed
+        if (cur) load_filt(t - 2 * NP, nmu[1], nS[1]);
+        else load_filt(t - 2 * NP, nmu[0], nS[0]);
+      }
+      const int slot = slot_of(t);
+      if (produced >= 2) bar_sync(1 + RING + slot);        // the consumer has released this slot (each producer owns 2)
+      ++produced;
+      T* r = ring + (i64)slot * NCH * 32 + lane;
+      RD_UNROLL for (int b = 0; b < NB; ++b) {
+        MT mp[P];
+        T Sp[NS], G[P][P], Ct[P][P], Cv[NS];
+        predict<T, P, QK>(C.Q[b], C.R[b], f.rs[b], f.mu[b], f.S[b], mp, Sp);          // pred[t+1]
+        smooth_gain<T, P, QK>(C.Q[b], f.S[b], Sp, G, Ct);
+        cond_var<T, P>(f.S[b], G, Ct, Cv);
+        T* rb = r + (i64)b * (P * P + P + NS) * 32;
+        RD_UNROLL for (int i = 0; i < P; ++i)
+          RD_UNROLL for (int j = 0; j < P; ++j) rb[(i * P + j) * 32] = G[i][j];
+        // the consumer forms mu_f + G (m - mu_p) exactly as fenrir_kernel does: it gets mu_f and mu_p rather than b_t
+        RD_UNROLL for (int i = 0; i < P; ++i) rb[(P * P + i) * 32] = (T)f.mu[b][i];
+        RD_UNROLL for (int k = 0; k < NS; ++k) rb[(P * P + P + k) * 32] = Cv[k];
+        T* rp = ring + (i64)RING * NCH * 32 + ((i64)slot * NB * P + b * P) * 32 + lane;
+        RD_UNROLL for (int i = 0; i < P; ++i) rp[i * 32] = (T)mp[i];
+      }
+      bar_arrive(1 + slot);
+    }
+    return;
+  }
+
+  // ---- consumer
+  LogPdfAcc<T> acc;
+  acc.init();
+  int i = o.n_obs - 1;
+  auto obs_at = [&](int k) { return __ldg(o.obs_ind + (k < 0 ? k + o.n_obs : k)); };
+  if (obs_at(i) >= N) {                                   // terminal point update (fenrir.py:196-220)
+    bk.template update_y<NOBS>(o, i, acc);
+    --i;
+  }
+  int next_obs = obs_at(i);
+  for (int t = N - 1; t >= 0; --t) {
+    const int slot = slot_of(t);
+    bar_sync(1 + slot);
+    const T* r = ring + (i64)slot * NCH * 32 + lane;
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      const T* rb = r + (i64)b * (P * P + P + NS) * 32;
+      const T* rp = ring + (i64)RING * NCH * 32 + ((i64)slot * NB * P + b * P) * 32 + lane;
+      T G[P][P], Cv[NS];
+      MT mf[P], mp[P], nm[P];
+      RD_UNROLL for (int ii = 0; ii < P; ++ii)
+        RD_UNROLL for (int j = 0; j < P; ++j) G[ii][j] = rb[(ii * P + j) * 32];
+      RD_UNROLL for (int ii = 0; ii < P; ++ii) { mf[ii] = (MT)rb[(P * P + ii) * 32]; mp[ii] = (MT)rp[ii * 32]; }
+      RD_UNROLL for (int k = 0; k < NS; ++k) Cv[k] = rb[(P * P + P + k) * 32];
+      // predict the backward filter through the chain (fenrir.py:151-157): same expressions as fenrir_kernel
+      RD_UNROLL for (int rr = 0; rr < P; ++rr) {
+        MT acc2 = mf[rr];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) acc2 = rd_fma((MT)G[rr][jj], bk.mu[b][jj] - mp[jj], acc2);
+        nm[rr] = acc2;
+      }
+      add_GDGt<T, P>(G, bk.S[b], Cv);
+      RD_UNROLL for (int rr = 0; rr < P; ++rr) bk.mu[b][rr] = nm[rr];
+      RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = Cv[k];
+    }
+    bar_arrive(1 + RING + slot);                          // the slot may be refilled
+    if (next_obs == t) {
+      bk.template update_y<NOBS>(o, i < 0 ? i + o.n_obs : i, acc);
+      --i;
+      next_obs = obs_at(i);
+    }
+    acc.ld.renorm();
+  }
+  if (live) loglik[idx] = (T)acc.value();
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // fenrir.solve_mv: posterior mean / variance p(X_{0:N} | Z_{1:N}, Y_{0:M}) by the Fenrir construction

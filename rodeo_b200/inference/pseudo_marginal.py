@@ -38,55 +38,71 @@ class SamplingAlgorithm(NamedTuple):
     step: Callable
 
 
-def _generator(key):
-    k0, k1 = _host.parse_key(key)
-    g = torch.Generator(device=_host.device())
-    g.manual_seed(((k0 << 32) | k1) & 0x7FFFFFFFFFFFFFFF)
-    return g
-
-
 def init(position, logdensity_fn, rng_key):
     """reference src/rodeo/inference/pseudo_marginal.py:135-149"""
-    position = _host.to_dev(position)
+    position = _host.to_dev(position).clone()
     logdensity, auxdata = logdensity_fn(position, rng_key)
-    return RWAState(position, logdensity, auxdata)
+    return RWAState(position, logdensity.contiguous(), auxdata)
+
+
+def _split3(rng_key):
+    """three independent sub-keys (proposal, accept, log-density) of the step's key -- the role of
+    jax.random.split(rng_key, 3) at reference :470 (not bit-compatible with threefry)"""
+    k0, k1 = _host.parse_key(rng_key)
+    mix = lambda a, b: ((k0 ^ a) & 0xFFFFFFFF, (k1 * 0x9E3779B1 + b) & 0xFFFFFFFF)
+    return mix(0x243F6A88, 1), mix(0x85A308D3, 2), mix(0x13198A2E, 3)
 
 
 def normal_random_walk(logdensity_fn, sigma):
     """RW-MH with a Gaussian proposal N(position, diag(sigma^2)) -- reference :175-189, :332-379, :452-483.
 
-    ``logdensity_fn(position (C, d) CUDA tensor, key) -> (logdensity (C,), auxdata)``; ``auxdata`` may be a tensor with
-    a leading chain axis (it is carried per chain through accept/reject) or ``None``.
+    ``logdensity_fn(position (C, d) CUDA tensor, key) -> (logdensity (C,), auxdata)``: typically
+    ``rodeo_b200.solve_sim_loglik`` plus a log-prior, i.e. ONE fused kernel and no trajectories (``auxdata = None``).
+    If it does return a tensor with a leading chain axis (e.g. the draws), only the ACCEPTED chains' rows are copied
+    into the carried tensor (an indexed row copy; rejected rows are not touched).
+
     ``step(rng_key, state) -> (new_state, RWAInfo)``; ``rng_key`` is a uint32[2] key or an int (one per iteration,
-    like the reference's ``jax.random.split`` keys).
+    like the reference's ``jax.random.split`` keys).  Proposal and accept / reject are two small kernels
+    (``rodeo_b200_rwmh_propose_f64`` / ``_accept_f64``); nothing returns to the host inside ``step``.  The state's
+    ``position`` / ``logdensity`` (and ``auxdata``) buffers are updated IN PLACE and handed on to the new state.
+    ``_z`` (C, d) / ``_u`` (C,) inject the proposal normals and the acceptance uniforms (testing hook).
     """
     sig = None
+    lib = _lib.load()
 
     def init_fn(position, rng_key=None):
         return init(position, logdensity_fn, rng_key)
 
-    def step_fn(rng_key, state):
+    def step_fn(rng_key, state, _z=None, _u=None):
         nonlocal sig
         pos, logd, aux = state
+        C, d = pos.shape
         if sig is None:
-            sig = _host.to_dev(sigma, pos.dtype)
-        g = _generator(rng_key)
-        # key_proposal / key_accept / key_logdensity of the reference (:470): three independent streams
-        prop = pos + sig * torch.randn(pos.shape, dtype=pos.dtype, device=pos.device, generator=g)
-        logu = torch.log(torch.rand(pos.shape[0], dtype=pos.dtype, device=pos.device, generator=g))
-        k0, k1 = _host.parse_key(rng_key)
-        new_logd, new_aux = logdensity_fn(prop, (k0 ^ 0x9E3779B9, k1 ^ 0x85EBCA6B))
-        log_p = new_logd - logd                                  # symmetric proposal (:438-443)
-        log_p = torch.where(torch.isnan(log_p), torch.full_like(log_p, -float("inf")), log_p)
-        acc = logu < log_p
-        new_pos = torch.where(acc[:, None], prop, pos)
-        out_logd = torch.where(acc, new_logd, logd)
-        if aux is None or new_aux is None:
-            out_aux = new_aux
-        else:
-            out_aux = torch.where(acc.view((-1,) + (1,) * (new_aux.dim() - 1)), new_aux, aux)
-        p_accept = torch.clamp(torch.exp(log_p), max=1.0)
-        return RWAState(new_pos, out_logd, out_aux), RWAInfo(p_accept, acc, RWAState(prop, new_logd, new_aux))
+            sig = _host.to_dev(torch.as_tensor(sigma, dtype=torch.float64).expand(d).contiguous())
+        kp, ka, kl = _split3(rng_key)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        prop = torch.empty_like(pos)
+        z = None if _z is None else _host.to_dev(_z)
+        kbuf = (ctypes.c_uint32 * 2)(*kp)
+        _lib.check(lib.rodeo_b200_rwmh_propose_f64(C, d, _host.ptr(pos), _host.ptr(sig), _host.ptr(z), kbuf, 0,
+                                                   _host.ptr(prop), stream), "rwmh_propose")
+        new_logd, new_aux = logdensity_fn(prop, kl)
+        new_logd = new_logd.contiguous()
+        acc = torch.empty(C, dtype=torch.int32, device=pos.device)
+        p_accept = torch.empty(C, dtype=torch.float64, device=pos.device)
+        u = None if _u is None else _host.to_dev(_u)
+        kbuf = (ctypes.c_uint32 * 2)(*ka)
+        _lib.check(lib.rodeo_b200_rwmh_accept_f64(C, d, _host.ptr(pos), _host.ptr(logd), _host.ptr(prop),
+                                                  _host.ptr(new_logd), _host.ptr(u), kbuf, 0, _host.ptr(acc),
+                                                  _host.ptr(p_accept), stream), "rwmh_accept")
+        is_acc = acc.bool()
+        if aux is not None and new_aux is not None:
+            rows = is_acc.nonzero(as_tuple=True)[0]            # accepted chains only
+            aux.index_copy_(0, rows, new_aux.index_select(0, rows))
+        elif new_aux is not None:
+            aux = new_aux
+        new_state = RWAState(pos, logd, aux)
+        return new_state, RWAInfo(p_accept, is_acc, new_state)     # reference :350: RWAInfo(p_accept, do_accept, new_state)
 
     return SamplingAlgorithm(init_fn, step_fn)
 

@@ -1,2 +1,2 @@
 """Kalman primitives with the reference's module layout (src/rodeo/kalmantv/)."""
-from . import standard  # noqa: F401
+from . import standard, square_root  # noqa: F401

@@ -73,3 +73,42 @@ def solve_sim(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interro
                                          _host.ptr(x), _host.ptr(ws), n, pb.stream())
     _lib.check(rc, "solve_sim")
     return pb.unbatch(x)
+
+
+def solve_sim_loglik(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars=None,
+                     obs_data=None, obs_times=None, noise_sd=None, kalman_type="standard", prior_weight=None,
+                     prior_var=None, return_draws=False, _z_interr=None, _z_smooth=None, _particle_offset=0, **params):
+    r"""``solve_sim`` fused with the Gaussian observation log-likelihood of the draw: per theta,
+    :math:`\sum_{i,k} \log N(y_{ik};\ X_{\mathrm{ind}(i), k, 0},\ \mathrm{sd}^2)` with ``ind = searchsorted(sim_times,
+    obs_times)`` -- the ``logdensity_fn`` of the reference's pseudo-marginal MCMC walkthrough
+    (docs/examples/parameter.md:333-354: ``rodeo.solve_sim``, ``Xt[obs_ind]``, ``fitz_loglik``) in ONE kernel.  The
+    observation terms are accumulated inside the backward sweep; unless ``return_draws`` the trajectories are never
+    written to memory.
+
+    obs_data: ``(n_obs, n_block)``; obs_times: ``(n_obs,)`` sorted.  Returns ``loglik (B,)`` or ``(loglik, Xt)``.
+    """
+    if key is None and _z_smooth is None:
+        raise TypeError("solve_sim_loglik needs a PRNG key")
+    pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
+                       prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
+    if pb.sfx != "f64" or kalman_type != "standard":
+        raise NotImplementedError('solve_sim_loglik is compiled for float64, kalman_type="standard"')
+    pb.set_obs(obs_data, obs_times)
+    if pb.obs_data.dim() == 3 and pb.obs_data.shape[-1] == 1:
+        pb.obs_data = pb.obs_data[..., 0].contiguous()
+    if tuple(pb.obs_data.shape) != (pb.c.n_obs, pb.nb):
+        raise ValueError("obs_data must have shape (n_obs, n_block)")
+    if (pb.obs_ind_host[1:] < pb.obs_ind_host[:-1]).any():
+        raise ValueError("obs_times must be sorted")
+    N = pb.n_steps
+    x = pb.empty(pb.B, N + 1, pb.nb, pb.p) if return_draws else None
+    ll = pb.empty(pb.B)
+    ws, n = pb.workspace(_lib.OP_SOLVE_SIM)
+    zi = None if _z_interr is None else pb.dev(_z_interr)
+    zs = None if _z_smooth is None else pb.dev(_z_smooth)
+    rc = pb.lib.rodeo_b200_solve_sim_loglik_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
+                                                _host.ptr(pb.x0), _host.ptr(pb.theta), _host.ptr(zi), _host.ptr(zs),
+                                                _host.ptr(pb.obs_ind), _host.ptr(pb.obs_data), float(noise_sd),
+                                                _host.ptr(ll), _host.ptr(x), _host.ptr(ws), n, pb.stream())
+    _lib.check(rc, "solve_sim_loglik")
+    return (pb.unbatch(ll), pb.unbatch(x)) if return_draws else pb.unbatch(ll)

@@ -105,3 +105,67 @@ def test_device_logpdf_matches_scipy_and_cutoff():
     assert np.isclose(got, -0.5 * (0.5 + np.log(2.0)) - 0.5 * np.log(2 * np.pi), rtol=1e-13)
     got = float(lp(np.array([5.0, 1.0, 0.3]), np.zeros(3), np.diag([1e-9, 2.0, 4.0])))
     assert np.isclose(got, -0.5 * (0.5 + np.log(2.0) + 0.09 / 4 + np.log(4.0)) - np.log(2 * np.pi), rtol=1e-13)
+
+
+# ---- square-root family (reference tests/test_square_root.py:19-168) ---------------------------------------------------
+@pytest.mark.parametrize("seed", range(10))
+def test_square_root_primitives_match_bruteforce_conditioning(seed):
+    """The reference's known-answer tests of rodeo.kalmantv.square_root, restated against the CUDA primitives: with
+    Cholesky factors in, L L^T of every factor out equals brute-force conditioning of the dense joint Gaussian (the
+    reference compares L L^T too, and only to 2 decimal places for the smooth_sim / smooth_cond variances)."""
+    import rodeo_b200
+    sq = rodeo_b200.kalmantv.square_root
+    chol = np.linalg.cholesky
+    sqr = lambda L: _np(L) @ _np(L).T
+    rng = np.random.default_rng(100 + seed)
+    ssm = gm.random_ssm(rng)
+    mean, cov = gm.joint_gaussian(ssm)
+    T, s = ssm["n_tot"], ssm["n_state"]
+    filt, pred = [], []
+    m_p, L_p = ssm["mean_state"][0], chol(ssm["var_state"][0])
+    for n in range(T):
+        if n > 0:
+            m_p, L_p = sq.predict(mean_state_past=filt[-1][0], var_state_past=filt[-1][1],
+                                  mean_state=ssm["mean_state"][n], wgt_state=ssm["wgt_state"][n - 1],
+                                  var_state=chol(ssm["var_state"][n]))
+            m_p, L_p = _np(m_p), _np(L_p)
+            assert np.array_equal(np.triu(L_p, 1), np.zeros_like(L_p))
+        pred.append((m_p, L_p))
+        bm, bv = gm.theta_mn(ssm, mean, cov, n, n - 1)
+        assert ref_rel_err(bm, m_p) < 5e-8 and ref_rel_err(bv, L_p @ L_p.T) < 5e-8
+        m_f, L_f = map(_np, sq.update(mean_state_pred=m_p, var_state_pred=L_p, x_meas=ssm["x_meas"][n],
+                                      mean_meas=ssm["mean_meas"][n], wgt_meas=ssm["wgt_meas"][n],
+                                      var_meas=chol(ssm["var_meas"][n])))
+        filt.append((m_f, L_f))
+        bm, bv = gm.theta_mn(ssm, mean, cov, n, n)
+        assert ref_rel_err(bm, m_f) < 5e-8 and ref_rel_err(bv, L_f @ L_f.T) < 5e-8
+        fm, fv = map(_np, sq.forecast(mean_state_pred=m_p, var_state_pred=L_p, mean_meas=ssm["mean_meas"][n],
+                                      wgt_meas=ssm["wgt_meas"][n], var_meas=chol(ssm["var_meas"][n])))
+        W = ssm["wgt_meas"][n]
+        assert np.allclose(fm, W @ m_p + ssm["mean_meas"][n], rtol=1e-12, atol=1e-13)
+        assert np.allclose(fv, W @ (L_p @ L_p.T) @ W.T + ssm["var_meas"][n], rtol=1e-10, atol=1e-12)
+    ms, Ls = filt[T - 1]
+    for n in range(T - 2, -1, -1):
+        ms, Ls = map(_np, sq.smooth_mv(mean_state_next=ms, var_state_next=Ls, mean_state_filt=filt[n][0],
+                                       var_state_filt=filt[n][1], mean_state_pred=pred[n + 1][0],
+                                       var_state_pred=pred[n + 1][1], wgt_state=ssm["wgt_state"][n],
+                                       var_state=chol(ssm["var_state"][n + 1])))
+        bm, bv = gm.theta_mn(ssm, mean, cov, n, T - 1)
+        assert ref_rel_err(bm, ms) < 5e-8 and ref_rel_err(bv, Ls @ Ls.T) < 5e-8
+    x_next = rng.standard_normal(s)
+    for n in range(T - 1):
+        mj, vj = gm.theta_mn(ssm, mean, cov, [n, n + 1], T - 1)
+        cm, cv = gm.condition(mj, vj, np.arange(s), np.arange(s, 2 * s), x_next)
+        kw = dict(mean_state_filt=filt[n][0], var_state_filt=filt[n][1], mean_state_pred=pred[n + 1][0],
+                  var_state_pred=pred[n + 1][1], wgt_state=ssm["wgt_state"][n], var_state=chol(ssm["var_state"][n + 1]))
+        m_sim, L_sim = sq.smooth_sim(x_state_next=x_next, **kw)
+        assert ref_rel_err(cm, _np(m_sim)) < 5e-8 and ref_rel_err(cv, sqr(L_sim)) < 5e-8
+        A, b, Lc = sq.smooth_cond(**kw)
+        assert np.allclose(_np(A) @ x_next + _np(b), cm, rtol=1e-8, atol=1e-11)
+        assert np.allclose(sqr(Lc), cv, rtol=1e-8, atol=1e-11)
+        # and the covariance-form primitives agree with the squared factors
+        std = rodeo_b200.kalmantv.standard
+        m2, v2 = std.smooth_sim(x_state_next=x_next, mean_state_filt=filt[n][0], var_state_filt=filt[n][1] @ filt[n][1].T,
+                                mean_state_pred=pred[n + 1][0], var_state_pred=pred[n + 1][1] @ pred[n + 1][1].T,
+                                wgt_state=ssm["wgt_state"][n])
+        assert np.allclose(_np(m2), _np(m_sim), rtol=1e-9, atol=1e-12) and np.allclose(_np(v2), sqr(L_sim), rtol=1e-8, atol=1e-11)

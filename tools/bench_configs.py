@@ -67,7 +67,7 @@ def run(only="", reps=5, scale=1.0, quiet=False):
             print(json.dumps(line), flush=True)
         res.append(line)
 
-    want = lambda k: (k in args.only.split(",")) if args.only else not k.endswith("f32")
+    want = lambda k: (k in args.only.split(",")) if args.only else not (k.endswith("f32") or k == "C5x")
     sc = args.scale
 
     if want("C1"):
@@ -117,11 +117,22 @@ def run(only="", reps=5, scale=1.0, quiet=False):
                                         prior_pars=(pr["Q"], pr["R"]), theta=th, **obd)
         report("C4 second-order fenrir kramer", B, 2000, timeit(f, args.reps, flush), 1230.0, 0.0)
     if want("C5"):
+        # BASELINE configs[4]: one pseudo-marginal iteration = solve_sim + Gaussian observation log-likelihood per
+        # particle; the fused kernel never writes the trajectories (SURVEY 8(d) C5 "~0 B, log-lik only")
+        B = int(32768 * sc); pr = P.fitz_problem(B, seed=0); ob = P.fitz_obs(pr, None)
+        X0, th = D(pr["X0"]), D(pr["theta"])
+        Y = D(ob["obs_data"][:, :, 0])
+        f = lambda: rb.solve_sim_loglik(np.array([5, 6], dtype=np.uint32), rb.models.fitzhugh_nagumo, pr["W"], X0, 0.0,
+                                        40.0, 800, chk, prior_pars=(pr["Q"], pr["R"]), theta=th, obs_data=Y,
+                                        obs_times=ob["obs_times"], noise_sd=0.0707)
+        report("C5 FN solve_sim chkrebtii + obs log-lik, fused, no Xt (one GPU's 32,768 of 262,144 particles)", B, 800,
+               timeit(f, args.reps, flush), 1035.0, 0.0)
+    if want("C5x"):
         B = int(32768 * sc); pr = P.fitz_problem(B, seed=0)
         X0, th = D(pr["X0"]), D(pr["theta"])
         f = lambda: rb.solve_sim(np.array([5, 6], dtype=np.uint32), rb.models.fitzhugh_nagumo, pr["W"], X0, 0.0, 40.0,
                                  800, chk, prior_pars=(pr["Q"], pr["R"]), theta=th)
-        report("C5 FN solve_sim chkrebtii (one GPU's 32,768 of 262,144 particles)", B, 800,
+        report("C5x FN solve_sim chkrebtii writing Xt (32,768 particles)", B, 800,
                timeit(f, args.reps, flush), 1035.0, 48.0)
     del flush
     torch.cuda.empty_cache()
