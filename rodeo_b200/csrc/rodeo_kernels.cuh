@@ -1832,15 +1832,21 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 //   warps 1..NP PRODUCERS: producer p takes the steps t = N-1-p, N-1-p-NP, ...: load filt[t] (two of its steps ahead),
 //               predict, LDL^T gain, conditional variance -> (A_t, mu_f, mu_p, C_t) into a 2 NP-slot shared-memory ring.
 // Hand-over by named barriers (bar.arrive / bar.sync with 64 participants: one producer warp + the consumer), the
-// producer / consumer pattern of the PTX manual.  NP = 3: measured on BASELINE configs[3], a produced step costs ~1,750
-// cycles (476 issue cycles + history latency + FP64-pipe contention with the neighbouring warps) against ~300 for the
-// consumer's.  The arithmetic is the same __device__ functions in the same order as
+// producer / consumer pattern of the PTX manual.  NP = 2: measured on BASELINE configs[3] (B200, 16,384 thetas, N = 2,000)
+// fenrir_kernel 2.65 ms, NP = 2: 2.01 ms, NP = 3: 2.87 ms (164 registers x 128 threads leave 3 CTAs per SM: two waves)
+// or 2.51 ms capped at 128 registers (spills).  What is left: the forward sweep is one warp per CTA and costs ~670
+// cycles per step against 320 issue cycles (the double-precision sin of the right-hand side, the history stores'
+// address arithmetic), and a produced step costs ~1,750 cycles (476 issue cycles + FP64-pipe contention between the
+// 10 warps an SM now holds) against ~300 for the consumer's.  The arithmetic is the same __device__ functions in the same order as
 // fenrir_kernel: the log-likelihoods are bitwise identical.
 #ifndef RODEO_FENRIR_NP
-#define RODEO_FENRIR_NP 3
+#define RODEO_FENRIR_NP 2
+#endif
+#ifndef RODEO_FENRIR_WS_MINB
+#define RODEO_FENRIR_WS_MINB 1
 #endif
 template <typename T, class Model, int INTERR, int QK, int NOBS>
-__global__ void __launch_bounds__(32 * (1 + RODEO_FENRIR_NP))
+__global__ void __launch_bounds__(32 * (1 + RODEO_FENRIR_NP), RODEO_FENRIR_WS_MINB)
 fenrir_ws_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                  const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ stash, i64 ldb,
                  T* __restrict__ loglik) {

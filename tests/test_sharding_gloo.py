@@ -41,6 +41,14 @@ def _worker(rank, world, port, B, q):
         return torch.from_numpy(ll) + 0.0 * offset
 
     full = parallel.sharded_loglik(local, pr["theta"], pr["X0"])
+    # the pipelined gather (CPU tensors: the collectives run in program order): three batches over two buffer pairs
+    pipe = parallel.GatherPipeline(4, "cpu")
+    for k in range(3):
+        pipe.local_buffer().copy_(torch.arange(4, dtype=torch.float64) + 10 * rank + 100 * k)
+        slot = pipe.submit()
+        want = torch.cat([torch.arange(4, dtype=torch.float64) + 10 * r + 100 * k for r in range(world)])
+        assert torch.equal(pipe.result(slot), want)
+    pipe.drain()
     if rank == 0:
         q.put(full.numpy())
     dist.barrier()
