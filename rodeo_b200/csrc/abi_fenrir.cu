@@ -26,7 +26,10 @@ struct FenrirRun {
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;
-    bool ws = sizeof(real_t) == 8;                         // warp-specialised backward sweep (rodeo_kernels.cuh)
+    // warp-specialised backward sweep (rodeo_kernels.cuh) while all of its CTAs are resident at once, i.e. while the
+    // one-warp kernel would be bound by a theta's serial chain; measured on B200: second-order ODE, 16,384 thetas x 2,000
+    // steps 2.65 -> 2.0-2.2 ms; FitzHugh-Nagumo, 65,536 thetas x 800 steps 3.54 -> 3.64 ms (throughput-bound: not used)
+    bool ws = sizeof(real_t) == 8 && (long long)grid_for(p.B, 32) <= 4LL * sm_count();
     if (const char* e = getenv("RODEO_FENRIR_WS")) ws = ws && e[0] == '1';      // tuning / tests
     if constexpr (sizeof(real_t) == 8) {
       if (ws) {
@@ -35,6 +38,9 @@ struct FenrirRun {
                                 (int)sizeof(real_t);
         RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_ws_kernel<real_t, Model, INTERR, QK, 1>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WS));
+        RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_ws_kernel<real_t, Model, INTERR, QK, 1>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
         fenrir_ws_kernel<real_t, Model, INTERR, QK, 1><<<grid_for(p.B, 32), 32 * (1 + RODEO_FENRIR_NP), SMEM_WS, s>>>(C, a, o, stash,
                                                                                                stash_ldb(p.B), out);
       }

@@ -1842,11 +1842,15 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 #ifndef RODEO_FENRIR_NP
 #define RODEO_FENRIR_NP 2
 #endif
+// 4 CTAs per SM (BASELINE configs[3] needs 3.46 to hold its 512 CTAs in one wave): 170 registers at 96 threads.  Without
+// the bound ptxas takes 174 and the launch falls into two waves (measured 3.11 ms instead of 2.01)
+// (models with more than 20 state entries per theta would spill under that bound and keep ptxas's own choice)
 #ifndef RODEO_FENRIR_WS_MINB
-#define RODEO_FENRIR_WS_MINB 1
+#define RODEO_FENRIR_WS_MINB(NSTATE) ((RODEO_FENRIR_NP == 2 && (NSTATE) <= 20) ? 4 : 1)
 #endif
 template <typename T, class Model, int INTERR, int QK, int NOBS>
-__global__ void __launch_bounds__(32 * (1 + RODEO_FENRIR_NP), RODEO_FENRIR_WS_MINB)
+__global__ void __launch_bounds__(32 * (1 + RODEO_FENRIR_NP),
+                                  RODEO_FENRIR_WS_MINB(Model::NB * (Model::P + Model::P * (Model::P + 1) / 2)))
 fenrir_ws_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
                  const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ stash, i64 ldb,
                  T* __restrict__ loglik) {
