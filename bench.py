@@ -356,6 +356,49 @@ def run_ours(args):
                         "sharded_equals_unsharded_bitwise": bool(torch.equal(full1, fullN))})
         strong = rec
 
+    # ---- BASELINE configs[4] at its stated total: 262,144 particles of one pseudo-marginal iteration (solve_sim +
+    #      interrogate_chkrebtii + Gaussian observation log-likelihood, ONE fused kernel, no trajectories written) over
+    #      the `world` GPUs, the per-particle log-likelihoods all-gathered
+    strong_c5 = None
+    if args.thetas == B_PER_GPU and not args.skip_configs:
+        import functools
+        P5 = 262144
+        lo, hi = parallel.shard_bounds(P5, rank, world)
+        pr5 = workload(P5, seed=5)
+        ob5 = obs_for(pr5, truth.cpu().numpy())
+        chk = functools.partial(rodeo_b200.interrogate.interrogate_chkrebtii, kalman_type="standard")
+        X5 = torch.as_tensor(pr5["X0"][lo:hi], device=dev)
+        th5 = torch.as_tensor(pr5["theta"][lo:hi], device=dev)
+        Y5 = torch.as_tensor(ob5["obs_data"][:, :, 0], device=dev)
+        g5 = torch.empty(P5, dtype=torch.float64, device=dev) if world > 1 else None
+
+        def c5_step(k):
+            ll = rodeo_b200.solve_sim_loglik(np.array([9, k], dtype=np.uint32), fn, pr5["W"], X5, 0.0, T_MAX, N,
+                                             chk, prior_pars=(pr5["Q"], pr5["R"]), theta=th5, obs_data=Y5,
+                                             obs_times=ob5["obs_times"], noise_sd=float(np.sqrt(0.005)),
+                                             _particle_offset=lo)
+            return parallel.all_gather_loglik(ll, P5, out=g5)
+        for k in range(2):
+            full5 = c5_step(k)
+        barrier()
+        n5 = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n5):
+            full5 = c5_step(10 + k)
+        e1.record()
+        barrier()
+        t5 = torch.tensor([e0.elapsed_time(e1) / n5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        strong_c5 = {"particles_total": P5, "particles_per_gpu": hi - lo, "n_steps": N, "ms_per_iteration": float(t5.item()),
+                     "value": P5 * N / (float(t5.item()) * 1e-3), "unit": UNIT,
+                     "finite": bool(torch.isfinite(full5).all().item()),
+                     "what": "rodeo_b200.solve_sim_loglik (fused solve_sim + chkrebtii + Gaussian obs log-lik, no Xt) per "
+                             "shard + all-gather of the log-likelihoods"}
+        del X5, th5, full5
+        torch.cuda.empty_cache()
+
     # ---- end to end through the C ABI with host buffers (pinned), H2D + kernel + D2H inside the timed region
     h_x0 = torch.from_numpy(pr["X0"]).pin_memory()
     h_th = torch.from_numpy(pr["theta"]).pin_memory()
@@ -513,7 +556,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "rodeo_b200_dalton_f64_host (C ABI, pinned host buffers)", "matches_device_path": same},
-        "e2e_python": e2e_py, "strong": strong, "sustained": sustained, "configs": configs,
+        "e2e_python": e2e_py, "strong": strong, "strong_c5": strong_c5, "sustained": sustained, "configs": configs,
         "gather_matches_rank_outputs": gather_ok,
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "wall_s_timed_region": t_wall,

@@ -26,8 +26,25 @@ struct DaltonRun {
                  const CommonArgs<real_t>& a, const ObsArgs<real_t>& o, real_t* out, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
+    if (p.n_bobs == 2) {
+      // two observation rows per block (correlated noise allowed): the stacked (1 + 2)-row update with the reference's
+      // eigen-decomposition log-pdf; float64, interrogate_kramer, one thread per (theta, filter)
+      if constexpr (sizeof(real_t) == 8 && INTERR == INTERR_KRAMER && Model::M == 1) {
+        if (p.B == 0) return RODEO_OK;
+        CommonArgs<real_t> ag = a;
+        ag.dalton_geometry = 2;
+        RODEO_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)p.B * sizeof(real_t), s));
+        dalton_kernel<real_t, Model, INTERR, QK, 2><<<2 * grid_for(p.B, 32), 32, 0, s>>>(C, ag, o, out);
+        g_launches++;
+        RODEO_CUDA_OK(cudaGetLastError());
+        return RODEO_OK;
+      } else {
+        set_error("dalton: n_bobs=2 is compiled for float64 and interrogate_kramer only");
+        return RODEO_ERR_UNSUPPORTED;
+      }
+    }
     if (p.n_bobs != 1) {
-      set_error("dalton: n_bobs=%d is not compiled ahead of time (only 1)", p.n_bobs);
+      set_error("dalton: n_bobs=%d is not compiled ahead of time (1 or 2)", p.n_bobs);
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;

@@ -21,8 +21,24 @@ struct FenrirRun {
                  const CommonArgs<real_t>& a, const ObsArgs<real_t>& o, real_t* stash, real_t* out, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
+    if (p.n_bobs == 2) {
+      // two observation rows per block: float64, interrogate_kramer, the one-warp kernel
+      if constexpr (sizeof(real_t) == 8 && INTERR == INTERR_KRAMER) {
+        if (p.B == 0) return RODEO_OK;
+        constexpr int SMEM2 = 2 * SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
+        RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_kernel<real_t, Model, INTERR, QK, 2>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+        fenrir_kernel<real_t, Model, INTERR, QK, 2><<<grid_for(p.B, 32), 32, SMEM2, s>>>(C, a, o, stash, stash_ldb(p.B), out);
+        g_launches++;
+        RODEO_CUDA_OK(cudaGetLastError());
+        return RODEO_OK;
+      } else {
+        set_error("fenrir: n_bobs=2 is compiled for float64 and interrogate_kramer only");
+        return RODEO_ERR_UNSUPPORTED;
+      }
+    }
     if (p.n_bobs != 1) {
-      set_error("fenrir: n_bobs=%d is not compiled ahead of time (only 1)", p.n_bobs);
+      set_error("fenrir: n_bobs=%d is not compiled ahead of time (1 or 2)", p.n_bobs);
       return RODEO_ERR_UNSUPPORTED;
     }
     if (p.B == 0) return RODEO_OK;

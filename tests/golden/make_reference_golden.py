@@ -167,6 +167,23 @@ def build():
     out["fitzmid_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
         key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs2), pr)
 
+    # two observation rows per block with correlated noise (n_bobs = 2): the stacked 3-row update and the 3x3 / 2x2
+    # eigen-decompositions of the forecast variances (dalton.py:136-149, fenrir.py:160-179)
+    rngb = np.random.default_rng(77)
+    n_ob = len(ob["obs_times"])
+    ob3 = {"obs_times": ob["obs_times"].copy()}
+    D3 = np.zeros((n_ob, 2, 2, 3)); D3[..., 0, 0] = 1.0; D3[..., 1, 0] = 0.5; D3[..., 1, 1] = 0.2
+    Om3 = np.zeros((n_ob, 2, 2, 2)); Om3[..., 0, 0] = 0.005; Om3[..., 1, 1] = 0.02; Om3[..., 0, 1] = Om3[..., 1, 0] = 0.003
+    ob3["obs_weight"], ob3["obs_var"] = D3, Om3
+    ob3["obs_data"] = np.concatenate([ob["obs_data"], 0.5 * ob["obs_data"] + 0.05 * rngb.standard_normal(ob["obs_data"].shape)],
+                                     axis=2)
+    save_problem("fitzbobs2", pr, ob3)
+    obs3 = {k: jnp.array(v) for k, v in ob3.items()}
+    out["fitzbobs2_dalton"] = per_theta(lambda X0, th: rodeo.inference.dalton(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs3), pr)
+    out["fitzbobs2_fenrir"] = per_theta(lambda X0, th: rodeo.inference.fenrir(
+        key=key, ode_init=X0, interrogate=kramer, theta=th, **common, **obs3), pr)
+
     # shortest solves the reference's scans support (the backward scan has length n_steps - 1 >= 1): n_steps = 2, 3,
     # with observations on both end points
     for Ns in (2, 3):

@@ -28,7 +28,7 @@ def ll_err(a, b):
 
 
 MODEL = {"fitz": "fitzhugh_nagumo", "fitzmid": "fitzhugh_nagumo", "readme": "fitzhugh_nagumo", "lorenz": "lorenz63",
-         "so": "second_order_sin", "fitzN2": "fitzhugh_nagumo", "fitzN3": "fitzhugh_nagumo", "fitzpast": "fitzhugh_nagumo", "hes1": "hes1", "seirah": "seirah"}
+         "so": "second_order_sin", "fitzN2": "fitzhugh_nagumo", "fitzN3": "fitzhugh_nagumo", "fitzpast": "fitzhugh_nagumo", "fitzbobs2": "fitzhugh_nagumo", "hes1": "hes1", "seirah": "seirah"}
 
 
 def grid(tag):
@@ -79,7 +79,7 @@ def test_oracle_solve_sim_same_normals_svd_factor():
     assert P.maxnorm_rel(x, G["fitz_sim_x"]) < 1e-10
 
 
-@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "fitzpast", "readme", "so", "fitzN2", "fitzN3"])
+@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "fitzpast", "readme", "so", "fitzN2", "fitzN3", "fitzbobs2"])
 def test_oracle_dalton_fenrir(tag):
     a, o = oargs(tag)
     assert ll_err(orc.fenrir(*a, *o), G[f"{tag}_fenrir"]) < 1e-11
@@ -196,7 +196,7 @@ def test_cuda_solve_mv_chkrebtii_same_normals(rb):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "fitzpast", "readme", "so", "fitzN2", "fitzN3"])
+@pytest.mark.parametrize("tag", ["fitz", "fitzmid", "fitzpast", "readme", "so", "fitzN2", "fitzN3", "fitzbobs2"])
 def test_cuda_dalton_fenrir(rb, tag):
     a, kw, ob = gargs(rb, tag)
     assert ll_err(_np(rb.inference.fenrir(*a, **kw, **ob)), G[f"{tag}_fenrir"]) < TOL
