@@ -217,6 +217,12 @@ int rodeo_b200_solve_mv_sqrt_f64(const RodeoProblem* prob, const double* ode_wei
                                  const double* z_interr, double* mean_out, double* var_sqrt_out, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* float32 factors (and means carried in double inside the kernel); same workspace size */
+int rodeo_b200_solve_mv_sqrt_f32(const RodeoProblem* prob, const float* ode_weight, const float* prior_weight,
+                                 const float* prior_var_sqrt, const float* ode_init, const float* theta,
+                                 const float* z_interr, float* mean_out, float* var_sqrt_out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 /*
  * float32 instantiations: identical argument lists with `float` buffers (and a `float` time in ode_init_pad).
  * The reference's float width follows jax_enable_x64; its own unit tests run in float32 when tox is not used.

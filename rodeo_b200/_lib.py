@@ -76,6 +76,7 @@ SIGNATURES = {
     "rodeo_b200_dalton_solve_sim_f64": (_i, [_P] + [_vp] * 12 + [_vp, _sz, _vp]),
     "rodeo_b200_solve_mv_sqrt_workspace_bytes": (_sz, [_P]),
     "rodeo_b200_solve_mv_sqrt_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "rodeo_b200_solve_mv_sqrt_f32": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_fenrir_solve_mv_workspace_bytes": (_sz, [_P]),
     "rodeo_b200_fenrir_solve_mv_f64": (_i, [_P] + [_vp] * 12 + [_vp, _sz, _vp]),
     "rodeo_b200_ktv_predict_f64": (_i, [ctypes.c_int64, _i] + [_vp] * 7 + [_vp]),

@@ -739,13 +739,14 @@ RD_DEV void qr_lower(T (&A)[ROWS][P], T (&Lout)[P * (P + 1) / 2]) {
 }
 
 // predict: mu_p = Q mu ;  L_p = add_sqrt(Q L, R^{1/2})            (square_root.py:57-58)
-template <typename T, int P>
-RD_DEV void sqrt_predict(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], const T (&mu)[P],
-                         const T (&L)[P * (P + 1) / 2], T (&mup)[P], T (&Lp)[P * (P + 1) / 2]) {
+// (means in the mean type MT -- double also for T = float, see MeanOf -- factors in T)
+template <typename T, int P, typename MT>
+RD_DEV void sqrt_predict(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], const MT (&mu)[P],
+                         const T (&L)[P * (P + 1) / 2], MT (&mup)[P], T (&Lp)[P * (P + 1) / 2]) {
   T A[2 * P][P];
   RD_UNROLL for (int i = 0; i < P; ++i) {
-    T m = Q[i][0] * mu[0];
-    RD_UNROLL for (int j = 1; j < P; ++j) m = rd_fma(Q[i][j], mu[j], m);
+    MT m = (MT)Q[i][0] * mu[0];
+    RD_UNROLL for (int j = 1; j < P; ++j) m = rd_fma((MT)Q[i][j], mu[j], m);
     mup[i] = m;
   }
   // rows 0..P-1: (Q L)^T, i.e. A[r][c] = sum_{k >= r} Q[c][k] L[k][r] ; rows P..2P-1: (R^{1/2})^T
@@ -764,8 +765,8 @@ RD_DEV void sqrt_predict(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], con
 //   L_f = add_sqrt(L - K wl, K vrow)
 // `vrow` is the measurement-noise square-root BLOCK the reference stacks: a 1 x NV row (NV = 0: none, i.e.
 // interrogate_kramer / schober; NV = P for interrogate_chkrebtii's var_meas = W L).
-template <typename T, int P, int NV>
-RD_DEV void sqrt_update_row(T (&mu)[P], T (&L)[P * (P + 1) / 2], const T (&w)[P], T res, const T* vrow) {
+template <typename T, int P, int NV, typename MT>
+RD_DEV void sqrt_update_row(MT (&mu)[P], T (&L)[P * (P + 1) / 2], const T (&w)[P], MT res, const T* vrow) {
   T wl[P], K[P];
   T s2 = T(0);
   RD_UNROLL for (int c = 0; c < P; ++c) {
@@ -780,7 +781,7 @@ RD_DEV void sqrt_update_row(T (&mu)[P], T (&L)[P * (P + 1) / 2], const T (&w)[P]
     T a = T(0);
     RD_UNROLL for (int c = 0; c <= i; ++c) a = rd_fma(L[lidx(i, c)], wl[c], a);
     K[i] = a * rs2;
-    mu[i] = rd_fma(K[i], res, mu[i]);
+    mu[i] = rd_fma((MT)K[i], res, mu[i]);
   }
   T A[P + NV][P];
   RD_UNROLL for (int r = 0; r < P; ++r)
@@ -792,10 +793,10 @@ RD_DEV void sqrt_update_row(T (&mu)[P], T (&L)[P * (P + 1) / 2], const T (&w)[P]
 
 // smooth_mv (square_root.py:160-222):  G = S_f Q^T S_p^{-1} through two triangular solves with L_p,
 //   mu_s = mu_f + G (mu_s' - mu_p) ;  L_s = add_sqrt(G [L_s', R^{1/2}], (I - G Q) L_f)
-template <typename T, int P>
-RD_DEV void sqrt_smooth_mv(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], const T (&muf)[P],
-                           const T (&Lf)[P * (P + 1) / 2], const T (&mup)[P], const T (&Lp)[P * (P + 1) / 2],
-                           T (&ms)[P], T (&Ls)[P * (P + 1) / 2]) {
+template <typename T, int P, typename MT>
+RD_DEV void sqrt_smooth_mv(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], const MT (&muf)[P],
+                           const T (&Lf)[P * (P + 1) / 2], const MT (&mup)[P], const T (&Lp)[P * (P + 1) / 2],
+                           MT (&ms)[P], T (&Ls)[P * (P + 1) / 2]) {
   T Sf[P][P], X[P][P], G[P][P], rd[P];
   RD_UNROLL for (int i = 0; i < P; ++i) {
     rd[i] = rcp(Lp[lidx(i, i)]);
@@ -846,12 +847,13 @@ RD_DEV void sqrt_smooth_mv(const T (&Q)[P][P], const T (&Rh)[P * (P + 1) / 2], c
       }
       A[r][c] = a; A[P + r][c] = b; A[2 * P + r][c] = j;
     }
+  MT mnew[P];      // ms is read in full before it is overwritten
   RD_UNROLL for (int i = 0; i < P; ++i) {
-    T m = muf[i];
-    RD_UNROLL for (int jx = 0; jx < P; ++jx) m = rd_fma(G[i][jx], ms[jx] - mup[jx], m);
-    X[0][i] = m;   // reuse as scratch so that ms is read before it is overwritten
+    MT m = muf[i];
+    RD_UNROLL for (int jx = 0; jx < P; ++jx) m = rd_fma((MT)G[i][jx], ms[jx] - mup[jx], m);
+    mnew[i] = m;
   }
-  RD_UNROLL for (int i = 0; i < P; ++i) ms[i] = X[0][i];
+  RD_UNROLL for (int i = 0; i < P; ++i) ms[i] = mnew[i];
   qr_lower<T, 3 * P, P>(A, Ls);
 }
 

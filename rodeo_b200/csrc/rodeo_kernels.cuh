@@ -1325,19 +1325,22 @@ solve_mv_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, 
 // of the prior variance (the caller passes prior_pars = (Q, cholesky(R)), docs/examples/higher_order.md:108-112).
 template <typename T, class Model, int INTERR>
 RD_DEV void forward_step_sqrt(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
-                              const typename Model::template Par<T>& q, i64 idx, int n,
+                              const typename Fwd<T, Model, INTERR, QK_DENSE>::Par& q, i64 idx, int n,
                               Fwd<T, Model, INTERR, QK_DENSE>& f) {
+  typedef typename Fwd<T, Model, INTERR, QK_DENSE>::MT MT;      // means / right-hand side: double also for T = float
   constexpr int NB = Model::NB, P = Model::P, M = Model::M, JC = Model::JCOLS, NS = P * (P + 1) / 2;
   static_assert(M == 1, "square-root path: scalar measurements per block");
   constexpr bool CHK = (INTERR == INTERR_CHKREBTII);
-  const T t = Model::USES_TIME ? step_time<T>(a.t_min, a.t_max, n, a.n_steps) : T(0);
+  const MT t = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, n, a.n_steps) : MT(0);
   RD_UNROLL for (int b = 0; b < NB; ++b) {
-    T mp[P], Lp[NS];
+    MT mp[P];
+    T Lp[NS];
     sqrt_predict<T, P>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Lp);
     RD_UNROLL for (int i = 0; i < P; ++i) f.mu[b][i] = mp[i];
     RD_UNROLL for (int k = 0; k < NS; ++k) f.S[b][k] = Lp[k];
   }
-  T x[NB][JC], vrow[NB][CHK ? P : 1];
+  MT x[NB][JC];
+  T vrow[NB][CHK ? P : 1];
   if constexpr (CHK) {
     // interrogate.py:36-47 ("square-root" branch), literally: var_meas = W L is an (m, p) block and
     // x_state = mean + var_meas @ z, whose single entry broadcasts over every state entry of the block
@@ -1349,12 +1352,12 @@ RD_DEV void forward_step_sqrt(const FilterConsts<T, Model::NB, Model::P, Model::
       philox_normals<T, NB * P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, z);
     }
     RD_UNROLL for (int b = 0; b < NB; ++b) {
-      T shift = T(0);
+      MT shift = MT(0);
       RD_UNROLL for (int c = 0; c < P; ++c) {
         T v = T(0);
         RD_UNROLL for (int k = c; k < P; ++k) v = rd_fma(C.W[b][0][k], f.S[b][lidx(k, c)], v);
         vrow[b][c] = v;
-        shift = rd_fma(v, z[b * P + c], shift);
+        shift = rd_fma((MT)v, (MT)z[b * P + c], shift);
       }
       RD_UNROLL for (int j = 0; j < JC; ++j) x[b][j] = f.mu[b][j] + shift;
     }
@@ -1364,19 +1367,20 @@ RD_DEV void forward_step_sqrt(const FilterConsts<T, Model::NB, Model::P, Model::
       RD_UNROLL for (int j = 0; j < JC; ++j) x[b][j] = f.mu[b][j];
     }
   }
-  T fv[NB][M], jl[NB][M][JC];
+  MT fv[NB][M], jl[NB][M][JC];
   if constexpr (INTERR == INTERR_KRAMER) {
-    eval_f_jac<Model, T>(q, t, x, fv, jl);
+    eval_f_jac<Model, MT>(q, t, x, fv, jl);
   } else {
-    Model::template rhs<T, T>(q, t, x, fv);
+    Model::template rhs<MT, MT>(q, t, x, fv);
     RD_UNROLL for (int b = 0; b < NB; ++b)
-      RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][0][j] = T(0);
+      RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][0][j] = MT(0);
   }
   RD_UNROLL for (int b = 0; b < NB; ++b) {
-    T w[P], res = fv[b][0];
+    T w[P];
+    MT res = fv[b][0];
     RD_UNROLL for (int j = 0; j < P; ++j) {
-      w[j] = (INTERR == INTERR_KRAMER && j < JC) ? C.W[b][0][j] - jl[b][0][j] : C.W[b][0][j];
-      res = rd_fma(-C.W[b][0][j], f.mu[b][j], res);
+      w[j] = (INTERR == INTERR_KRAMER && j < JC) ? C.W[b][0][j] - (T)jl[b][0][j] : C.W[b][0][j];
+      res = rd_fma(-(MT)C.W[b][0][j], f.mu[b][j], res);
     }
     sqrt_update_row<T, P, CHK ? P : 0>(f.mu[b], f.S[b], w, res, vrow[b]);
   }
@@ -1409,7 +1413,8 @@ solve_mv_sqrt_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P
       }
     }
   }
-  T ms[NB][P], Ls[NB][NS];
+  typename F::MT ms[NB][P];
+  T Ls[NB][NS];
   RD_UNROLL for (int b = 0; b < NB; ++b) {
     RD_UNROLL for (int i = 0; i < P; ++i) ms[b][i] = f.mu[b][i];
     RD_UNROLL for (int k = 0; k < NS; ++k) Ls[b][k] = f.S[b][k];
@@ -1435,7 +1440,8 @@ solve_mv_sqrt_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P
       if (n0 + s == 0) break;
       buf.get(s, f.mu, f.S);                               // filt[n] (mean, lower factor)
       RD_UNROLL for (int b = 0; b < NB; ++b) {
-        T mp[P], Lp[NS];
+        typename F::MT mp[P];
+        T Lp[NS];
         sqrt_predict<T, P>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Lp);      // pred[n+1]
         sqrt_smooth_mv<T, P>(C.Q[b], C.R[b], f.mu[b], f.S[b], mp, Lp, ms[b], Ls[b]);
       }

@@ -25,11 +25,11 @@ def solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrog
     if kalman_type == "square-root":
         # prior_pars = (Q, cholesky(R)); `var` receives lower-triangular factors, as in the reference
         # (src/rodeo/kalmantv/square_root.py; docs/examples/higher_order.md:108-127)
-        if pb.sfx != "f64" or pb.r_scale is not None:
-            raise NotImplementedError('kalman_type="square-root" is compiled for float64 and a shared prior only')
+        if pb.r_scale is not None:
+            raise NotImplementedError('kalman_type="square-root" is compiled for a shared prior only')
         n = pb.lib.rodeo_b200_solve_mv_sqrt_workspace_bytes(ctypes.byref(pb.c))
         ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
-        rc = pb.lib.rodeo_b200_solve_mv_sqrt_f64(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q),
+        rc = pb.fn("solve_mv_sqrt")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q),
                                                  _host.ptr(pb.R), _host.ptr(pb.x0), _host.ptr(pb.theta),
                                                  _host.ptr(zi), _host.ptr(mean), _host.ptr(var), _host.ptr(ws), n,
                                                  pb.stream())

@@ -675,6 +675,26 @@ def test_solve_mv_square_root(rb, interr):
         assert P.maxnorm_rel(_np(m), _np(m2)) < 1e-9 and P.maxnorm_rel(_sq(L), _np(v2)) < 1e-8
 
 
+@pytest.mark.parametrize("N,tm", [(200, 10.0), (800, 40.0)])
+def test_solve_mv_square_root_float32(rb, N, tm):
+    """The square-root form is the numerically robust one for float32: float32 factors and QR, means
+    carried in double, against the FLOAT64 oracle at BASELINE's float32 gate of 1e-5."""
+    import torch
+    pr = P.fitz_problem(32, n_steps=N, t_max=tm, seed=73)
+    Rh = np.linalg.cholesky(pr["R"])
+    th32, X32 = pr["theta"].astype(np.float32), pr["X0"].astype(np.float32)
+    m, L = rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], X32, 0.0, tm, N, rb.interrogate.interrogate_kramer,
+                       prior_pars=(pr["Q"], Rh), kalman_type="square-root", theta=th32)
+    assert m.dtype == torch.float32 and L.dtype == torch.float32
+    om, oL = orc.solve_mv_sqrt(orc.MODELS["fitzhugh_nagumo"], pr["W"], X32.astype(np.float64), 0.0, tm, N,
+                               orc.interrogate_kramer, (pr["Q"], Rh), th32.astype(np.float64))
+    L = _np(L).astype(np.float64)
+    em, ev = P.maxnorm_rel(_np(m).astype(np.float64), om), P.maxnorm_rel(_sq(L), _sq(oL))
+    print(f"float32 square-root solve_mv N={N}: mean {em:.2e} var (L L^T) {ev:.2e}")
+    assert em < 1e-5 and ev < 1e-4
+    assert not np.triu(L, 1).any()
+
+
 def test_square_root_higher_order_docs_example(rb):
     # reference docs/examples/higher_order.md:104-127: sigma = .001, n_steps = 400, prior_chol = cholesky(prior_R)
     pr = P.second_order_problem(8, n_steps=400, sigma=0.001, seed=3)
