@@ -336,6 +336,18 @@ int rodeo_b200_fp64_peak_probe(int reps, double* tflops_out);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t rodeo_b200_launch_count(void);
 
+/*
+ * Covariance schedules (rodeo_b200/csrc/rodeo_sched.cuh).  Under interrogate_chkrebtii / _schober / _rodeo
+ * (src/rodeo/interrogate.py:13-60, 87-115: wgt_meas == 0, var_meas a function of the predicted variance) every
+ * variance, gain and sampling factor of solve_sim depends on (prior, ode_weight, n_steps) only; the library computes
+ * them once into a device table it owns and re-uses the table in later calls (any stream, any theta batch, any key).
+ *   rodeo_b200_schedule_builds  number of tables built since load (a repeated call must not increase it)
+ *   rodeo_b200_schedule_clear   drop every cached table (synchronises the device)
+ * RODEO_SIM_SCHEDULE=0 in the environment sends solve_sim through the full kernels instead (A/B checks).
+ */
+int64_t rodeo_b200_schedule_builds(void);
+void rodeo_b200_schedule_clear(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,8 @@ SIGNATURES = {
     "rodeo_b200_abi_version": (_i, []),
     "rodeo_b200_problem_sizeof": (_sz, []),
     "rodeo_b200_launch_count": (ctypes.c_int64, []),
+    "rodeo_b200_schedule_builds": (ctypes.c_int64, []),
+    "rodeo_b200_schedule_clear": (None, []),
     "rodeo_b200_solve_mv_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_solve_sim_f64": (_i, [_P] + [_vp] * 8 + [_vp, _sz, _vp]),
     "rodeo_b200_dalton_f64": (_i, [_P] + [_vp] * 11 + [_vp, _sz, _vp]),

@@ -2,6 +2,10 @@
 // gather / initial-value kernels.  See include/rodeo_b200.h.
 #include "rodeo_host.h"
 
+#include <list>
+#include <mutex>
+#include <string>
+
 namespace rodeo {
 namespace host {
 
@@ -13,6 +17,74 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- schedule cache (rodeo_sched.cuh) --------------------------------------------------------------------------------
+// Covariance schedules depend on (device, instantiation, n_steps, W, Q, R) only.  They are built once on the stream of
+// the first call that needs them and kept in library-owned device memory (a few hundred KB each); every later call,
+// on any stream, waits on the build's event and reads the table.  Least-recently-used eviction at 16 entries.
+namespace {
+struct SchedEntry {
+  std::string key;
+  void* dev = nullptr;
+  cudaEvent_t ready = nullptr;
+};
+std::mutex g_sched_mu;
+std::list<SchedEntry> g_sched;      // front = most recently used
+constexpr size_t SCHED_MAX = 16;
+std::atomic<long long> g_sched_builds{0};
+}  // namespace
+
+long long sched_builds() { return g_sched_builds.load(); }
+
+void sched_clear() {
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  if (!g_sched.empty()) cudaDeviceSynchronize();
+  for (auto& e : g_sched) { cudaFree(e.dev); cudaEventDestroy(e.ready); }
+  g_sched.clear();
+}
+
+int sched_get(const void* key, size_t key_bytes, size_t bytes, const std::function<int(void*, cudaStream_t)>& build,
+              cudaStream_t s, const void** table) {
+  int dev = 0;
+  RODEO_CUDA_OK(cudaGetDevice(&dev));
+  std::string k((const char*)&dev, sizeof(dev));
+  k.append((const char*)&bytes, sizeof(bytes));
+  k.append((const char*)key, key_bytes);
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  for (auto it = g_sched.begin(); it != g_sched.end(); ++it)
+    if (it->key == k) {
+      g_sched.splice(g_sched.begin(), g_sched, it);
+      RODEO_CUDA_OK(cudaStreamWaitEvent(s, it->ready, 0));
+      *table = it->dev;
+      return RODEO_OK;
+    }
+  if (g_sched.size() >= SCHED_MAX) {
+    // a kernel on another stream may still be reading the victim: drain the device before freeing it (rare path)
+    RODEO_CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(g_sched.back().dev);
+    cudaEventDestroy(g_sched.back().ready);
+    g_sched.pop_back();
+  }
+  SchedEntry e;
+  e.key = std::move(k);
+  RODEO_CUDA_OK(cudaMalloc(&e.dev, bytes));
+  cudaError_t ce = cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming);
+  if (ce != cudaSuccess) { cudaFree(e.dev); return cuda_fail(ce, "cudaEventCreateWithFlags"); }
+  int rc = build(e.dev, s);
+  if (rc == RODEO_OK) {
+    ce = cudaEventRecord(e.ready, s);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "cudaEventRecord");
+  }
+  if (rc != RODEO_OK) {
+    cudaStreamSynchronize(s);
+    cudaFree(e.dev); cudaEventDestroy(e.ready);
+    return rc;
+  }
+  g_sched_builds++;
+  *table = e.dev;
+  g_sched.push_front(std::move(e));
+  return RODEO_OK;
 }
 
 template <typename T>
@@ -125,6 +197,8 @@ const char* rodeo_b200_last_error(void) { return g_err; }
 int rodeo_b200_abi_version(void) { return RODEO_B200_ABI_VERSION; }
 size_t rodeo_b200_problem_sizeof(void) { return sizeof(RodeoProblem); }
 int64_t rodeo_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t rodeo_b200_schedule_builds(void) { return (int64_t)sched_builds(); }
+void rodeo_b200_schedule_clear(void) { sched_clear(); }
 
 size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes) {
   if (!p || (elem_bytes != 8 && elem_bytes != 4)) return 0;

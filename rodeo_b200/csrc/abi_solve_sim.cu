@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "rodeo_host.h"
+#include "rodeo_sched.cuh"
 
 #ifndef RODEO_REAL
 #define RODEO_REAL double
@@ -25,6 +26,47 @@ struct SolveSimRun {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
     pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
     if (p.B == 0) return RODEO_OK;
+    // State-independent interrogations: covariances, gains and factors come from a cached schedule and the kernel
+    // carries the block means only (rodeo_sched.cuh).  interrogate_schober with a per-theta prior scale keeps the full
+    // kernels (singular filtered variance: the sign of a rounding-noise pivot is not scale invariant).
+    if constexpr (INTERR != INTERR_KRAMER) {
+      bool use = !(INTERR == INTERR_SCHOBER && a.r_scale != nullptr);
+      if (const char* e = getenv("RODEO_SIM_SCHEDULE")) use = use && e[0] != '0';
+      if (use) {
+        typedef Sched<real_t, Model, INTERR, QK> SC;
+        struct Key {
+          int tag, model, interr, qk, n_steps, elem;
+          FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
+        } key;
+        memset(&key, 0, sizeof(key));
+        key.tag = 1; key.model = p.model_id; key.interr = INTERR; key.qk = QK; key.n_steps = p.n_steps;
+        key.elem = (int)sizeof(real_t);
+        memcpy(&key.C, &C, sizeof(C));
+        const int N = p.n_steps;
+        auto build = [&](void* t, cudaStream_t st) -> int {
+          sched_forward_kernel<real_t, Model, INTERR, QK><<<1, 32, 0, st>>>(C, N, (real_t*)t);
+          RODEO_CUDA_OK(cudaGetLastError());
+          sched_backward_kernel<real_t, Model, INTERR, QK><<<grid_for((long long)N * Model::NB, 128), 128, 0, st>>>(
+              C, N, (real_t*)t);
+          RODEO_CUDA_OK(cudaGetLastError());
+          g_launches += 2;
+          return RODEO_OK;
+        };
+        const void* tab = nullptr;
+        if (int rc = sched_get(&key, sizeof(key), (size_t)SC::total(N) * sizeof(real_t), build, s, &tab)) return rc;
+        if (x_out != nullptr)
+          solve_sim_sched_kernel<real_t, Model, INTERR, QK, true>
+              <<<grid_for(p.B, 32), 32, SchedSim<real_t, Model, INTERR, QK, true>::SMEM, s>>>(
+                  C, a, (const real_t*)tab, z_smooth, stash, stash_ldb(p.B), x_out, sl);
+        else
+          solve_sim_sched_kernel<real_t, Model, INTERR, QK, false>
+              <<<grid_for(p.B, 32), 32, SchedSim<real_t, Model, INTERR, QK, false>::SMEM, s>>>(
+                  C, a, (const real_t*)tab, z_smooth, stash, stash_ldb(p.B), x_out, sl);
+        g_launches++;
+        RODEO_CUDA_OK(cudaGetLastError());
+        return RODEO_OK;
+      }
+    }
     // (theta, block) lanes shorten the serial chain of a lane by n_block and multiply the warps by n_block, at the price
     // of redundant right-hand-side / Philox work per lane (and 32 % n_block idle lanes).  They win while the launch is
     // latency-bound, i.e. while all of its warps are resident at once; measured on B200 (N = 800 / 4,000):

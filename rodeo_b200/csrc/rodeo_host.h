@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,12 @@ namespace host {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+
+// Schedule cache (abi_common.cu): *table = the device table for `key`, built by `build(table, s)` on first use.
+int sched_get(const void* key, size_t key_bytes, size_t bytes, const std::function<int(void*, cudaStream_t)>& build,
+              cudaStream_t s, const void** table);
+long long sched_builds();
+void sched_clear();
 
 inline int cuda_fail(cudaError_t e, const char* what) {
   set_error("%s: %s", what, cudaGetErrorString(e));

@@ -363,6 +363,7 @@ def test_solve_sim_draws_do_not_depend_on_the_lane_mapping(rb, monkeypatch):
     for name, pr in (("fitzhugh_nagumo", P.fitz_problem(40, n_steps=50, t_max=2.5, seed=61)),
                      ("lorenz63", P.lorenz_problem(23, n_steps=40, t_max=0.2, sigma=1.0, seed=62))):
         out = []
+        monkeypatch.setenv("RODEO_SIM_SCHEDULE", "0")          # the full kernels (tests/test_gpu_schedule.py covers the schedule)
         for force in ("0", "1"):
             monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", force)
             out.append(_np(rb.solve_sim(np.array([3, 4], dtype=np.uint32), getattr(rb.models, name), pr["W"], pr["X0"],
@@ -777,6 +778,7 @@ def test_solve_sim_loglik_fused_equals_the_two_calls(rb):
     common = dict(prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"])
     for lanes in ("0", "1"):
         os.environ["RODEO_SIM_BLOCK_LANES"] = lanes
+        os.environ["RODEO_SIM_SCHEDULE"] = "0"
         try:
             x = rb.solve_sim(key, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, tm, N, chk, **common)
             want = _np(pm.gauss_obs_loglik(x, ind, Y, 0.07))
@@ -787,6 +789,7 @@ def test_solve_sim_loglik_fused_equals_the_two_calls(rb):
                                           **common)
         finally:
             del os.environ["RODEO_SIM_BLOCK_LANES"]
+            del os.environ["RODEO_SIM_SCHEDULE"]
         assert np.array_equal(_np(x2), _np(x)) and np.array_equal(_np(ll2), _np(ll))
         assert ll_err(_np(ll), want) < 1e-12
         assert ll_err(want, orc.gauss_obs_loglik(_np(x), ind, Y, 0.07)) < 1e-12
@@ -884,14 +887,16 @@ def test_fenrir_c4_full_size_subset_against_the_numpy_oracle(rb):
     assert e < TOL
 
 
-@pytest.mark.parametrize("lanes", ["0", "1"])
+@pytest.mark.parametrize("lanes", ["0", "1", "schedule"])
 def test_solve_sim_c5_injected_normals_subset(rb, monkeypatch, lanes):
     """BASELINE configs[4] (C5): FitzHugh-Nagumo solve_sim + interrogate_chkrebtii at N = 800, a 64-theta subset of one
     GPU's 32,768 particles with the SAME standard normals injected into kernel and oracle, for both lane mappings the
     host may pick.  With chkrebtii the measurement noise W S_p W^T keeps every filtered covariance full rank, but the
     smoothing covariance S_f - G (S_f Q^T)^T is formed by cancellation: its factor, hence the draw, is reproducible
-    to ~1e-9 of the state scale between two float64 evaluations, not 1e-10."""
-    monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", lanes)
+    to ~1e-9 of the state scale between two float64 evaluations, not 1e-10.  "schedule": the covariance-schedule kernel
+    the host picks by default for this interrogation (rodeo_sched.cuh); "0" / "1": the full kernels."""
+    monkeypatch.setenv("RODEO_SIM_SCHEDULE", "1" if lanes == "schedule" else "0")
+    monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", "0" if lanes == "schedule" else lanes)
     pr_all = P.fitz_problem(32768, seed=0)
     sub = np.sort(np.random.default_rng(5).choice(32768, 64, replace=False))
     rng = np.random.default_rng(6)
