@@ -904,7 +904,11 @@ RD_DEV void normal_pair_fast(unsigned ru, unsigned ra, float& z0, float& z1) {
   if (e >= 24) { mant = (float)(ru >> (e - 23)) * (1.0f / 8388608.0f); ex = e; }      // mantissa in [1, 2) to 24 bits
   else { mant = (float)ru + 0.5f; ex = 0; }                                           // small ru: exact in float
   const float ln_u = ((float)(ex - 32) + __log2f(mant)) * 0.69314718056f;             // ln(x 2^-32), < 0
-  const float rad = sqrtf(-2.0f * ln_u);
+  // sqrt as x rsqrt(x) (MUFU.RSQ + FMUL, 2 ulp): sqrtf's correctly-rounded fix-up with its slow-path branch is not
+  // needed at the 2^-21 accuracy of this variant.  The approximate log2 may return exactly 1 for a mantissa just below
+  // 2 (u within 2^-24 of 1), i.e. r2 == 0: selected to a zero radius, as sqrtf would give
+  const float r2 = -2.0f * ln_u;
+  const float rad = r2 > 0.0f ? r2 * rsqrtf(r2) : 0.0f;
   const float ang = (float)(ra >> 8) * (6.28318530718f / 16777216.0f);
   float s, c;
   __sincosf(ang, &s, &c);

@@ -265,6 +265,42 @@ RD_DEV void sched_lds(const T* p, T (&r)[CNT]) {
   }
 }
 
+// History of filtered means: entry e (= mu_f[e + 1]) holds ROW values per theta, stored as 2-element vectors with theta
+// innermost -- [entry][pair][theta][2] (+ [entry][theta] for an odd last value) -- so a lane moves two values per
+// instruction and a warp access is one contiguous run (512 B of float64 pairs).
+template <typename T> struct Vec2Of { typedef double2 type; };
+template <> struct Vec2Of<float> { typedef float2 type; };
+template <typename T, int ROW>
+struct SchedHist {
+  static constexpr int NP = ROW / 2;
+  typedef typename Vec2Of<T>::type V2;
+  T* base; i64 ldb, idx;
+  RD_DEV T* entry(int e) const { return base + (i64)e * ROW * ldb; }
+  template <typename MT>
+  RD_DEV void store(int e, const MT (&v)[ROW]) const {
+    T* h = entry(e);
+    RD_UNROLL for (int j = 0; j < NP; ++j) {
+      V2 w; w.x = (T)v[2 * j]; w.y = (T)v[2 * j + 1];
+      reinterpret_cast<V2*>(h)[j * ldb + idx] = w;
+    }
+    if (ROW & 1) h[(i64)NP * 2 * ldb + idx] = (T)v[ROW - 1];
+  }
+  RD_DEV void load(int e, T (&v)[ROW]) const {
+    const T* h = entry(e);
+    RD_UNROLL for (int j = 0; j < NP; ++j) {
+      const V2 w = reinterpret_cast<const V2*>(h)[j * ldb + idx];
+      v[2 * j] = w.x; v[2 * j + 1] = w.y;
+    }
+    if (ROW & 1) v[ROW - 1] = h[(i64)NP * 2 * ldb + idx];
+  }
+  RD_DEV void prefetch(int e) const {
+    const T* h = entry(e);
+    RD_UNROLL for (int j = 0; j < NP; ++j)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const V2*>(h) + j * ldb + idx));
+    if (ROW & 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (i64)NP * 2 * ldb + idx));
+  }
+};
+
 template <typename T, class Model, int INTERR, int QK, bool XOUT>
 struct SchedSim {
   typedef Sched<T, Model, INTERR, QK> SC;
@@ -272,7 +308,7 @@ struct SchedSim {
   static constexpr int K = XOUT ? SC::KOUT : 16;
   static constexpr int OUT_ELEMS = XOUT ? ((K * SC::ROW * SEG_PITCH + 1) & ~1) : 0;   // even: the table chunks stay 16-byte aligned
   static constexpr int BCH_ELEMS = K * SC::NB * SC::BWD;                 // one backward table chunk
-  static constexpr int TAB_ELEMS = 2 * BCH_ELEMS;
+  static constexpr int TAB_ELEMS = (XOUT ? 1 : 2) * BCH_ELEMS;             // XOUT: the next chunk travels during the copy-out
   // forward chunk: what fits the same region, at most 32 steps
   static constexpr int FROW = SC::NB * SC::FWD;
   static constexpr int CHF_RAW = (OUT_ELEMS + TAB_ELEMS) / (2 * FROW);
@@ -308,6 +344,7 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
   MT mu[NB][P];
   RD_UNROLL for (int b = 0; b < NB; ++b)
     RD_UNROLL for (int i = 0; i < P; ++i) mu[b][i] = (MT)x0[b * P + i];
+  const SchedHist<T, ROW> hist{stash, ldb, idx};
 
   // ---- forward: mu_f[n] -> mu_f[n+1]  (solve.py:59-88 with the variances read from the schedule) ----
   auto interr_normals = [&](int n, T (&zc)[NB][JC]) {
@@ -344,11 +381,10 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
       }
       __syncwarp();
       const T* frow = smem + (c & 1) * CHF * FROW;
-      for (int n = n_lo; n < n_hi; ++n) {
+      _Pragma("unroll 1") for (int n = n_lo; n < n_hi; ++n) {
         // the next step's normals do not depend on the state: issued ahead of this step's dependency chain
         T zn[NB][JC];
-        if (n + 1 < N) interr_normals(n + 1, zn);
-        else { RD_UNROLL for (int b = 0; b < NB; ++b) RD_UNROLL for (int j = 0; j < JC; ++j) zn[b][j] = T(0); }
+        interr_normals(n + 1 < N ? n + 1 : N - 1, zn);            // (the last one is generated twice and dropped)
         const MT t = t_next;
         if (Model::USES_TIME) t_next = step_time<MT>(a.t_min, a.t_max, n + 1, N);
         MT mp[NB][P], x[NB][JC], f[NB][M];
@@ -360,7 +396,7 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
             MT acc = mp[b][j];
             if constexpr (SC::DRAW) {
               RD_UNROLL for (int k = 0; k <= j; ++k)
-                acc = rd_fma((MT)r[b][j * (j + 1) / 2 + k] * sq[b], (MT)zc[b][k], acc);
+                acc = rd_fma((MT)r[b][j * (j + 1) / 2 + k], (MT)zc[b][k] * sq[b], acc);
             }
             x[b][j] = acc;
           }
@@ -386,10 +422,11 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
             }
           }
         }
-        if (live && n + 1 < N) {                                  // history entry n+1 = mu_f[n+1]
-          T* h = stash + (i64)n * ROW * ldb + idx;
+        if (live && n + 1 < N) {                                  // history entry n = mu_f[n+1]
+          MT flat[ROW];
           RD_UNROLL for (int b = 0; b < NB; ++b)
-            RD_UNROLL for (int i = 0; i < P; ++i) h[(i64)(b * P + i) * ldb] = (T)mu[b][i];
+            RD_UNROLL for (int i = 0; i < P; ++i) flat[b * P + i] = mu[b][i];
+          hist.store(n, flat);
         }
         RD_UNROLL for (int b = 0; b < NB; ++b)
           RD_UNROLL for (int j = 0; j < JC; ++j) zc[b][j] = zn[b][j];
@@ -419,7 +456,7 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
   auto stage_seg = [&](int j) {
     const int n0 = j * K, cnt = (N - n0) < K ? (N - n0) : K;
     const int lo = (n0 < 1 ? 1 : n0) - 1, hi = n0 + cnt - 2;     // inclusive
-    if (hi >= lo) sched_stage<T, BROW>(btab, lo, hi - lo + 1, tbuf + (j & 1) * SS::BCH_ELEMS, lane);
+    if (hi >= lo) sched_stage<T, BROW>(btab, lo, hi - lo + 1, tbuf + (XOUT ? 0 : (j & 1) * SS::BCH_ELEMS), lane);
     else cp_async_commit();
   };
   const int jtop = (N - 1) / K;
@@ -433,7 +470,7 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
       sched_load<T, SC::BWD>(btab + ((i64)(N - 1) * NB + b) * SC::BWD, r);
       RD_UNROLL for (int i = 0; i < P; ++i) {
         MT acc = mu[b][i];
-        RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)r[P * P + lidx(i, k)] * sq[b], (MT)z[b * P + k], acc);
+        RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)r[P * P + lidx(i, k)], (MT)z[b * P + k] * sq[b], acc);
         x[b][i] = acc;
       }
     }
@@ -450,31 +487,25 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
 
   // mu_f[n] is loaded one row ahead into registers and requested from HBM RODEO_SCHED_PF rows ahead
   T nmu[ROW];
-  auto hload = [&](int n) {
-    if (n >= 1) {
-      const T* h = stash + (i64)(n - 1) * ROW * ldb + idx;
-      RD_UNROLL for (int k = 0; k < ROW; ++k) nmu[k] = h[(i64)k * ldb];
-    }
-  };
-  auto hprefetch = [&](int n) {
-    if (n >= 1) {
-      const T* h = stash + (i64)(n - 1) * ROW * ldb + idx;
-      RD_UNROLL for (int k = 0; k < ROW; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (i64)k * ldb));
-    }
-  };
-  for (int n = N - 2; n > N - 2 - RODEO_SCHED_PF; --n) hprefetch(n);
-  hload(N - 1);
+  // (row indices below 1 are clamped to 1: a redundant load instead of a branch; N == 1 has no history at all)
+  auto hload = [&](int n) { hist.load((n < 1 ? 1 : n) - 1, nmu); };
+  auto hprefetch = [&](int n) { hist.prefetch((n < 1 ? 1 : n) - 1); };
   T z[NB * P];
-  if (N > 1) normals(N - 1, z);
-  else { RD_UNROLL for (int k = 0; k < ROW; ++k) z[k] = T(0); }
+  if (N > 1) {
+    for (int n = N - 2; n > N - 2 - RODEO_SCHED_PF; --n) hprefetch(n);
+    hload(N - 1);
+    normals(N - 1, z);
+  } else {
+    RD_UNROLL for (int k = 0; k < ROW; ++k) { z[k] = T(0); nmu[k] = T(0); }
+  }
   for (int j = jtop; j >= 0; --j) {
     const int n0 = j * K;
     const int cnt = (N - n0) < K ? (N - n0) : K;
-    if (j > 0) { stage_seg(j - 1); cp_async_wait_1(); }
+    if (!XOUT && j > 0) { stage_seg(j - 1); cp_async_wait_1(); }
     else cp_async_wait_all();
     __syncwarp();
-    const T* trow0 = tbuf + (j & 1) * SS::BCH_ELEMS - (i64)((n0 < 1 ? 1 : n0) - 1) * BROW;   // row index n-1 -> trow0 + (n-1) BROW
-    for (int s = cnt - 1; s >= 0; --s) {
+    const T* trow0 = tbuf + (XOUT ? 0 : (j & 1) * SS::BCH_ELEMS) - (i64)((n0 < 1 ? 1 : n0) - 1) * BROW;   // row index n-1 -> trow0 + (n-1) BROW
+    _Pragma("unroll 1") for (int s = cnt - 1; s >= 0; --s) {
       const int n = n0 + s;
       if (n == 0) {                                             // row 0 = ode_init: x0 is known, not sampled
         if constexpr (XOUT)
@@ -488,20 +519,20 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
       hload(n - 1);
       hprefetch(n - 1 - RODEO_SCHED_PF);
       T zn[NB * P];
-      if (n > 1) normals(n - 1, zn);
-      else { RD_UNROLL for (int k = 0; k < ROW; ++k) zn[k] = T(0); }
+      normals(n > 1 ? n - 1 : 1, zn);
       const T* brow = trow0 + (i64)(n - 1) * BROW;
       MT xn[NB][P];
       RD_UNROLL for (int b = 0; b < NB; ++b) {
         T r[SC::BWD];
         sched_lds<T, SC::BWD>(brow + b * SC::BWD, r);
-        MT mp[P];
+        MT mp[P], zs[P];
+        RD_UNROLL for (int k = 0; k < P; ++k) zs[k] = (MT)z[b * P + k] * sq[b];
         sched_predict_mean<T, P, QK, MT>(C.Q[b], mf[b], mp);
         // m = mu_f + G (x' - mu_p) ;  x = m + A z      (standard.py:251-254, solve.py:179)
         RD_UNROLL for (int i = 0; i < P; ++i) {
           MT acc = mf[b][i];
           RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma((MT)r[i * P + jj], x[b][jj] - mp[jj], acc);
-          RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)r[P * P + lidx(i, k)] * sq[b], (MT)z[b * P + k], acc);
+          RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)r[P * P + lidx(i, k)], zs[k], acc);
           xn[b][i] = acc;
         }
       }
@@ -515,6 +546,7 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
     }
     __syncwarp();                                               // table chunk j is free; staged rows are complete
     if constexpr (XOUT) {
+      if (j > 0) stage_seg(j - 1);                              // lands while the rows of segment j are copied out
       // rows n0 .. n0+cnt-1: per theta one contiguous run of cnt*ROW elements, consecutive lanes store consecutive elements
       constexpr int NIT = (K * ROW + 31) / 32;
       const int run = cnt * ROW;
