@@ -47,7 +47,9 @@ enum { RODEO_INTERROGATE_KRAMER = 0, RODEO_INTERROGATE_CHKREBTII = 1, RODEO_INTE
 enum { RODEO_KALMAN_STANDARD = 0, RODEO_KALMAN_SQUARE_ROOT = 1 };
 /* built-in ODE right-hand sides; ids >= RODEO_MODEL_USER_BASE come from rodeo_b200_register_model_nvrtc() */
 enum { RODEO_MODEL_FITZHUGH_NAGUMO = 0, RODEO_MODEL_LORENZ63 = 1, RODEO_MODEL_SECOND_ORDER_SIN = 2,
-       RODEO_MODEL_HES1 = 3, RODEO_MODEL_SEIRAH = 4, RODEO_MODEL_USER_BASE = 1000 };
+       RODEO_MODEL_HES1 = 3, RODEO_MODEL_SEIRAH = 4,
+       RODEO_MODEL_PAIR_ONE_BLOCK = 5,   /* n_bmeas = 2; float64 solve_mv / dalton / fenrir only */
+       RODEO_MODEL_USER_BASE = 1000 };
 /* ops, for rodeo_b200_workspace_bytes() */
 enum { RODEO_OP_SOLVE_MV = 0, RODEO_OP_SOLVE_SIM = 1, RODEO_OP_DALTON = 2, RODEO_OP_FENRIR = 3,
        RODEO_OP_BASIC_GATHER = 4, RODEO_OP_ODE_INIT_PAD = 5 };
@@ -71,7 +73,10 @@ typedef struct RodeoProblem {
   uint32_t key[2];         /* the jax PRNG key (uint32[2]); only sampling paths read it                    */
   double t_min, t_max;
   int32_t user_wcol;       /* user (NVRTC) models only: the ODE is X[:, user_wcol] = f(X, t), i.e. W = e_user_wcol  */
-  int32_t reserved;
+  int32_t prior_batched;   /* nonzero: prior_weight / prior_var of the call are DEVICE arrays (B, n_block, p, p), one prior per
+                            * theta (the reference takes any prior_pars per theta under vmap,
+                            * docs/examples/parameter.md:218-236); float64 solve_mv / solve_sim / dalton / fenrir.
+                            * Zero: HOST arrays (n_block, p, p) shared by every theta (see "Common inputs") */
   /* optional pointer (B, n_block), same arithmetic type as the call, or NULL: per-theta scale of the prior
    * variance, R(theta, b) = prior_var_scale[theta, b] * prior_var[b].  Covers an IBM prior whose sigma is part of
    * theta (sigma^2 R_1, src/rodeo/prior/ibm.py:84-86) without a (B, n_block, p, p) array.  A DEVICE pointer for the

@@ -209,12 +209,28 @@ def _seirah_jac(X, t, th):
     return J
 
 
+def _pair1b_fun(X, t, th):
+    # tests/golden/make_reference_golden.py (pair_one_block): one block, two measured variables (n_bmeas = 2)
+    out = np.empty((X.shape[0], 1, 2))
+    out[:, 0, 0] = -th[:, 0] * X[:, 0, 0] + np.sin(t)
+    out[:, 0, 1] = -th[:, 1] * X[:, 0, 3] * X[:, 0, 3]
+    return out
+
+
+def _pair1b_jac(X, t, th):
+    J = np.zeros((X.shape[0], 1, 2, X.shape[2]))
+    J[:, 0, 0, 0] = -th[:, 0]
+    J[:, 0, 1, 3] = -2 * th[:, 1] * X[:, 0, 3]
+    return J
+
+
 MODELS = {
     "fitzhugh_nagumo": OracleModel("fitzhugh_nagumo", 2, 3, 3, _fn_fun, _fn_jac),
     "lorenz63": OracleModel("lorenz63", 3, 3, 3, _lorenz_fun, _lorenz_jac),
     "second_order_sin": OracleModel("second_order_sin", 1, 4, 2, _so_fun, _so_jac),
     "hes1": OracleModel("hes1", 3, 3, 7, _hes1_fun, _hes1_jac),
     "seirah": OracleModel("seirah", 6, 3, 6, _seirah_fun, _seirah_jac),
+    "pair_one_block": OracleModel("pair_one_block", 1, 6, 3, _pair1b_fun, _pair1b_jac),
 }
 
 

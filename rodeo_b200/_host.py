@@ -108,24 +108,28 @@ class Problem:
         Qh, Rh = prior_from(prior_pars, prior_weight, prior_var)
         Qh, Rh = to_host(Qh), to_host(Rh)
         self.r_scale = None
-        if Rh.ndim == 4:
-            # per-theta prior variance (B, n_block, p, p): supported when it is a per-(theta, block) multiple of a
-            # shared matrix, which is what ibm_init gives when sigma is part of theta (R = sigma^2 R_1)
-            if Qh.ndim == 4:
-                if not np.all(Qh == Qh[:1]):
-                    raise NotImplementedError("per-theta prior_weight (Q) is not supported")
-                Qh = Qh[0]
-            ref = Rh[0]
-            scale = Rh[:, :, -1, -1] / ref[None, :, -1, -1]
-            if not np.allclose(Rh, scale[:, :, None, None] * ref[None], rtol=1e-13, atol=0.0):
-                raise NotImplementedError("per-theta prior_var must be a per-(theta, block) multiple of one matrix "
-                                          "(e.g. ibm_init with a theta-dependent sigma)")
-            self.r_scale_host, Rh = scale, ref
+        self.prior_batch = None
+        if Rh.ndim == 4 or Qh.ndim == 4:
+            # per-theta prior.  When it is a per-(theta, block) multiple of one shared matrix -- what ibm_init gives when
+            # sigma is part of theta (R = sigma^2 R_1) -- the kernels keep the shared matrices in the constant bank and
+            # take one scale per (theta, block).  Any other per-theta (Q, R) (the reference accepts whatever prior_pars
+            # the user vmaps over, docs/examples/parameter.md:218-236) goes to the device as (B, n_block, p, p) arrays.
+            Qb = Qh if Qh.ndim == 4 else np.broadcast_to(Qh, (Rh.shape[0],) + Qh.shape)
+            Rb = Rh if Rh.ndim == 4 else np.broadcast_to(Rh, (Qh.shape[0],) + Rh.shape)
+            ref = Rb[0]
+            with np.errstate(all="ignore"):
+                scale = Rb[:, :, -1, -1] / ref[None, :, -1, -1]
+            if np.all(Qb == Qb[:1]) and np.all(np.isfinite(scale)) and \
+                    np.allclose(Rb, scale[:, :, None, None] * ref[None], rtol=1e-13, atol=0.0):
+                self.r_scale_host, Qh, Rh = scale, Qb[0], ref
+            else:
+                self.prior_batch = (np.ascontiguousarray(Qb), np.ascontiguousarray(Rb))
+                Qh, Rh = Qb[0], Rb[0]
         # the prior is built in float64 on the host (ibm_init) and rounded once to the compute type
         self.Q, self.R = to_host(Qh, npdt), to_host(Rh, npdt)
         if self.Q.shape != (self.nb, self.p, self.p) or self.R.shape != (self.nb, self.p, self.p):
-            raise ValueError(f"prior matrices must have shape {(self.nb, self.p, self.p)}; per-theta priors are "
-                             f"not supported yet (got {self.Q.shape}, {self.R.shape})")
+            raise ValueError(f"prior matrices must have shape {(self.nb, self.p, self.p)} or (B, "
+                             f"{self.nb}, {self.p}, {self.p}) (got {self.Q.shape}, {self.R.shape})")
         extra = set(params) - {"theta"}
         if extra:
             raise TypeError(f"unsupported ODE parameters {sorted(extra)}: device models take `theta` only")
@@ -167,6 +171,17 @@ class Problem:
                 raise ValueError("per-theta prior_var disagrees with the batch size")
             self.r_scale = to_dev(np.broadcast_to(self.r_scale_host, (B, self.nb)).copy(), self.dtype)
             c.prior_var_scale = self.r_scale.data_ptr()
+            self.batched = True
+        if self.prior_batch is not None:
+            Qb, Rb = self.prior_batch
+            if Qb.shape[0] not in (1, B):
+                raise ValueError("per-theta prior disagrees with the batch size")
+            if self.sfx != "f64":
+                raise NotImplementedError("a general per-theta prior is compiled for float64 only")
+            # self.Q / self.R are what the entry points receive: DEVICE arrays (B, n_block, p, p) with prior_batched set
+            self.Q = to_dev(np.broadcast_to(Qb, (B,) + Qb.shape[1:]).copy(), self.dtype)
+            self.R = to_dev(np.broadcast_to(Rb, (B,) + Rb.shape[1:]).copy(), self.dtype)
+            c.prior_batched = 1
             self.batched = True
         self.c = c
         self.lib = _lib.load()

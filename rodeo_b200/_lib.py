@@ -33,7 +33,7 @@ class RodeoProblem(ctypes.Structure):
         ("t_min", ctypes.c_double),
         ("t_max", ctypes.c_double),
         ("user_wcol", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("prior_batched", ctypes.c_int32),
         ("prior_var_scale", ctypes.c_void_p),
     ]
 

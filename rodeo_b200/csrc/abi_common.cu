@@ -211,7 +211,8 @@ size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes)
       // state (KC = 1).  See rodeo_kernels.cuh.
       const int nstate = nstate_of(p->n_block, p->n_bstate);
       // solve_mv of a built-in model with n_block >= 2 runs the (theta, block)-lane kernel, whose segments are longer
-      const bool bl = p->n_block >= 2 && p->model_id < RODEO_MODEL_USER_BASE;
+      // (a per-theta prior runs the one-lane-per-theta kernel)
+      const bool bl = p->n_block >= 2 && p->model_id < RODEO_MODEL_USER_BASE && !p->prior_batched;
       // (solve_sim's one-lane-per-theta kernel keeps only one checkpoint per segment as well, but the (theta, block)-lane
       // kernel the host may pick instead keeps every state: sized for the latter)
       const int KC = (op == RODEO_OP_SOLVE_MV) ? (bl ? seg_len_bl(nstate, p->n_block, elem_bytes) : seg_len(nstate)) : 1;

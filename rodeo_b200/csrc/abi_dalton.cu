@@ -1,6 +1,10 @@
 // rodeo_b200_dalton_f64: batched rodeo.inference.dalton (reference src/rodeo/inference/dalton.py:39-235).
 #include <cstdlib>
 
+#ifndef RODEO_REAL
+#define RODEO_PRIOR_BATCH      /* float64 build: also instantiate the per-theta-prior kernels (QK_DENSE_BATCH) */
+#define RODEO_WIDE_MODELS      /* ... and the n_bmeas = 2 model (rodeo_host.h) */
+#endif
 #include "rodeo_host.h"
 
 // (theta, filter, block) lanes while their grid has at most this many warps per SM sub-partition
@@ -23,13 +27,17 @@ namespace host {
 template <class Model, int INTERR, int QK>
 struct DaltonRun {
   static int run(const RodeoProblem& p, const real_t* W, const real_t* Q, const real_t* R,
-                 const CommonArgs<real_t>& a, const ObsArgs<real_t>& o, real_t* out, cudaStream_t s) {
+                 const CommonArgs<real_t>& a_in, const ObsArgs<real_t>& o, real_t* out, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
-    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
+    // per-theta prior: Q, R are device arrays (B, n_block, p, p) the kernels read per thread; one lane per theta
+    constexpr bool BATCH = QK == QK_DENSE_BATCH;
+    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, BATCH ? nullptr : Q, BATCH ? nullptr : R, C);
+    CommonArgs<real_t> a = a_in;
+    if (BATCH) { a.q_batch = Q; a.r_batch = R; }
     if (p.n_bobs == 2) {
       // two observation rows per block (correlated noise allowed): the stacked (1 + 2)-row update with the reference's
       // eigen-decomposition log-pdf; float64, interrogate_kramer, one thread per (theta, filter)
-      if constexpr (sizeof(real_t) == 8 && INTERR == INTERR_KRAMER && Model::M == 1) {
+      if constexpr (sizeof(real_t) == 8 && INTERR == INTERR_KRAMER && Model::M == 1 && !BATCH) {
         if (p.B == 0) return RODEO_OK;
         CommonArgs<real_t> ag = a;
         ag.dalton_geometry = 2;
@@ -39,7 +47,7 @@ struct DaltonRun {
         RODEO_CUDA_OK(cudaGetLastError());
         return RODEO_OK;
       } else {
-        set_error("dalton: n_bobs=2 is compiled for float64 and interrogate_kramer only");
+        set_error("dalton: n_bobs=2 is compiled for float64, interrogate_kramer and a shared prior only");
         return RODEO_ERR_UNSUPPORTED;
       }
     }
@@ -57,7 +65,7 @@ struct DaltonRun {
       // block lanes: 2,048 thetas 0.146 / 0.138 ms, 4,096: 0.162 / 0.138, 8,192: 0.147 / 0.176, 16,384: 0.243 / 0.310,
       // 65,536: 0.733 / 0.976.  Both kernels return bitwise the same numbers.
       bool block_lanes = false;
-      if constexpr (Model::NB >= 2) {
+      if constexpr (Model::NB >= 2 && !BATCH) {
         // (theta, filter, block) lanes while every warp of theirs still gets an SM sub-partition to itself
         typedef BlockLane<real_t, Model, INTERR, QK> L0;
         block_lanes = 2.0 * grid_for(p.B, L0::TW) <= RODEO_DALTON_BL_BELOW * 4.0 * sm_count();

@@ -1,6 +1,10 @@
 // rodeo_b200_fenrir_f64: batched rodeo.inference.fenrir (reference src/rodeo/inference/fenrir.py:86-328).
 #include <cstdlib>
 
+#ifndef RODEO_REAL
+#define RODEO_PRIOR_BATCH      /* float64 build: also instantiate the per-theta-prior kernels (QK_DENSE_BATCH) */
+#define RODEO_WIDE_MODELS      /* ... and the n_bmeas = 2 model (rodeo_host.h) */
+#endif
 #include "rodeo_host.h"
 
 #ifndef RODEO_REAL
@@ -18,12 +22,16 @@ namespace host {
 template <class Model, int INTERR, int QK>
 struct FenrirRun {
   static int run(const RodeoProblem& p, const real_t* W, const real_t* Q, const real_t* R,
-                 const CommonArgs<real_t>& a, const ObsArgs<real_t>& o, real_t* stash, real_t* out, cudaStream_t s) {
+                 const CommonArgs<real_t>& a_in, const ObsArgs<real_t>& o, real_t* stash, real_t* out, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
-    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
+    // per-theta prior: Q, R are device arrays (B, n_block, p, p) the kernels read per thread; one lane per theta
+    constexpr bool BATCH = QK == QK_DENSE_BATCH;
+    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, BATCH ? nullptr : Q, BATCH ? nullptr : R, C);
+    CommonArgs<real_t> a = a_in;
+    if (BATCH) { a.q_batch = Q; a.r_batch = R; }
     if (p.n_bobs == 2) {
       // two observation rows per block: float64, interrogate_kramer, the one-warp kernel
-      if constexpr (sizeof(real_t) == 8 && INTERR == INTERR_KRAMER) {
+      if constexpr (sizeof(real_t) == 8 && INTERR == INTERR_KRAMER && !BATCH) {
         if (p.B == 0) return RODEO_OK;
         constexpr int SMEM2 = 2 * SegBuf<real_t, Fwd<real_t, Model, INTERR, QK>>::BYTES;
         RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_kernel<real_t, Model, INTERR, QK, 2>,
@@ -33,7 +41,7 @@ struct FenrirRun {
         RODEO_CUDA_OK(cudaGetLastError());
         return RODEO_OK;
       } else {
-        set_error("fenrir: n_bobs=2 is compiled for float64 and interrogate_kramer only");
+        set_error("fenrir: n_bobs=2 is compiled for float64, interrogate_kramer and a shared prior only");
         return RODEO_ERR_UNSUPPORTED;
       }
     }
@@ -45,9 +53,9 @@ struct FenrirRun {
     // warp-specialised backward sweep (rodeo_kernels.cuh) while all of its CTAs are resident at once, i.e. while the
     // one-warp kernel would be bound by a theta's serial chain; measured on B200: second-order ODE, 16,384 thetas x 2,000
     // steps 2.65 -> 2.0-2.2 ms; FitzHugh-Nagumo, 65,536 thetas x 800 steps 3.54 -> 3.64 ms (throughput-bound: not used)
-    bool ws = sizeof(real_t) == 8 && (long long)grid_for(p.B, 32) <= 4LL * sm_count();
+    bool ws = !BATCH && sizeof(real_t) == 8 && (long long)grid_for(p.B, 32) <= 4LL * sm_count();
     if (const char* e = getenv("RODEO_FENRIR_WS")) ws = ws && e[0] == '1';      // tuning / tests
-    if constexpr (sizeof(real_t) == 8) {
+    if constexpr (sizeof(real_t) == 8 && !BATCH) {
       if (ws) {
         constexpr int NSP = Model::P * (Model::P + 1) / 2;
         constexpr int SMEM_WS = 2 * RODEO_FENRIR_NP * Model::NB * (Model::P * Model::P + 2 * Model::P + NSP) * 32 *

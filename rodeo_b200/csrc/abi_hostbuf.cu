@@ -178,6 +178,7 @@ extern "C" int rodeo_b200_dalton_f64_host(const RodeoProblem* p, const double* o
                                           const int32_t* obs_ind, const double* obs_data, const double* obs_weight,
                                           const double* obs_var, double* loglik_out) {
   if (int rc = check_common(p)) return rc;
+  if (p->prior_batched) { set_error("the *_host wrappers take a shared prior (prior_batched must be 0)"); return RODEO_ERR_UNSUPPORTED; }
   if (p->n_obs < 1) { set_error("dalton needs n_obs >= 1"); return RODEO_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(g_arena.mu);
   const int rc = dalton_host_body(p, ode_weight, prior_weight, prior_var, ode_init, theta, obs_ind, obs_data,
@@ -222,6 +223,7 @@ extern "C" int rodeo_b200_solve_mv_f64_host(const RodeoProblem* p, const double*
                                             const double* prior_var, const double* ode_init, const double* theta,
                                             double* mean_out, double* var_out) {
   if (int rc = check_common(p)) return rc;
+  if (p->prior_batched) { set_error("the *_host wrappers take a shared prior (prior_batched must be 0)"); return RODEO_ERR_UNSUPPORTED; }
   std::lock_guard<std::mutex> lk(g_arena.mu);
   const int rc = solve_mv_host_body(p, ode_weight, prior_weight, prior_var, ode_init, theta, mean_out, var_out);
   if (rc != RODEO_OK) g_arena.drain();

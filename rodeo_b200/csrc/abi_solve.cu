@@ -1,5 +1,9 @@
 // rodeo_b200_solve_mv_f64: batched rodeo.solve_mv
 // (reference src/rodeo/solve.py:125-302).
+#ifndef RODEO_REAL
+#define RODEO_PRIOR_BATCH      /* float64 build: also instantiate the per-theta-prior kernels (QK_DENSE_BATCH) */
+#define RODEO_WIDE_MODELS      /* ... and the n_bmeas = 2 model (rodeo_host.h) */
+#endif
 #include "rodeo_host.h"
 
 #ifndef RODEO_REAL
@@ -17,11 +21,15 @@ namespace host {
 template <class Model, int INTERR, int QK>
 struct SolveMvRun {
   static int run(const RodeoProblem& p, const real_t* W, const real_t* Q, const real_t* R,
-                 const CommonArgs<real_t>& a, real_t* stash, real_t* mean_out, real_t* var_out, cudaStream_t s) {
+                 const CommonArgs<real_t>& a_in, real_t* stash, real_t* mean_out, real_t* var_out, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
-    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
+    // per-theta prior: Q, R are device arrays (B, n_block, p, p) the kernels read per thread; one lane per theta
+    constexpr bool BATCH = QK == QK_DENSE_BATCH;
+    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, BATCH ? nullptr : Q, BATCH ? nullptr : R, C);
+    CommonArgs<real_t> a = a_in;
+    if (BATCH) { a.q_batch = Q; a.r_batch = R; }
     if (p.B == 0) return RODEO_OK;
-    if constexpr (Model::NB >= 2) {
+    if constexpr (Model::NB >= 2 && !BATCH) {
       // one lane per (theta, block): fewer thetas per warp => longer contiguous output runs (rodeo_kernels.cuh)
       typedef BlockLane<real_t, Model, INTERR, QK> L;
       RODEO_CUDA_OK(cudaFuncSetAttribute(solve_mv_bl_kernel<real_t, Model, INTERR, QK>,

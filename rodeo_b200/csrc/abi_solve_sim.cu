@@ -2,6 +2,9 @@
 // (reference src/rodeo/solve.py:125-302).
 #include <cstdlib>
 
+#ifndef RODEO_REAL
+#define RODEO_PRIOR_BATCH      /* float64 build: also instantiate the per-theta-prior kernels (QK_DENSE_BATCH) */
+#endif
 #include "rodeo_host.h"
 #include "rodeo_sched.cuh"
 
@@ -21,15 +24,19 @@ namespace host {
 template <class Model, int INTERR, int QK>
 struct SolveSimRun {
   static int run(const RodeoProblem& p, const real_t* W, const real_t* Q, const real_t* R,
-                 const CommonArgs<real_t>& a, const real_t* z_smooth, real_t* stash, real_t* x_out,
+                 const CommonArgs<real_t>& a_in, const real_t* z_smooth, real_t* stash, real_t* x_out,
                  const SimLoglik<real_t>& sl, cudaStream_t s) {
     FilterConsts<real_t, Model::NB, Model::P, Model::M> C;
-    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, Q, R, C);
+    // per-theta prior: Q, R are device arrays (B, n_block, p, p) the kernels read per thread; one lane per theta
+    constexpr bool BATCH = QK == QK_DENSE_BATCH;
+    pack_consts<real_t, Model::NB, Model::P, Model::M>(W, BATCH ? nullptr : Q, BATCH ? nullptr : R, C);
+    CommonArgs<real_t> a = a_in;
+    if (BATCH) { a.q_batch = Q; a.r_batch = R; }
     if (p.B == 0) return RODEO_OK;
     // State-independent interrogations: covariances, gains and factors come from a cached schedule and the kernel
     // carries the block means only (rodeo_sched.cuh).  interrogate_schober with a per-theta prior scale keeps the full
     // kernels (singular filtered variance: the sign of a rounding-noise pivot is not scale invariant).
-    if constexpr (INTERR != INTERR_KRAMER) {
+    if constexpr (INTERR != INTERR_KRAMER && !BATCH) {
       bool use = !(INTERR == INTERR_SCHOBER && a.r_scale != nullptr);
       if (const char* e = getenv("RODEO_SIM_SCHEDULE")) use = use && e[0] != '0';
       if (use) {
@@ -75,7 +82,7 @@ struct SolveSimRun {
     // so: block lanes iff their grid fits the resident slots (n_block 2), half of them (n_block >= 3: 30 of 32 lanes
     // and three redundant Jacobians make its saturated throughput a quarter of the one-theta kernel's).
     bool block_lanes = false;
-    if constexpr (Model::NB >= 2) {
+    if constexpr (Model::NB >= 2 && !BATCH) {
       typedef BlockLane<real_t, Model, INTERR, QK> L;
       constexpr int SMEM_BL = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
       RODEO_CUDA_OK(cudaFuncSetAttribute(solve_sim_bl_kernel<real_t, Model, INTERR, QK>,
@@ -84,7 +91,7 @@ struct SolveSimRun {
       block_lanes = (double)grid_for(p.B, L::TW) <= (Model::NB == 2 ? 1.0 : 0.5) * slots;
       if (const char* e = getenv("RODEO_SIM_BLOCK_LANES")) block_lanes = e[0] == '1';      // tuning experiments
     }
-    if constexpr (Model::NB >= 2) if (block_lanes) {
+    if constexpr (Model::NB >= 2 && !BATCH) if (block_lanes) {
       typedef BlockLane<real_t, Model, INTERR, QK> L;
       constexpr int SMEM = 16 * Model::NB * Model::P * L::PITCH * (int)sizeof(real_t);
       solve_sim_bl_kernel<real_t, Model, INTERR, QK><<<grid_for(p.B, L::TW), 32, SMEM, s>>>(

@@ -24,7 +24,9 @@ namespace rodeo {
 
 // ---- enums shared with the C ABI (include/rodeo_b200.h) -------------------------------------------------
 enum : int { INTERR_KRAMER = 0, INTERR_CHKREBTII = 1, INTERR_SCHOBER = 2, INTERR_RODEO = 3 };
-enum : int { QK_DENSE = 0, QK_UNIT_UPPER = 1 };   // structure of the prior transition matrix Q
+// structure of the prior transition matrix Q.  QK_DENSE_BATCH: dense, and (Q, R) are per-theta DEVICE arrays
+// (B, n_block, p, p) that every thread loads into registers instead of reading the kernel-parameter bank
+enum : int { QK_DENSE = 0, QK_UNIT_UPPER = 1, QK_DENSE_BATCH = 2 };
 
 // packed index of a symmetric PxP matrix, requires i <= j
 template <int P>

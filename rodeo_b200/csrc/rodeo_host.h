@@ -55,8 +55,16 @@ inline int detect_structure(const T* Q, const T* W, int nb, int p, int m, int wc
   return QK_UNIT_UPPER;
 }
 
+// Q == nullptr (batched prior: Q, R are per-theta device arrays the kernels read themselves) packs W only
 template <typename T, int NB, int P, int M>
 inline void pack_consts(const T* W, const T* Q, const T* R, FilterConsts<T, NB, P, M>& C) {
+  if (Q == nullptr || R == nullptr) {
+    memset(&C, 0, sizeof(C));
+    for (int b = 0; b < NB; ++b)
+      for (int r = 0; r < M; ++r)
+        for (int j = 0; j < P; ++j) C.W[b][r][j] = W[(b * M + r) * P + j];
+    return;
+  }
   for (int b = 0; b < NB; ++b) {
     for (int i = 0; i < P; ++i)
       for (int j = 0; j < P; ++j) C.Q[b][i][j] = Q[(b * P + i) * P + j];
@@ -76,6 +84,7 @@ inline CommonArgs<T> make_common(const RodeoProblem& p, const T* ode_init, const
   a.theta = theta; a.ode_init = ode_init; a.key0 = p.key[0]; a.key1 = p.key[1]; a.z_interr = z_interr;
   a.r_scale = (const T*)p.prior_var_scale;
   a.dalton_geometry = 0;
+  a.q_batch = nullptr; a.r_batch = nullptr;
   return a;
 }
 
@@ -90,6 +99,10 @@ inline int check_common(const RodeoProblem* p) {
   if (p->kalman_type != RODEO_KALMAN_STANDARD) {
     // reference src/rodeo/solve.py:236-241 raises NotImplementedError for unknown kalman_type
     set_error("kalman_type %d is not built (only \"standard\")", p->kalman_type);
+    return RODEO_ERR_UNSUPPORTED;
+  }
+  if (p->prior_batched && p->model_id >= RODEO_MODEL_USER_BASE) {
+    set_error("a per-theta prior (prior_batched) is not supported for user (NVRTC) models");
     return RODEO_ERR_UNSUPPORTED;
   }
   return RODEO_OK;
@@ -111,12 +124,37 @@ inline long long stash_ldb(long long B) { return (long long)round_up((size_t)(B 
   X(Hes1, RODEO_MODEL_HES1)                              \
   X(Seirah, RODEO_MODEL_SEIRAH)
 #endif
+// n_bmeas = 2 (one block, two measured variables): instantiated by the translation units that define RODEO_WIDE_MODELS
+// (float64 solve_mv, dalton, fenrir), dense Q / W only
+#if defined(RODEO_WIDE_MODELS) && !defined(RODEO_FAST_BUILD)
+#define RODEO_AOT_MODELS_WIDE(X) X(PairOneBlock, RODEO_MODEL_PAIR_ONE_BLOCK)
+#else
+#define RODEO_AOT_MODELS_WIDE(X)
+#endif
 
 // Calls FN<Model, INTERR, QK>::run(args...) for the runtime (model_id, interr, qk); RODEO_ERR_UNSUPPORTED otherwise.
 template <template <class, int, int> class FN, class Model, int INTERR, typename... A>
 inline int dispatch_qk(int qk, A&&... args) {
+  if constexpr (Model::M != 1) {
+    // vector measurements per block: the dense instantiation only (the structured one needs W = e_wcol, one row)
+    if (qk == QK_DENSE_BATCH) {
+      set_error("a per-theta prior (prior_batched) is compiled for n_bmeas = 1 models only");
+      return RODEO_ERR_UNSUPPORTED;
+    }
+    return FN<Model, INTERR, QK_DENSE>::run(static_cast<A&&>(args)...);
+  } else {
+  if (qk == QK_DENSE_BATCH) {
+#ifdef RODEO_PRIOR_BATCH     /* translation units that instantiate the per-theta-prior kernels */
+    return FN<Model, INTERR, QK_DENSE_BATCH>::run(static_cast<A&&>(args)...);
+#else
+    set_error("a per-theta prior (RodeoProblem.prior_batched) is compiled for the float64 solve_mv, solve_sim, dalton "
+              "and fenrir entry points only");
+    return RODEO_ERR_UNSUPPORTED;
+#endif
+  }
   if (qk == QK_UNIT_UPPER) return FN<Model, INTERR, QK_UNIT_UPPER>::run(static_cast<A&&>(args)...);
   return FN<Model, INTERR, QK_DENSE>::run(static_cast<A&&>(args)...);
+  }
 }
 template <template <class, int, int> class FN, class Model, typename... A>
 inline int dispatch_interr(int interr, int qk, A&&... args) {
@@ -141,10 +179,12 @@ inline int dispatch_model(const RodeoProblem& p, const R* W, const R* Q, A&&... 
       return RODEO_ERR_INVALID;                                                                               \
     }                                                                                                         \
     return dispatch_interr<FN, MODEL>(p.interrogate,                                                          \
+                                      p.prior_batched ? QK_DENSE_BATCH :                                      \
                                       (W && Q) ? detect_structure<R>(Q, W, MODEL::NB, MODEL::P, MODEL::M, \
                                                                           MODEL::WCOL) : QK_DENSE,             \
                                       static_cast<A&&>(args)...);
     RODEO_AOT_MODELS(RODEO_CASE)
+    RODEO_AOT_MODELS_WIDE(RODEO_CASE)
 #undef RODEO_CASE
   }
   set_error("model id %d is not compiled into the library (register it with rodeo_b200_register_model_nvrtc)", p.model_id);

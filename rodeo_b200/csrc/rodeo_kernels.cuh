@@ -39,6 +39,33 @@ struct CommonArgs {
   const T* z_interr;      // optional injected normals for interrogate_chkrebtii, (B, n_steps, NSTREAM, NB, P)
   const T* r_scale;       // optional per-theta scale of the prior variance, (B, NB): R(theta, b) = r_scale * R[b]
   int dalton_geometry;    // dalton_kernel only: how the joint and marginal filters of a theta are laid out (see there)
+  const T* q_batch;       // QK_DENSE_BATCH only: per-theta prior weight / variance, (B, NB, P, P) each -- the reference
+  const T* r_batch;       //   takes any prior_pars per theta under vmap (docs/examples/parameter.md:218-236)
+};
+
+// The filter constants a thread works with: the kernel parameter itself, or (QK_DENSE_BATCH) a register copy whose Q, R
+// are this theta's own rows of the batched prior.
+template <typename T, int NB, int P, int M, int QK>
+struct PriorConsts {
+  const FilterConsts<T, NB, P, M>& C;
+  RD_DEV PriorConsts(const FilterConsts<T, NB, P, M>& Cp, const CommonArgs<T>&, i64) : C(Cp) {}
+};
+template <typename T, int NB, int P, int M>
+struct PriorConsts<T, NB, P, M, QK_DENSE_BATCH> {
+  FilterConsts<T, NB, P, M> C;
+  RD_DEV PriorConsts(const FilterConsts<T, NB, P, M>& Cp, const CommonArgs<T>& a, i64 idx) {
+    const T* q = a.q_batch + idx * (NB * P * P);
+    const T* r = a.r_batch + idx * (NB * P * P);
+    RD_UNROLL for (int b = 0; b < NB; ++b) {
+      RD_UNROLL for (int i = 0; i < P; ++i)
+        RD_UNROLL for (int j = 0; j < P; ++j) {
+          C.Q[b][i][j] = q[(b * P + i) * P + j];
+          if (j >= i) C.R[b][sidx<P>(i, j)] = r[(b * P + i) * P + j];
+        }
+      RD_UNROLL for (int m = 0; m < M; ++m)
+        RD_UNROLL for (int j = 0; j < P; ++j) C.W[b][m][j] = Cp.W[b][m][j];
+    }
+  }
 };
 
 template <typename T>
@@ -454,7 +481,7 @@ struct Fwd {
 //      0 - b + a are both exactly fl(a - b), so the result is bitwise the one of the other geometries (float64 output).
 template <typename T, class Model, int INTERR, int QK, int NOBS>
 __global__ void __launch_bounds__(64, RODEO_DALTON_MINB / 2)
-dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> Cg,
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ loglik) {
   typedef Fwd<T, Model, INTERR, QK> F;
   constexpr int NB = F::NB, P = F::P, M = F::M, JC = F::JC, MS = F::MS;
@@ -467,6 +494,8 @@ dalton_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   i64 idx = geo == 0 ? (tid >> 1) : tid;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;                 // keep the whole warp in the loop for the final shuffle
+  const PriorConsts<T, Model::NB, Model::P, Model::M, QK> pc(Cg, a, idx);
+  const FilterConsts<T, Model::NB, Model::P, Model::M>& C = pc.C;
   typedef typename F::MT MT;
   const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   F f;
@@ -796,7 +825,7 @@ extern __shared__ double rodeo_dyn_smem[];
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32)
-solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> Cg,
                 const CommonArgs<T> a, T* __restrict__ stash, i64 ldb,
                 T* __restrict__ mean_out, T* __restrict__ var_out, const ObsHook<T> oh = ObsHook<T>()) {
   const ObsHook<T>* hook = OBS ? &oh : nullptr;
@@ -807,6 +836,8 @@ solve_mv_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mod
   i64 idx = theta0 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;                 // the whole warp takes part in the cooperative copy-out
+  const PriorConsts<T, Model::NB, Model::P, Model::M, QK> pc(Cg, a, idx);
+  const FilterConsts<T, Model::NB, Model::P, Model::M>& C = pc.C;
   const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
@@ -1627,7 +1658,7 @@ solve_sim_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P,
 #endif
 template <typename T, class Model, int INTERR, int QK, bool OBS = false>
 __global__ void __launch_bounds__(32, Model::NB <= 3 ? RODEO_SIM_T_MINB : 1)
-solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> Cg,
                  const CommonArgs<T> a, const T* __restrict__ z_smooth, T* __restrict__ stash, i64 ldb,
                  T* __restrict__ x_out, const ObsHook<T> oh = ObsHook<T>(), const SimLoglik<T> sl = SimLoglik<T>()) {
   const ObsHook<T>* hook = OBS ? &oh : nullptr;
@@ -1638,6 +1669,8 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   i64 idx = theta0 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;
+  const PriorConsts<T, Model::NB, Model::P, Model::M, QK> pc(Cg, a, idx);
+  const FilterConsts<T, Model::NB, Model::P, Model::M>& C = pc.C;
   const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   Buf buf{reinterpret_cast<T*>(rodeo_dyn_smem), (int)threadIdx.x};
@@ -1742,7 +1775,7 @@ solve_sim_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
 #endif
 template <typename T, class Model, int INTERR, int QK, int NOBS>
 __global__ void __launch_bounds__(32, RODEO_FENRIR_MINB)
-fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> Cg,
               const CommonArgs<T> a, const ObsArgs<T> o, T* __restrict__ stash, i64 ldb,
               T* __restrict__ loglik) {
   typedef Fwd<T, Model, INTERR, QK> F;
@@ -1751,6 +1784,8 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
   i64 idx = (i64)blockIdx.x * 32 + threadIdx.x;
   const bool live = idx < a.B;
   if (!live) idx = a.B - 1;
+  const PriorConsts<T, Model::NB, Model::P, Model::M, QK> pc(Cg, a, idx);
+  const FilterConsts<T, Model::NB, Model::P, Model::M>& C = pc.C;
   const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
   const int N = a.n_steps;
   // two history buffers: while segment j is processed out of one, segment j-1 travels HBM -> shared memory into the

@@ -196,4 +196,27 @@ struct Seirah {
   RD_DEV static void jac(const Par<T>&, T, const T (&)[NB][JCOLS], T (&)[NB][M][JCOLS]) {}
 };
 
+// ---- two uncoupled variables in ONE block (n_bmeas = 2): state (x, x', x'', y, y', y''), x' = -a x + sin t,
+//      y' = -b y^2, theta = (a, b, c) (c unused); W = [[0,1,0,0,0,0],[0,0,0,0,1,0]].  The reference's API allows any
+//      n_bmeas (ode_weight is (n_block, n_bmeas, n_bstate), src/rodeo/solve.py:216-218); this is the instantiation the
+//      n_bmeas = 2 golden vectors pin (tests/golden/make_reference_golden.py, pair_one_block) ------------------------
+struct PairOneBlock {
+  static constexpr int NB = 1, P = 6, M = 2, NTHETA = 3, JCOLS = 4, WCOL = 1;
+  static constexpr bool USES_TIME = true, HAS_JAC = true;
+  template <class T> struct Par { T a, b; };
+  template <class T> RD_DEV static Par<T> load(const T* th) { Par<T> q; q.a = th[0]; q.b = th[1]; return q; }
+  template <class T, class X>
+  RD_DEV static void rhs(const Par<T>& q, T t, const X (&x)[NB][JCOLS], X (&f)[NB][M]) {
+    f[0][0] = -q.a * x[0][0] + sin(t);
+    f[0][1] = -q.b * x[0][3] * x[0][3];
+  }
+  template <class T>
+  RD_DEV static void jac(const Par<T>& q, T, const T (&x)[NB][JCOLS], T (&J)[NB][M][JCOLS]) {
+    RD_UNROLL for (int r = 0; r < M; ++r)
+      RD_UNROLL for (int j = 0; j < JCOLS; ++j) J[0][r][j] = T(0);
+    J[0][0][0] = -q.a;
+    J[0][1][3] = T(-2) * q.b * x[0][3];
+  }
+};
+
 }  // namespace rodeo

@@ -33,8 +33,11 @@ second_order_sin = OdeModel("second_order_sin", 2, 1, 4, 1, 2,
                             wcol=2)
 hes1 = OdeModel("hes1", 3, 3, 3, 1, 7, "log-scale Hes1 (reference examples/timings.py:253-262)")
 seirah = OdeModel("seirah", 4, 6, 3, 1, 6, "SEIRAH (reference examples/timings.py:339-351)")
+pair_one_block = OdeModel("pair_one_block", 5, 1, 6, 2, 3,
+                          "n_bmeas = 2: (x, x', x'', y, y', y'') in one block, x' = -a x + sin t, y' = -b y^2, "
+                          "theta=(a,b,c); float64 solve_mv / dalton / fenrir (tests/golden/make_reference_golden.py)")
 
-BUILTIN = {m.name: m for m in (fitzhugh_nagumo, lorenz63, second_order_sin, hes1, seirah)}
+BUILTIN = {m.name: m for m in (fitzhugh_nagumo, lorenz63, second_order_sin, hes1, seirah, pair_one_block)}
 
 _USER_TEMPLATE = """
 struct UserModel {{

@@ -25,7 +25,7 @@ def solve_mv(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrog
     if kalman_type == "square-root":
         # prior_pars = (Q, cholesky(R)); `var` receives lower-triangular factors, as in the reference
         # (src/rodeo/kalmantv/square_root.py; docs/examples/higher_order.md:108-127)
-        if pb.r_scale is not None:
+        if pb.r_scale is not None or pb.prior_batch is not None:
             raise NotImplementedError('kalman_type="square-root" is compiled for a shared prior only')
         n = pb.lib.rodeo_b200_solve_mv_sqrt_workspace_bytes(ctypes.byref(pb.c))
         ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)

@@ -315,6 +315,71 @@ def build():
     out["fitzsig_mean"], out["fitzsig_var"], out["fitzsig_dalton"] = np.stack(ms_), np.stack(vs_), np.array(ll_)
 
     # ===============================================================================================================
+    # a general per-theta prior: every theta brings its own (Q, R), neither shared nor a multiple of a shared matrix
+    # (the reference takes whatever prior_pars the user's vmap hands it, docs/examples/parameter.md:218-236)
+    # ===============================================================================================================
+    rq = np.random.default_rng(31)
+    Qg = np.repeat(pr["Q"][None], 3, 0).copy()
+    Rg = np.repeat(pr["R"][None], 3, 0).copy()
+    for i in range(3):
+        for b in range(2):
+            Qg[i, b] = Qg[i, b] * (1.0 + 0.05 * rq.standard_normal((3, 3))) + 0.01 * rq.standard_normal((3, 3))
+            Lr = np.linalg.cholesky(Rg[i, b])
+            a_ = 0.3 * rq.standard_normal((3, 3))
+            Rg[i, b] = Lr @ (np.eye(3) + a_ @ a_.T) @ Lr.T
+            Rg[i, b] = 0.5 * (Rg[i, b] + Rg[i, b].T)
+    out["fitzqr_in_Q"], out["fitzqr_in_R"] = Qg, Rg
+    ms_, vs_, ll_, fl_ = [], [], [], []
+    for i in range(3):
+        ci = dict(common, prior_pars=(jnp.array(Qg[i]), jnp.array(Rg[i])))
+        a_ = dict(key=key, ode_init=jnp.array(pr["X0"][i]), interrogate=kramer, theta=jnp.array(pr["theta"][i]))
+        m, v = rodeo.solve_mv(**a_, **ci)
+        ll_.append(float(rodeo.inference.dalton(**a_, **ci, **obs)))
+        fl_.append(float(rodeo.inference.fenrir(**a_, **ci, **obs)))
+        ms_.append(A(m)); vs_.append(A(v))
+    out["fitzqr_mean"], out["fitzqr_var"] = np.stack(ms_), np.stack(vs_)
+    out["fitzqr_dalton"], out["fitzqr_fenrir"] = np.array(ll_), np.array(fl_)
+
+    # ===============================================================================================================
+    # n_bmeas = 2: ONE block that holds two variables, state (x, x', x'', y, y', y''), measurement rows
+    # W = [[0,1,0,0,0,0],[0,0,0,0,1,0]], prior = blockdiag of two IBM priors; x' = -a x + sin t, y' = -b y^2
+    # (theta = (a, b, c)); observations of x only (n_bobs = 1).  The two variables are not coupled: with a coupled pair
+    # (FitzHugh-Nagumo in one block) the reference's covariance-form recursion itself loses the symmetry of its variance
+    # within the 60 steps and its dalton value is NaN, so there is nothing to pin.
+    # ===============================================================================================================
+    def pair_one_block(X, t, **params):
+        a, b, c = params["theta"]
+        return jnp.array([[-a * X[0, 0] + jnp.sin(t), -b * X[0, 3] * X[0, 3]]])
+
+    Q3, R3 = rodeo.prior.ibm_init(dt=3.0 / 60, n_deriv=3, sigma=jnp.array([0.1, 0.1]))
+    Q1b = np.zeros((1, 6, 6)); R1b = np.zeros((1, 6, 6))
+    Q1b[0, :3, :3], Q1b[0, 3:, 3:] = A(Q3)[0], A(Q3)[1]
+    R1b[0, :3, :3], R1b[0, 3:, 3:] = A(R3)[0], A(R3)[1]
+    W1b = np.zeros((1, 2, 6)); W1b[0, 0, 1] = 1.0; W1b[0, 1, 4] = 1.0
+    X01b = np.zeros((3, 1, 6))
+    X01b[:, 0, 0], X01b[:, 0, 3] = 1.0 + 0.1 * np.arange(3), 0.5 - 0.05 * np.arange(3)
+    X01b[:, 0, 1] = -pr["theta"][:, 0] * X01b[:, 0, 0]
+    X01b[:, 0, 4] = -pr["theta"][:, 1] * X01b[:, 0, 3] ** 2
+    ow1b = np.zeros((4, 1, 1, 6)); ow1b[..., 0] = 1.0
+    ob1b = dict(obs_data=ob["obs_data"][:, 0:1, :], obs_times=ob["obs_times"], obs_weight=ow1b,
+                obs_var=ob["obs_var"][:, 0:1])
+    out["pair1b_in_W"], out["pair1b_in_Q"], out["pair1b_in_R"], out["pair1b_in_X0"] = W1b, Q1b, R1b, X01b
+    for k, v in ob1b.items():
+        out["pair1b_in_" + k] = v
+    c1b = dict(ode_fun=pair_one_block, ode_weight=jnp.array(W1b), t_min=0.0, t_max=3.0, n_steps=60,
+               prior_pars=(jnp.array(Q1b), jnp.array(R1b)))
+    o1b = {k: jnp.array(v) for k, v in ob1b.items()}
+    ms_, vs_, ll_, fl_ = [], [], [], []
+    for i in range(3):
+        a_ = dict(key=key, ode_init=jnp.array(X01b[i]), interrogate=kramer, theta=jnp.array(pr["theta"][i]))
+        m, v = rodeo.solve_mv(**a_, **c1b)
+        ll_.append(float(rodeo.inference.dalton(**a_, **c1b, **o1b)))
+        fl_.append(float(rodeo.inference.fenrir(**a_, **c1b, **o1b)))
+        ms_.append(A(m)); vs_.append(A(v))
+    out["pair1b_mean"], out["pair1b_var"] = np.stack(ms_), np.stack(vs_)
+    out["pair1b_dalton"], out["pair1b_fenrir"] = np.array(ll_), np.array(fl_)
+
+    # ===============================================================================================================
     # MAGI log-density (inference/magi.py): trajectories = the kramer posterior means above plus noise, expanded as the
     # ODE prescribes -- FitzHugh-Nagumo (x, f(x, theta), 0), second-order ODE (x, x', sin(w t) - k x, 0).
     # n_active = 1 is the well-conditioned case.  With n_active >= 2 the reference's covariance-form recursion observes

@@ -35,7 +35,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from rodeo_b200 import _lib
     # 2 x int64 + 10 x int32 + 2 x uint32 + 2 x double, naturally aligned
-    # + user_wcol, reserved, prior_var_scale
+    # + user_wcol, prior_batched, prior_var_scale
     assert ctypes.sizeof(_lib.RodeoProblem) == 16 + 40 + 8 + 16 + 8 + 8
 
 

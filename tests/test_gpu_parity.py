@@ -544,10 +544,23 @@ def test_theta_dependent_prior_scale(rb):
     want = orc.dalton(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
                       (Qo, Ro), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
     assert ll_err(_np(ll), want) < 2e-9
-    with pytest.raises(NotImplementedError):
-        bad = Rb.copy(); bad[3, 0, 0, 1] *= 1.5
-        rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(Q, bad),
-                    theta=pr["theta"])
+    # a per-theta prior that is NOT a multiple of one matrix takes the general (B, n_block, p, p) device-array path
+    bad = Ro.copy(); bad[3, 0, 0, 1] *= 1.01; bad[3, 0, 1, 0] = bad[3, 0, 0, 1]
+    m, v = rb.solve_mv(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr, prior_pars=(Q, bad),
+                       theta=pr["theta"])
+    om, ov = orc.solve_mv(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                          (Qo, bad), pr["theta"])
+    assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(v), ov) < TOL
+    ll = rb.inference.dalton(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr,
+                             prior_pars=(Q, bad), theta=pr["theta"], **ob)
+    want = orc.dalton(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                      (Qo, bad), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    assert ll_err(_np(ll), want) < 2e-9
+    fl = rb.inference.fenrir(None, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 10.0, 200, kr,
+                             prior_pars=(Q, bad), theta=pr["theta"], **ob)
+    want = orc.fenrir(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, 10.0, 200, orc.interrogate_kramer,
+                      (Qo, bad), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    assert ll_err(_np(fl), want) < 2e-9
 
 
 # ---- ragged batch sizes and out-of-bounds canaries (compute-sanitizer is closed on this pool) -----------------------------

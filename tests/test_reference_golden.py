@@ -126,6 +126,33 @@ def test_oracle_theta_dependent_prior():
     assert ll_err(orc.dalton(*a, *o), G["fitzsig_dalton"]) < 1e-11
 
 
+def test_oracle_general_per_theta_prior():
+    """every theta brings its own dense (Q, R) -- neither shared nor a multiple of a shared matrix"""
+    a, o = oargs("fitz")
+    a = a[:7] + ((G["fitzqr_in_Q"], G["fitzqr_in_R"]),) + a[8:]
+    m, v = orc.solve_mv(*a)
+    assert P.maxnorm_rel(m, G["fitzqr_mean"]) < 1e-12 and P.maxnorm_rel(v, G["fitzqr_var"]) < 1e-12
+    assert ll_err(orc.dalton(*a, *o), G["fitzqr_dalton"]) < 1e-11
+    assert ll_err(orc.fenrir(*a, *o), G["fitzqr_fenrir"]) < 1e-11
+
+
+def pair1b():
+    pr, _ = prob("fitz")
+    ob = {k: G["pair1b_in_" + k] for k in ("obs_data", "obs_times", "obs_weight", "obs_var")}
+    return {k: G["pair1b_in_" + k] for k in ("W", "X0", "Q", "R")}, pr["theta"], ob
+
+
+def test_oracle_two_measurement_rows_per_block():
+    """n_bmeas = 2: one block holding two variables, ode_weight (1, 2, 6)"""
+    pr, theta, ob = pair1b()
+    a = (orc.MODELS["pair_one_block"], pr["W"], pr["X0"], 0.0, 3.0, 60, orc.interrogate_kramer, (pr["Q"], pr["R"]), theta)
+    o = (ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    m, v = orc.solve_mv(*a)
+    assert P.maxnorm_rel(m, G["pair1b_mean"]) < 1e-12 and P.maxnorm_rel(v, G["pair1b_var"]) < 1e-12
+    assert ll_err(orc.dalton(*a, *o), G["pair1b_dalton"]) < 1e-11
+    assert ll_err(orc.fenrir(*a, *o), G["pair1b_fenrir"]) < 1e-11
+
+
 def test_oracle_magi_logdens():
     pr, _ = prob("fitz")
     pr2, _ = prob("so")
@@ -264,6 +291,49 @@ def test_cuda_theta_dependent_prior(rb):
     m, v = rb.solve_mv(*a, **kw)
     assert P.maxnorm_rel(_np(m), G["fitzsig_mean"]) < TOL and P.maxnorm_rel(_np(v), G["fitzsig_var"]) < TOL
     assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G["fitzsig_dalton"]) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_general_per_theta_prior(rb):
+    """prior_pars = (Q, R) of shape (B, n_block, p, p), arbitrary per theta (what the reference accepts under vmap,
+    docs/examples/parameter.md:218-236): device arrays read per thread (RodeoProblem.prior_batched)."""
+    a, kw, ob = gargs(rb, "fitz")
+    kw = dict(kw, prior_pars=(G["fitzqr_in_Q"], G["fitzqr_in_R"]))
+    m, v = rb.solve_mv(*a, **kw)
+    assert P.maxnorm_rel(_np(m), G["fitzqr_mean"]) < TOL and P.maxnorm_rel(_np(v), G["fitzqr_var"]) < TOL
+    assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G["fitzqr_dalton"]) < TOL
+    assert ll_err(_np(rb.inference.fenrir(*a, **kw, **ob)), G["fitzqr_fenrir"]) < TOL
+    # the same call with the shared prior repeated per theta takes the batched kernels and must reproduce the shared ones
+    pr, _ = prob("fitz")
+    Qp = np.repeat(pr["Q"][None], 3, 0).copy(); Qp[1, 0, 0, 1] += 1e-3         # not a multiple: forces the batched path
+    Rp = np.repeat(pr["R"][None], 3, 0)
+    m2, v2 = rb.solve_mv(*a, **dict(kw, prior_pars=(Qp, Rp)))
+    m0, v0 = rb.solve_mv(*a, **dict(kw, prior_pars=(pr["Q"], pr["R"])))
+    keep = [0, 2]                                                               # thetas whose prior was not perturbed
+    assert P.maxnorm_rel(_np(m2)[keep], _np(m0)[keep]) < 1e-12 and P.maxnorm_rel(_np(v2)[keep], _np(v0)[keep]) < 1e-12
+    x2 = rb.solve_sim(0, *a[1:], **dict(kw, prior_pars=(Qp, Rp)))
+    x0 = rb.solve_sim(0, *a[1:], **dict(kw, prior_pars=(pr["Q"], pr["R"])))
+    assert np.all(np.isfinite(_np(x2))) and P.maxnorm_rel(_np(x2)[keep], _np(x0)[keep]) < 1e-7
+
+
+@pytest.mark.gpu
+def test_cuda_two_measurement_rows_per_block(rb):
+    """n_bmeas = 2 (models.pair_one_block, the dense instantiation with a 2-row measurement update and, on observation
+    steps, the stacked 3-row one) against the reference source's values."""
+    pr, theta, ob = pair1b()
+    kr = rb.interrogate.interrogate_kramer
+    a = (None, rb.models.pair_one_block, pr["W"], pr["X0"], 0.0, 3.0, 60, kr)
+    kw = dict(prior_pars=(pr["Q"], pr["R"]), theta=theta)
+    m, v = rb.solve_mv(*a, **kw)
+    assert P.maxnorm_rel(_np(m), G["pair1b_mean"]) < TOL and P.maxnorm_rel(_np(v), G["pair1b_var"]) < TOL
+    assert ll_err(_np(rb.inference.dalton(*a, **kw, **ob)), G["pair1b_dalton"]) < TOL
+    assert ll_err(_np(rb.inference.fenrir(*a, **kw, **ob)), G["pair1b_fenrir"]) < TOL
+    for name in ("schober", "rodeo"):            # the other interrogations of the 2-row update, against the oracle
+        it = getattr(rb.interrogate, "interrogate_" + name)
+        m, v = rb.solve_mv(None, *a[1:7], it, **kw)
+        om, ov = orc.solve_mv(orc.MODELS["pair_one_block"], pr["W"], pr["X0"], 0.0, 3.0, 60,
+                              getattr(orc, "interrogate_" + name), (pr["Q"], pr["R"]), theta)
+        assert P.maxnorm_rel(_np(m), om) < TOL and P.maxnorm_rel(_np(v), ov) < TOL
 
 
 @pytest.mark.gpu
