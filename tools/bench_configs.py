@@ -36,6 +36,17 @@ def timeit(fn, reps, flush):
     return float(np.median(ts))
 
 
+def cold_ms(fn, lib):
+    """one call with the covariance-schedule cache emptied first: what the first call of a (prior, n_steps) pays"""
+    lib.rodeo_b200_schedule_clear()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out = fn(); e1.record()
+    torch.cuda.synchronize()
+    del out
+    return float(e0.elapsed_time(e1))
+
+
 def run(only="", reps=5, scale=1.0, quiet=False):
     """time the configs named in `only` (comma separated; empty = all float64 ones); returns the list of records"""
     class A:
@@ -118,7 +129,8 @@ def run(only="", reps=5, scale=1.0, quiet=False):
         ms = timeit(f, max(2, args.reps // 2), flush)
         x = f(); fin = bool(torch.isfinite(x).all().item()); del x
         report("C3 Lorenz63 solve_sim chkrebtii (4,096 theta x 16 draws)", B, 4000, ms, 1539.0, 72.0,
-               {"finite": fin, "moved_bytes_per_theta_step": 72.0 + (2 * 72.0 if sched else 2 * 216.0 / 2), "kernel": kname})
+               {"finite": fin, "moved_bytes_per_theta_step": 72.0 + (2 * 72.0 if sched else 2 * 216.0 / 2), "kernel": kname,
+                "first_call_ms_schedule_build_included": cold_ms(f, lib) if sched else None})
         del X0, th; torch.cuda.empty_cache()
     if want("C4"):
         B = int(16384 * sc); pr = P.second_order_problem(B, seed=0); ob = P.second_order_obs(pr)
@@ -138,7 +150,8 @@ def run(only="", reps=5, scale=1.0, quiet=False):
                                         obs_times=ob["obs_times"], noise_sd=0.0707)
         report("C5 FN solve_sim chkrebtii + obs log-lik, fused, no Xt (one GPU's 32,768 of 262,144 particles)", B, 800,
                timeit(f, args.reps, flush), 1035.0, 0.0,
-               {"moved_bytes_per_theta_step": 2 * 48.0 if sched else 2 * 144.0, "kernel": kname})
+               {"moved_bytes_per_theta_step": 2 * 48.0 if sched else 2 * 144.0, "kernel": kname,
+                "first_call_ms_schedule_build_included": cold_ms(f, lib) if sched else None})
     if want("C5x"):
         B = int(32768 * sc); pr = P.fitz_problem(B, seed=0)
         X0, th = D(pr["X0"]), D(pr["theta"])
