@@ -114,7 +114,9 @@ inline long long stash_ldb(long long B) { return (long long)round_up((size_t)(B 
 
 // ---- ahead-of-time instantiation set -----------------------------------------------------------------------------
 // X(ModelType, RODEO_MODEL_id)
-#ifdef RODEO_FAST_BUILD
+#if defined(RODEO_FAST_BUILD) && defined(RODEO_FAST_SECOND_ORDER)      /* development builds: one or two models */
+#define RODEO_AOT_MODELS(X) X(FitzHughNagumo, RODEO_MODEL_FITZHUGH_NAGUMO) X(SecondOrderSin, RODEO_MODEL_SECOND_ORDER_SIN)
+#elif defined(RODEO_FAST_BUILD)
 #define RODEO_AOT_MODELS(X) X(FitzHughNagumo, RODEO_MODEL_FITZHUGH_NAGUMO)
 #else
 #define RODEO_AOT_MODELS(X)                              \

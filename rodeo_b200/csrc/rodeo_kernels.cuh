@@ -268,7 +268,7 @@ struct Fwd {
   // identically.  Forming the cancelled expression directly drops an O(|J mu_p|) rounding term from a residual of
   // size sqrt(S) ~ 1e-3 and is strictly more accurate than evaluating both terms.
   RD_DEV void interrogate(const Consts& C, const Par& q, MT t, const T (&zc)[NB][JC],
-                          T (&jl)[NB][M][JC], MT (&res)[NB][M], T (&V)[NB][MS]) const {
+                          T (&jl)[NB][M][JC], MT (&res)[NB][M], T (&V)[NB][MS], const MT* frc = nullptr) const {
     MT x[NB][JC];
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       if constexpr (INTERR == INTERR_CHKREBTII) {
@@ -288,12 +288,12 @@ struct Fwd {
     MT f[NB][M];
     if constexpr (HAS_J) {
       MT jd[NB][M][JC];
-      eval_f_jac<Model, MT>(q, t, x, f, jd);
+      eval_f_jac<Model, MT>(q, t, x, f, jd, frc);
       RD_UNROLL for (int b = 0; b < NB; ++b)
         RD_UNROLL for (int r = 0; r < M; ++r)
           RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][r][j] = (T)jd[b][r][j];
     } else {
-      Model::template rhs<MT, MT>(q, t, x, f);
+      eval_f<Model, MT>(q, t, x, f, frc);
       RD_UNROLL for (int b = 0; b < NB; ++b)
         RD_UNROLL for (int r = 0; r < M; ++r)
           RD_UNROLL for (int j = 0; j < JC; ++j) jl[b][r][j] = T(0);
@@ -725,7 +725,8 @@ template <typename T, class Model, int INTERR, int QK>
 RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C, const CommonArgs<T>& a,
                          const typename Fwd<T, Model, INTERR, QK>::Par& q, i64 idx, int n,
                          Fwd<T, Model, INTERR, QK>& f, const ObsHook<T>* hook = nullptr,
-                         const typename Fwd<T, Model, INTERR, QK>::MT* t_given = nullptr) {
+                         const typename Fwd<T, Model, INTERR, QK>::MT* t_given = nullptr,
+                         const typename Fwd<T, Model, INTERR, QK>::MT* frc_given = nullptr) {
   typedef Fwd<T, Model, INTERR, QK> F;
   typedef typename F::MT MT;
   constexpr int NB = F::NB, M = F::M, JC = F::JC, MS = F::MS;
@@ -735,7 +736,7 @@ RD_DEV void forward_step(const FilterConsts<T, Model::NB, Model::P, Model::M>& C
   MT res[NB][M];
   f.predict_all(C);
   f.template interr_normals<1>(a, idx, n, 0, zc);
-  f.interrogate(C, q, t, zc, jl, res, V);
+  f.interrogate(C, q, t, zc, jl, res, V, frc_given);
   int io = -1;
   if (hook != nullptr) io = __ldg(hook->step_obs + n);
   if (io >= 0) f.template update_zy<1, false>(C, jl, res, V, hook->o, io, dummy);
@@ -1883,6 +1884,9 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 #ifndef RODEO_FENRIR_NP
 #define RODEO_FENRIR_NP 2
 #endif
+#ifndef RODEO_FENRIR_FCH
+#define RODEO_FENRIR_FCH 16        // steps per chunk of the forcing buffer (models with Forcing<Model>::HAS)
+#endif
 // 4 CTAs per SM (BASELINE configs[3] needs 3.46 to hold its 512 CTAs in one wave): 170 registers at 96 threads.  Without
 // the bound ptxas takes 174 and the launch falls into two waves (measured 3.11 ms instead of 2.01)
 // (models with more than 20 state entries per theta would spill under that bound and keep ptxas's own choice)
@@ -1916,10 +1920,52 @@ fenrir_ws_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   F f;
   F bk;                                                   // backward-filter state (consumer)
   f.load_scale(a, idx);
+  // Models with a state-independent forcing term (Forcing<Model>, rodeo_models.cuh): during the forward sweep the first
+  // producer warp, otherwise idle, evaluates forcing(t_n) -- a double-precision sin with its table loads for the
+  // second-order example, 40 % of the forward warp's time when it computed it itself -- into a shared-memory buffer
+  // behind the ring, NFB chunks of FCH steps.  Measured on BASELINE configs[3]: 2.19 -> 1.95 ms; two helper warps and
+  // four chunks give the same time (the forward warp then waits for 16 % instead of 43 % of the sweep, but the three
+  // warps of a sub-partition share its FP64 pipe and the filter step itself slows down by as much).
+  constexpr bool FRC = Forcing<Model>::HAS;
+  constexpr int FCH = RODEO_FENRIR_FCH, NFB = 2;          // chunk c lives in buffer c % NFB
+  static_assert(NFB <= RING, "the chunk barriers reuse the ring's ids (the ring is idle during the forward sweep)");
+  MT* frc_buf = reinterpret_cast<MT*>(ring + (i64)RING * (NCH + NB * P) * 32);      // [NFB][FCH][32]
+  // chunk barriers: 1 + buffer = "full", 1 + RING + buffer = "consumed"; every arrive is matched by a sync, so the ids are
+  // back in their initial state when the backward sweep starts using them for the ring
+  if constexpr (FRC) {
+    if (warp == 1) {
+      const typename F::Par q1 = load_par<Model, T>(a.theta + idx * Model::NTHETA);
+      for (int c = 0; c * FCH < N; ++c) {
+        if (c >= NFB) bar_sync(1 + RING + c % NFB);                                   // chunk c - NFB has been consumed
+        MT* dst = frc_buf + (c % NFB) * FCH * 32 + lane;
+        for (int s = 0; s < FCH && c * FCH + s < N; ++s)
+          dst[s * 32] = Forcing<Model>::template eval<MT>(q1, step_time<MT>(a.t_min, a.t_max, c * FCH + s, N));
+        bar_arrive(1 + c % NFB);
+      }
+    }
+  }
   if (warp == 0) {
     const typename F::Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
     f.init(a.ode_init + idx * NB * P);
-    forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
+    if constexpr (FRC) {
+      const int nch = (N + FCH - 1) / FCH;
+      MT t_next = step_time<MT>(a.t_min, a.t_max, 0, N);
+      for (int c = 0; c < nch; ++c) {
+        bar_sync(1 + c % NFB);
+        const MT* src = frc_buf + (c % NFB) * FCH * 32 + lane;
+        const int n_hi = (c + 1) * FCH < N ? (c + 1) * FCH : N;
+        for (int n = c * FCH; n < n_hi; ++n) {
+          const MT t_now = t_next;
+          t_next = step_time<MT>(a.t_min, a.t_max, n + 1, N);
+          const MT frc = src[(n - c * FCH) * 32];
+          forward_step<T, Model, INTERR, QK>(C, a, q, idx, n, f, nullptr, &t_now, &frc);
+          if (live && n + 1 < N) ckpt_store<T, F>(stash, ldb, idx, n + 1, f);
+        }
+        if (c + NFB < nch) bar_arrive(1 + RING + c % NFB);
+      }
+    } else {
+      forward_with_checkpoints<T, Model, INTERR, QK, 1>(C, a, q, idx, live, f, stash, ldb);
+    }
     RD_UNROLL for (int b = 0; b < NB; ++b) {
       RD_UNROLL for (int i = 0; i < P; ++i) bk.mu[b][i] = f.mu[b][i];
       RD_UNROLL for (int k = 0; k < NS; ++k) bk.S[b][k] = f.S[b][k];

@@ -151,6 +151,43 @@ struct SecondOrderSin {
   RD_DEV static void jac(const Par<T>& q, T, const T (&)[NB][JCOLS], T (&J)[NB][M][JCOLS]) { J[0][0][0] = -q.k; }
 };
 
+// Optional split of a right-hand side into a state-independent forcing term and the rest, f(X, t) = g(X; forcing(t)):
+// the forcing of step n+1 does not depend on the filter state, so a kernel may form it off the step's dependency chain
+// (fenrir_ws_kernel: an otherwise idle warp computes it ahead into shared memory).  Forcing<Model>::rhs(q, forcing(q, t),
+// x, f) must be the same expression as Model::rhs(q, t, x, f): results stay bitwise identical.
+template <class Model>
+struct Forcing { static constexpr bool HAS = false; };
+template <>
+struct Forcing<SecondOrderSin> {
+  static constexpr bool HAS = true;
+  template <class T> RD_DEV static T eval(const SecondOrderSin::Par<T>& q, T t) { return sin(q.om * t); }
+  template <class T, class X>
+  RD_DEV static void rhs(const SecondOrderSin::Par<T>& q, T frc, const X (&x)[1][1], X (&f)[1][1]) {
+    f[0][0] = frc - q.k * x[0][0];
+  }
+};
+// f and block-diagonal J with the forcing term given (frc != nullptr and the model has one) or not
+template <class Model, typename T>
+RD_DEV void eval_f_jac(const typename Model::template Par<T>& q, T t, const T (&x)[Model::NB][Model::JCOLS],
+                       T (&f)[Model::NB][Model::M], T (&J)[Model::NB][Model::M][Model::JCOLS], const T* frc) {
+  if constexpr (Forcing<Model>::HAS && Model::HAS_JAC) {
+    if (frc != nullptr) {
+      Forcing<Model>::template rhs<T, T>(q, *frc, x, f);
+      Model::template jac<T>(q, t, x, J);
+      return;
+    }
+  }
+  eval_f_jac<Model, T>(q, t, x, f, J);
+}
+template <class Model, typename T>
+RD_DEV void eval_f(const typename Model::template Par<T>& q, T t, const T (&x)[Model::NB][Model::JCOLS],
+                   T (&f)[Model::NB][Model::M], const T* frc) {
+  if constexpr (Forcing<Model>::HAS) {
+    if (frc != nullptr) { Forcing<Model>::template rhs<T, T>(q, *frc, x, f); return; }
+  }
+  Model::template rhs<T, T>(q, t, x, f);
+}
+
 // ---- Hes1 on the log scale  (reference examples/timings.py:253-262; theta = (a..g)) ----------------------------
 struct Hes1 {
   static constexpr int NB = 3, P = 3, M = 1, NTHETA = 7, JCOLS = 1, WCOL = 1;
