@@ -70,3 +70,35 @@ def test_null_problem():
     lib = _lib.load()
     assert lib.rodeo_b200_solve_mv_f64(None, None, None, None, None, None, None, None, None, None, 0, None) == 2
     assert lib.rodeo_b200_workspace_bytes(_lib.OP_SOLVE_MV, None, 8) == 0
+
+
+def test_per_theta_prior_is_refused_where_it_is_not_compiled():
+    """RodeoProblem.prior_batched: float64 solve_mv / solve_sim / dalton / fenrir only; everything else must say so"""
+    lib = _lib.load()
+    ws = ctypes.create_string_buffer(1 << 20)
+    W = np.zeros((2, 1, 3)); W[:, :, 1] = 1
+    Q = np.tile(np.eye(3), (2, 1, 1))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    # user (NVRTC) models: refused by the common checks
+    c = _problem(prior_batched=1, model_id=1000)
+    assert _call_solve_mv(lib, c, ctypes.cast(ws, ctypes.c_void_p), 1 << 20) == 1 and "per-theta prior" in _err(lib)
+    # float32 entry points carry no QK_DENSE_BATCH instantiation
+    c = _problem(prior_batched=1)
+    Wf, Qf = W.astype(np.float32), Q.astype(np.float32)
+    rc = lib.rodeo_b200_solve_mv_f32(ctypes.byref(c), p(Wf), p(Qf), p(Qf), None, None, None, None, None,
+                                     ctypes.cast(ws, ctypes.c_void_p), 1 << 20, None)
+    assert rc == 1 and "per-theta prior" in _err(lib)
+    # the host-buffer wrappers take a shared prior
+    rc = lib.rodeo_b200_solve_mv_f64_host(ctypes.byref(c), p(W), p(Q), p(Q), None, None, None, None)
+    assert rc == 1 and "shared prior" in _err(lib)
+
+
+def test_two_measurement_rows_model_is_compiled_for_the_float64_solvers_only():
+    lib = _lib.load()
+    ws = ctypes.create_string_buffer(1 << 20)
+    c = _problem(model_id=5, n_block=1, n_bstate=6, n_bmeas=2)
+    W = np.zeros((1, 2, 6), np.float32); Q = np.tile(np.eye(6, dtype=np.float32), (1, 1, 1))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.rodeo_b200_solve_mv_f32(ctypes.byref(c), p(W), p(Q), p(Q), None, None, None, None, None,
+                                     ctypes.cast(ws, ctypes.c_void_p), 1 << 20, None)
+    assert rc == 1 and "not compiled" in _err(lib)
