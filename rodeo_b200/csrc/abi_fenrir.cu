@@ -59,7 +59,7 @@ struct FenrirRun {
       if (ws) {
         constexpr int NSP = Model::P * (Model::P + 1) / 2;
         // ring + mu_p region, then the forcing buffer of models with a state-independent forcing term (two chunks)
-        constexpr int SMEM_WS = (2 * RODEO_FENRIR_NP * Model::NB * (Model::P * Model::P + 2 * Model::P + NSP) * 32 +
+        constexpr int SMEM_WS = (RODEO_FENRIR_SL * RODEO_FENRIR_NP * Model::NB * (Model::P * Model::P + 2 * Model::P + NSP) * 32 +
                                  (Forcing<Model>::HAS ? 2 * RODEO_FENRIR_FCH * 32 : 0)) * (int)sizeof(real_t);
         RODEO_CUDA_OK(cudaFuncSetAttribute(fenrir_ws_kernel<real_t, Model, INTERR, QK, 1>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WS));

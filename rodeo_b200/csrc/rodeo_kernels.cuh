@@ -1884,6 +1884,12 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 #ifndef RODEO_FENRIR_NP
 #define RODEO_FENRIR_NP 2
 #endif
+#ifndef RODEO_FENRIR_SL
+#define RODEO_FENRIR_SL 2          // ring slots per producer
+#endif
+#ifndef RODEO_FENRIR_PF
+#define RODEO_FENRIR_PF 2          // history states a producer holds in registers ahead of the one it works on (1 or 2)
+#endif
 #ifndef RODEO_FENRIR_FCH
 #define RODEO_FENRIR_FCH 16        // steps per chunk of the forcing buffer (models with Forcing<Model>::HAS)
 #endif
@@ -1891,7 +1897,7 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 // the bound ptxas takes 174 and the launch falls into two waves (measured 3.11 ms instead of 2.01)
 // (models with more than 20 state entries per theta would spill under that bound and keep ptxas's own choice)
 #ifndef RODEO_FENRIR_WS_MINB
-#define RODEO_FENRIR_WS_MINB(NSTATE) ((RODEO_FENRIR_NP == 2 && (NSTATE) <= 20) ? 4 : 1)
+#define RODEO_FENRIR_WS_MINB(NSTATE) ((RODEO_FENRIR_NP <= 3 && (NSTATE) <= 20) ? 4 : 1)
 #endif
 template <typename T, class Model, int INTERR, int QK, int NOBS>
 __global__ void __launch_bounds__(32 * (1 + RODEO_FENRIR_NP),
@@ -1904,7 +1910,7 @@ fenrir_ws_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
   constexpr int NB = F::NB, P = F::P, NS = F::NS, NSTATE = NB * (P + NS);
   static_assert(sizeof(T) == 8, "the ring stages the means as T: float64 only");
   constexpr int NCH = NB * (P * P + P + NS);             // per theta and step in the ring: A_t, mu_f, C_t per block ...
-  constexpr int NP = RODEO_FENRIR_NP, RING = 2 * NP;     // ... followed by a second region with mu_p: RING * NB * P
+  constexpr int NP = RODEO_FENRIR_NP, SL = RODEO_FENRIR_SL, RING = SL * NP;   // ... followed by a second region with mu_p: RING * NB * P
   static_assert(2 * RING + 1 <= 16, "named barriers");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   i64 idx = (i64)blockIdx.x * 32 + lane;
@@ -1990,25 +1996,32 @@ fenrir_ws_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Mo
         }
       }
     };
-    // software pipeline over this producer's steps: two loads in flight ahead of the step being computed
-    MT nmu[2][NB][P];
-    T nS[2][NB][NS];
+    // software pipeline over this producer's steps: PF loads in flight ahead of the step being computed
+    constexpr int PF = RODEO_FENRIR_PF;
+    static_assert(PF == 1 || PF == 2, "producer prefetch depth");
+    MT nmu[PF][NB][P];
+    T nS[PF][NB][NS];
     int t = N - 1 - pid;
     if (t >= 0) load_filt(t, nmu[0], nS[0]);
-    if (t - NP >= 0) load_filt(t - NP, nmu[1], nS[1]);
+    if (PF == 2 && t - NP >= 0) load_filt(t - NP, nmu[PF - 1], nS[PF - 1]);
     int produced = 0;
     for (; t >= 0; t -= NP) {
-      const int cur = produced & 1;
+      const int cur = PF == 2 ? (produced & 1) : 0;
       RD_UNROLL for (int b = 0; b < NB; ++b) {
-        RD_UNROLL for (int i = 0; i < P; ++i) f.mu[b][i] = cur ? nmu[1][b][i] : nmu[0][b][i];
-        RD_UNROLL for (int k = 0; k < NS; ++k) f.S[b][k] = cur ? nS[1][b][k] : nS[0][b][k];
+        RD_UNROLL for (int i = 0; i < P; ++i) f.mu[b][i] = cur ? nmu[PF - 1][b][i] : nmu[0][b][i];
+        RD_UNROLL for (int k = 0; k < NS; ++k) f.S[b][k] = cur ? nS[PF - 1][b][k] : nS[0][b][k];
       }
-      if (t - 2 * NP >= 0) {                               // refill the buffer just consumed
-        if (cur) load_filt(t - 2 * NP, nmu[1], nS[1]);
-        else load_filt(t - 2 * NP, nmu[0], nS[0]);
+      if (t - PF * NP >= 0) {                              // refill the buffer just consumed
+        if (cur) load_filt(t - PF * NP, nmu[PF - 1], nS[PF - 1]);
+        else load_filt(t - PF * NP, nmu[0], nS[0]);
+      }
+      if (PF == 1 && t - 2 * NP >= 0) {                    // the load after that one: requested into L2
+        const T* sp = stash + (i64)(t - 2 * NP - 1) * NSTATE * ldb + idx;
+        if (t - 2 * NP >= 1)
+          RD_UNROLL for (int k = 0; k < NSTATE; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (i64)k * ldb));
       }
       const int slot = slot_of(t);
-      if (produced >= 2) bar_sync(1 + RING + slot);        // the consumer has released this slot (each producer owns 2)
+      if (produced >= SL) bar_sync(1 + RING + slot);       // the consumer has released this slot (each producer owns SL)
       ++produced;
       T* r = ring + (i64)slot * NCH * 32 + lane;
       RD_UNROLL for (int b = 0; b < NB; ++b) {

@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:dalton_kernel -s 3 -c 1 -f -o gpurun_out/prof_dalton_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 summarise gpurun_out/prof_dalton_$TAG.ncu-rep $((65536*800/32)) gpurun_out/summary_${TAG}_dalton.txt
-for spec in "C1 solve_mv_bl $((65536*800/32))" "C5 solve_sim_bl $((32768*800/32))" "C4 fenrir_ws_kernel $((16384*2000/32))" "C3 solve_sim_kernel $((65536*4000/32))"; do
+for spec in "C1 solve_mv_bl $((65536*800/32))" "C5 solve_sim_sched_kernel $((32768*800/32))" "C4 fenrir_ws_kernel $((16384*2000/32))" "C3 solve_sim_sched_kernel $((65536*4000/32))"; do
   set -- $spec
   C="python tools/bench_configs.py --only $1 --reps 1"
   $C > gpurun_out/plain_${TAG}_$1.log 2>&1 &&
