@@ -20,13 +20,19 @@ def device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def to_dev(x, dtype=_DT):
-    """array-like / numpy / torch (any device) -> contiguous tensor on the current CUDA device"""
+def to_dev(x, dtype=_DT, dev=None):
+    """array-like / numpy / torch (any device) -> contiguous tensor on the current CUDA device (or on `dev`)"""
     if isinstance(x, torch.Tensor):
         t = x
     else:
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
-    return t.to(device=device(), dtype=dtype, non_blocking=True).contiguous()
+    return t.to(device=device() if dev is None else dev, dtype=dtype, non_blocking=True).contiguous()
+
+
+def on_host(*xs):
+    """True when none of the given arrays lives on a CUDA device (NumPy arrays, lists, scalars, CPU tensors, None):
+    such a call can go through the library's host-buffer entry points, which overlap the copies with the kernels."""
+    return not any(isinstance(x, torch.Tensor) and x.is_cuda for x in xs)
 
 
 def to_host(x, dtype=np.float64):
@@ -95,7 +101,9 @@ class Problem:
     """Validated, device-resident inputs of one batched call."""
 
     def __init__(self, key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
-                 prior_weight, prior_var, kalman_type, params, particle_offset=0):
+                 prior_weight, prior_var, kalman_type, params, particle_offset=0, host_inputs=False):
+        # host_inputs: keep theta / ode_init / observation arrays as (zero-copy) CPU tensors for the *_host entry points
+        self.where = torch.device("cpu") if host_inputs else device()
         self.model = _models.resolve(ode_fun)
         self.dtype = real_dtype(params.get("theta"), ode_init)
         self.sfx = "f32" if self.dtype == torch.float32 else "f64"
@@ -138,8 +146,8 @@ class Problem:
             if self.model.n_theta:
                 raise TypeError(f"model {self.model.name} needs theta=({self.model.n_theta},)")
             theta = np.zeros((1, 0))
-        theta = to_dev(theta, self.dtype)
-        x0 = to_dev(ode_init, self.dtype)
+        theta = to_dev(theta, self.dtype, self.where)
+        x0 = to_dev(ode_init, self.dtype, self.where)
         self.batched = theta.ndim == 2 or x0.ndim == 3
         if theta.ndim == 1:
             theta = theta[None]
@@ -169,7 +177,7 @@ class Problem:
         if getattr(self, "r_scale_host", None) is not None:
             if self.r_scale_host.shape[0] not in (1, B):
                 raise ValueError("per-theta prior_var disagrees with the batch size")
-            self.r_scale = to_dev(np.broadcast_to(self.r_scale_host, (B, self.nb)).copy(), self.dtype)
+            self.r_scale = to_dev(np.broadcast_to(self.r_scale_host, (B, self.nb)).copy(), self.dtype, self.where)
             c.prior_var_scale = self.r_scale.data_ptr()
             self.batched = True
         if self.prior_batch is not None:
@@ -195,10 +203,10 @@ class Problem:
         return getattr(self.lib, f"rodeo_b200_{name}_{self.sfx}")
 
     def dev(self, x):
-        return to_dev(x, self.dtype)
+        return to_dev(x, self.dtype, self.where)
 
     def empty(self, *shape):
-        return torch.empty(shape, dtype=self.dtype, device=device())
+        return torch.empty(shape, dtype=self.dtype, device=self.where)
 
     def workspace(self, op):
         n = self.lib.rodeo_b200_workspace_bytes(op, ctypes.byref(self.c), self.esize)
@@ -212,7 +220,7 @@ class Problem:
         ot = obs_times.detach().cpu().numpy() if isinstance(obs_times, torch.Tensor) else np.asarray(obs_times)
         ind = np.searchsorted(sim_times, ot.astype(np.float64)).astype(np.int32)
         self.obs_ind_host = ind
-        self.obs_ind = torch.from_numpy(ind).to(device())
+        self.obs_ind = torch.from_numpy(ind).to(self.where)
         self.c.n_obs = len(ind)
         self.obs_data = self.dev(obs_data)
         if obs_weight is not None:

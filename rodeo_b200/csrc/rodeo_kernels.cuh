@@ -1884,6 +1884,11 @@ fenrir_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model
 #ifndef RODEO_FENRIR_NP
 #define RODEO_FENRIR_NP 2
 #endif
+// Tuning knobs, measured on BASELINE configs[3] with the forcing buffer in place (B200): NP = 2, SL = 2, PF = 2 (the
+// defaults, 168 registers) 1.97 ms; NP = 2, PF = 1 (148 registers) 2.07 ms; NP = 3, SL = 1, PF = 1 (128 registers, 40 B
+// spilled, 4 CTAs of 4 warps per SM) 2.18 ms; NP = 3, SL = 1, PF = 2 (128 registers, 344 B spilled) 2.35 ms.  A third
+// producer does not help although the consumer waits for producers 38 % of the time: the four warps a sub-partition
+// then holds all compete for its one FP64 pipe ("math pipe throttle" is the producers' top stall reason).
 #ifndef RODEO_FENRIR_SL
 #define RODEO_FENRIR_SL 2          // ring slots per producer
 #endif

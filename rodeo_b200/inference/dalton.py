@@ -12,13 +12,32 @@ def dalton(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogat
     r"""DALTON marginal log-likelihood :math:`\log p(Y_{0:M} \mid Z_{1:N})` for Gaussian observations.
 
     Same arguments as the reference; ``theta`` / ``ode_init`` may carry a leading batch axis ``B``.
-    Returns a float64 CUDA tensor of shape ``(B,)`` (a 0-d tensor for an un-batched call).
+    Returns a tensor of shape ``(B,)`` (a 0-d tensor for an un-batched call) where the inputs live: on the CUDA device
+    when ``theta`` / ``ode_init`` / the observation arrays are CUDA tensors; on the host when all of them are host
+    arrays (NumPy, as a user of the reference has them) -- that call goes through ``rodeo_b200_dalton_f64_host``, which
+    cuts the batch in two and sends the second half while the kernel of the first one runs.
     """
+    if kalman_type != "standard":
+        raise NotImplementedError('only kalman_type="standard" is built for the log-likelihood layers')
+    host = _z_interr is None and obs_weight is not None and \
+        _host.on_host(params.get("theta"), ode_init, obs_data, obs_weight, obs_var) and \
+        _host.real_dtype(params.get("theta"), ode_init) == torch.float64
+    if host:
+        hp = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
+                           prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset,
+                           host_inputs=True)
+        if hp.prior_batch is None:                   # (a general per-theta prior takes the device entry point)
+            hp.set_obs(obs_data, obs_times, obs_weight, obs_var)
+            out = hp.empty(hp.B)
+            rc = hp.lib.rodeo_b200_dalton_f64_host(ctypes.byref(hp.c), _host.ptr(hp.W), _host.ptr(hp.Q), _host.ptr(hp.R),
+                                                   _host.ptr(hp.x0), _host.ptr(hp.theta), _host.ptr(hp.obs_ind),
+                                                   _host.ptr(hp.obs_data), _host.ptr(hp.obs_weight),
+                                                   _host.ptr(hp.obs_var), _host.ptr(out))
+            _lib.check(rc, "dalton (host buffers)")
+            return hp.unbatch(out)
     pb = _host.Problem(key, ode_fun, ode_weight, ode_init, t_min, t_max, n_steps, interrogate, prior_pars,
                        prior_weight, prior_var, kalman_type, params, particle_offset=_particle_offset)
     pb.set_obs(obs_data, obs_times, obs_weight, obs_var)
-    if kalman_type != "standard":
-        raise NotImplementedError('only kalman_type="standard" is built for the log-likelihood layers')
     out = pb.empty(pb.B)
     zi = None if _z_interr is None else pb.dev(_z_interr)
     rc = pb.fn("dalton")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R),
