@@ -61,7 +61,32 @@ struct SolveSimRun {
         };
         const void* tab = nullptr;
         if (int rc = sched_get(&key, sizeof(key), (size_t)SC::total(N) * sizeof(real_t), build, s, &tab)) return rc;
-        if (x_out != nullptr)
+        // (theta, block) lanes while their grid fills at most half of the resident slots, i.e. while the launch is
+        // latency-bound (rodeo_sched.cuh).  Measured on B200, FitzHugh-Nagumo N = 800, log-likelihood only, one lane per
+        // theta / per (theta, block): B = 8,192: 0.897 / 0.744 ms, 16,384: 0.914 / 0.824, 32,768: 1.058 / 1.117,
+        // 65,536: 1.60 / 1.90 (every lane repeats the step's Philox call and the right-hand side)
+        bool bl = false;
+        if constexpr (SchedSimBl<real_t, Model, INTERR, QK, false>::OK) {
+          typedef SchedSimBl<real_t, Model, INTERR, QK, false> SB;
+          const double slots = x_out != nullptr
+              ? resident_slots(solve_sim_sched_bl_kernel<real_t, Model, INTERR, QK, true>, 32,
+                               SchedSimBl<real_t, Model, INTERR, QK, true>::SMEM)
+              : resident_slots(solve_sim_sched_bl_kernel<real_t, Model, INTERR, QK, false>, 32, SB::SMEM);
+          bl = (double)grid_for(p.B, SB::TW) <= 0.5 * slots;
+          if (const char* e = getenv("RODEO_SIM_BLOCK_LANES")) bl = e[0] == '1';      // tuning / tests
+          if (bl) {
+            if (x_out != nullptr)
+              solve_sim_sched_bl_kernel<real_t, Model, INTERR, QK, true>
+                  <<<grid_for(p.B, SB::TW), 32, SchedSimBl<real_t, Model, INTERR, QK, true>::SMEM, s>>>(
+                      C, a, (const real_t*)tab, z_smooth, stash, stash_ldb(p.B), x_out, sl);
+            else
+              solve_sim_sched_bl_kernel<real_t, Model, INTERR, QK, false>
+                  <<<grid_for(p.B, SB::TW), 32, SB::SMEM, s>>>(
+                      C, a, (const real_t*)tab, z_smooth, stash, stash_ldb(p.B), x_out, sl);
+          }
+        }
+        if (bl) {
+        } else if (x_out != nullptr)
           solve_sim_sched_kernel<real_t, Model, INTERR, QK, true>
               <<<grid_for(p.B, 32), 32, SchedSim<real_t, Model, INTERR, QK, true>::SMEM, s>>>(
                   C, a, (const real_t*)tab, z_smooth, stash, stash_ldb(p.B), x_out, sl);

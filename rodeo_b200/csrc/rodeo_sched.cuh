@@ -566,4 +566,270 @@ solve_sim_sched_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model:
   if (sl.out != nullptr && live) sl.out[idx] = (T)la.ll;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// solve_sim over a schedule with one lane per (theta, block)
+// ------------------------------------------------------------------------------------------------------------------
+// solve_sim_sched_kernel is latency-bound when the batch does not fill the GPU: most of a step is the Philox /
+// Box-Muller work of its normals, on one dependency chain.  As in solve_sim_bl_kernel the blocks of a theta are spread
+// over lanes (block-major, lane = b * TW + tl, TW = 32 / n_block thetas per warp): the block recursions only meet in the
+// right-hand side, through one shuffle per visible column, so a lane applies the normals of its own block only and the
+// launch has n_block times more warps of a shorter chain.  It pays for small batches only (FitzHugh-Nagumo, N = 800:
+// 8,192 particles 0.90 -> 0.74 ms, 16,384: 0.91 -> 0.82, 32,768: 1.06 -> 1.12): the forward step's single Philox call and
+// the right-hand side are repeated by every lane of a theta, so the host uses it while its grid fills at most half of the
+// resident slots (abi_solve_sim.cu).  Same values in the same order per block: the draws are bitwise those of
+// solve_sim_sched_kernel; the fused log-likelihood sums per block first (as solve_sim_bl_kernel does).  Requires
+// 32 % n_block == 0 (the mean history is laid out per lane).
+template <typename T, class Model, int INTERR, int QK, bool XOUT>
+struct SchedSimBl {
+  typedef Sched<T, Model, INTERR, QK> SC;
+  static constexpr bool OK = SC::NB >= 2 && 32 % SC::NB == 0;
+  static constexpr int TW = 32 / SC::NB, PITCH = TW + 1;
+  static constexpr int KOUT_RAW = RODEO_SCHED_SMEM / (SC::ROW * PITCH * (int)sizeof(T));
+  static constexpr int K = XOUT ? (KOUT_RAW < 1 ? 1 : (KOUT_RAW > 16 ? 16 : KOUT_RAW)) : 16;
+  static constexpr int OUT_ELEMS = XOUT ? ((K * SC::ROW * PITCH + 1) & ~1) : 0;
+  static constexpr int BCH_ELEMS = K * SC::NB * SC::BWD;
+  static constexpr int TAB_ELEMS = (XOUT ? 1 : 2) * BCH_ELEMS;
+  static constexpr int FROW = SC::NB * SC::FWD;
+  static constexpr int CHF_RAW = (OUT_ELEMS + TAB_ELEMS) / (2 * FROW);
+  static constexpr int CHF = CHF_RAW > 32 ? 32 : CHF_RAW;
+  static constexpr int SMEM = (OUT_ELEMS + TAB_ELEMS) * (int)sizeof(T);
+  static_assert(CHF >= 1, "forward chunk");
+};
+
+template <typename T, class Model, int INTERR, int QK, bool XOUT>
+__global__ void __launch_bounds__(32, RODEO_SCHED_MINB)
+solve_sim_sched_bl_kernel(const __grid_constant__ FilterConsts<T, Model::NB, Model::P, Model::M> C,
+                          const CommonArgs<T> a, const T* __restrict__ tab, const T* __restrict__ z_smooth,
+                          T* __restrict__ stash, i64 ldb, T* __restrict__ x_out, const SimLoglik<T> sl) {
+  typedef Sched<T, Model, INTERR, QK> SC;
+  typedef SchedSimBl<T, Model, INTERR, QK, XOUT> SS;
+  typedef typename MeanOf<T>::type MT;
+  typedef typename Model::template Par<MT> Par;
+  constexpr int NB = SC::NB, P = SC::P, M = SC::M, JC = SC::JC, WK = SC::WK, ROW = SC::ROW, K = SS::K;
+  constexpr int TW = SS::TW, PITCH = SS::PITCH;
+  static_assert(SS::OK, "block lanes need 32 % n_block == 0");
+  const int lane = threadIdx.x;
+  const int b = lane / TW, tl = lane - b * TW;              // block-major lanes: every lane is a (theta, block)
+  const i64 theta0 = (i64)blockIdx.x * TW;
+  i64 idx = theta0 + tl;
+  const bool live = idx < a.B;
+  if (!live) idx = a.B - 1;
+  const Par q = load_par<Model, T>(a.theta + idx * Model::NTHETA);
+  const int N = a.n_steps;
+  T* smem = reinterpret_cast<T*>(rodeo_dyn_smem);
+  const T* x0 = a.ode_init + idx * ROW + b * P;
+
+  // this lane's block of the shared constants, in registers (the constant bank cannot be indexed per lane)
+  T Q[P][P], W[M][P];
+  RD_UNROLL for (int c = 0; c < NB; ++c)
+    if (c == b) {
+      RD_UNROLL for (int i = 0; i < P; ++i)
+        RD_UNROLL for (int j = 0; j < P; ++j) Q[i][j] = C.Q[c][i][j];
+      RD_UNROLL for (int r = 0; r < M; ++r)
+        RD_UNROLL for (int j = 0; j < P; ++j) W[r][j] = C.W[c][r][j];
+    }
+  const MT sq = a.r_scale != nullptr ? sqrt((MT)a.r_scale[idx * NB + b]) : MT(1);
+
+  MT mu[P];
+  RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = (MT)x0[i];
+  // mean history per lane: P values per entry, lane-global index (32 lanes per warp: NB * ldb lanes in all)
+  const SchedHist<T, P> hist{stash, (i64)NB * ldb, (i64)blockIdx.x * 32 + lane};
+
+  // ---- forward ----
+  auto interr_normals = [&](int n, T (&zc)[JC]) {
+    if constexpr (SC::DRAW) {
+      if (a.z_interr != nullptr) {
+        const T* z = a.z_interr + (idx * a.n_steps + n) * (NB * P) + b * P;
+        RD_UNROLL for (int j = 0; j < JC; ++j) zc[j] = z[j];
+      } else {
+        // the same stream layout as the one-lane-per-theta kernels: normal b*JC + j of the step's vector
+        philox_normal_range<T, JC>(a.key0, a.key1, a.particle_offset + idx, n, TAG_INTERR_A, b * JC, zc);
+      }
+    } else {
+      RD_UNROLL for (int j = 0; j < JC; ++j) zc[j] = T(0);
+    }
+  };
+  {
+    constexpr int CHF = SS::CHF, FROW = SS::FROW;
+    T zc[JC];
+    interr_normals(0, zc);
+    MT t_next = Model::USES_TIME ? step_time<MT>(a.t_min, a.t_max, 0, N) : MT(0);
+    const int nch = (N + CHF - 1) / CHF;
+    sched_stage<T, FROW>(tab, 0, N < CHF ? N : CHF, smem, lane);
+    for (int c = 0; c < nch; ++c) {
+      const int n_lo = c * CHF, n_hi = (n_lo + CHF) < N ? (n_lo + CHF) : N;
+      if (c + 1 < nch) {
+        sched_stage<T, FROW>(tab, n_hi, (n_hi + CHF) < N ? CHF : (N - n_hi), smem + ((c + 1) & 1) * CHF * FROW, lane);
+        cp_async_wait_1();
+      } else {
+        cp_async_wait_all();
+      }
+      __syncwarp();
+      const T* frow = smem + (c & 1) * CHF * FROW + b * SC::FWD;
+      _Pragma("unroll 1") for (int n = n_lo; n < n_hi; ++n) {
+        T zn[JC];
+        interr_normals(n + 1 < N ? n + 1 : N - 1, zn);
+        const MT t = t_next;
+        if (Model::USES_TIME) t_next = step_time<MT>(a.t_min, a.t_max, n + 1, N);
+        MT mp[P], xo[JC], x[NB][JC], f[NB][M];
+        T r[SC::FWD];
+        sched_lds<T, SC::FWD>(frow, r);
+        frow += FROW;
+        sched_predict_mean<T, P, QK, MT>(Q, mu, mp);
+        RD_UNROLL for (int j = 0; j < JC; ++j) {
+          MT acc = mp[j];
+          if constexpr (SC::DRAW) {
+            RD_UNROLL for (int k = 0; k <= j; ++k) acc = rd_fma((MT)r[j * (j + 1) / 2 + k], (MT)zc[k] * sq, acc);
+          }
+          xo[j] = acc;
+        }
+        RD_UNROLL for (int c2 = 0; c2 < NB; ++c2)
+          RD_UNROLL for (int j = 0; j < JC; ++j) x[c2][j] = __shfl_sync(0xffffffffu, xo[j], c2 * TW + tl);
+        Model::template rhs<MT, MT>(q, t, x, f);
+        MT fo[M];
+        RD_UNROLL for (int rr = 0; rr < M; ++rr) {
+          fo[rr] = f[0][rr];
+          RD_UNROLL for (int c2 = 1; c2 < NB; ++c2) fo[rr] = (b == c2) ? f[c2][rr] : fo[rr];
+        }
+        if constexpr (SC::UNITW) {
+          const MT res = sub_exact(fo[0], mp[WK]);
+          const MT g = res * (MT)r[SC::NFA + P];
+          RD_UNROLL for (int i = 0; i < P; ++i) mu[i] = rd_fma((MT)r[SC::NFA + i], g, mp[i]);
+        } else {
+          MT res[M];
+          RD_UNROLL for (int rr = 0; rr < M; ++rr) {
+            MT acc = fo[rr];
+            RD_UNROLL for (int j = 0; j < P; ++j) acc = rd_fma(-(MT)W[rr][j], mp[j], acc);
+            res[rr] = acc;
+          }
+          RD_UNROLL for (int i = 0; i < P; ++i) {
+            MT m = mp[i];
+            RD_UNROLL for (int rr = 0; rr < M; ++rr) m = rd_fma((MT)r[SC::NFA + rr * P + i], res[rr], m);
+            mu[i] = m;
+          }
+        }
+        if (live && n + 1 < N) hist.store(n, mu);                 // history entry n = mu_f[n+1]
+        RD_UNROLL for (int j = 0; j < JC; ++j) zc[j] = zn[j];
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- backward ----
+  auto normals = [&](int n, T (&z)[P]) {
+    if (z_smooth != nullptr) {
+      const T* zp = z_smooth + (idx * (i64)(N + 1) + n) * ROW + b * P;
+      RD_UNROLL for (int k = 0; k < P; ++k) z[k] = zp[k];
+    } else {
+      philox_normals<T, P>(a.key0, a.key1, a.particle_offset + idx, n, TAG_SMOOTH, z, b * ((P + 3) / 4));
+    }
+  };
+  constexpr int BROW = NB * SC::BWD;
+  const T* btab = tab + SC::bwd_off(N);
+  T* tbuf = smem + SS::OUT_ELEMS;
+  T* buf = smem;
+  auto stage_seg = [&](int j) {
+    const int n0 = j * K, cnt = (N - n0) < K ? (N - n0) : K;
+    const int lo = (n0 < 1 ? 1 : n0) - 1, hi = n0 + cnt - 2;
+    if (hi >= lo) sched_stage<T, BROW>(btab, lo, hi - lo + 1, tbuf + (XOUT ? 0 : (j & 1) * SS::BCH_ELEMS), lane);
+    else cp_async_commit();
+  };
+  const int jtop = (N - 1) / K;
+  stage_seg(jtop);
+  MT x[P];
+  {                                                             // terminal draw from N(mu_f[N], S_f[N])
+    T z[P], r[SC::BWD];
+    normals(N, z);
+    sched_load<T, SC::BWD>(btab + ((i64)(N - 1) * NB + b) * SC::BWD, r);
+    RD_UNROLL for (int i = 0; i < P; ++i) {
+      MT acc = mu[i];
+      RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)r[P * P + lidx(i, k)], (MT)z[k] * sq, acc);
+      x[i] = acc;
+    }
+    if (live && x_out != nullptr) {
+      T* dst = x_out + (idx * (i64)(N + 1) + N) * ROW + b * P;
+      RD_UNROLL for (int i = 0; i < P; ++i) dst[i] = (T)x[i];
+    }
+  }
+  SimLoglikAcc<T, MT> la;
+  la.init(sl, N + 1);
+  la.row(sl, N, NB, b, b + 1, [&](int) { return x[0]; });
+
+  T nmu[P];
+  auto hload = [&](int n) { hist.load((n < 1 ? 1 : n) - 1, nmu); };
+  auto hprefetch = [&](int n) { hist.prefetch((n < 1 ? 1 : n) - 1); };
+  T z[P];
+  if (N > 1) {
+    for (int n = N - 2; n > N - 2 - RODEO_SCHED_PF; --n) hprefetch(n);
+    hload(N - 1);
+    normals(N - 1, z);
+  } else {
+    RD_UNROLL for (int k = 0; k < P; ++k) { z[k] = T(0); nmu[k] = T(0); }
+  }
+  for (int j = jtop; j >= 0; --j) {
+    const int n0 = j * K;
+    const int cnt = (N - n0) < K ? (N - n0) : K;
+    if (!XOUT && j > 0) { stage_seg(j - 1); cp_async_wait_1(); }
+    else cp_async_wait_all();
+    __syncwarp();
+    const T* trow0 = tbuf + (XOUT ? 0 : (j & 1) * SS::BCH_ELEMS) - (i64)((n0 < 1 ? 1 : n0) - 1) * BROW + b * SC::BWD;
+    _Pragma("unroll 1") for (int s = cnt - 1; s >= 0; --s) {
+      const int n = n0 + s;
+      if (n == 0) {                                             // row 0 = ode_init: known, not sampled
+        if constexpr (XOUT)
+          RD_UNROLL for (int k = 0; k < P; ++k) buf[(s * ROW + b * P + k) * PITCH + tl] = x0[k];
+        la.row(sl, 0, NB, b, b + 1, [&](int) { return (MT)x0[0]; });
+        break;
+      }
+      MT mf[P];
+      RD_UNROLL for (int i = 0; i < P; ++i) mf[i] = (MT)nmu[i];
+      hload(n - 1);
+      hprefetch(n - 1 - RODEO_SCHED_PF);
+      T zn[P];
+      normals(n > 1 ? n - 1 : 1, zn);
+      T r[SC::BWD];
+      sched_lds<T, SC::BWD>(trow0 + (i64)(n - 1) * BROW, r);
+      MT mp[P], zs[P], xn[P];
+      RD_UNROLL for (int k = 0; k < P; ++k) zs[k] = (MT)z[k] * sq;
+      sched_predict_mean<T, P, QK, MT>(Q, mf, mp);
+      RD_UNROLL for (int i = 0; i < P; ++i) {
+        MT acc = mf[i];
+        RD_UNROLL for (int jj = 0; jj < P; ++jj) acc = rd_fma((MT)r[i * P + jj], x[jj] - mp[jj], acc);
+        RD_UNROLL for (int k = 0; k <= i; ++k) acc = rd_fma((MT)r[P * P + lidx(i, k)], zs[k], acc);
+        xn[i] = acc;
+      }
+      RD_UNROLL for (int i = 0; i < P; ++i) {
+        x[i] = xn[i];
+        if constexpr (XOUT) buf[(s * ROW + b * P + i) * PITCH + tl] = (T)xn[i];
+      }
+      RD_UNROLL for (int k = 0; k < P; ++k) z[k] = zn[k];
+      la.row(sl, n, NB, b, b + 1, [&](int) { return x[0]; });
+    }
+    __syncwarp();
+    if constexpr (XOUT) {
+      if (j > 0) stage_seg(j - 1);
+      constexpr int NIT = (K * ROW + 31) / 32;
+      const int run = cnt * ROW;
+      const i64 stride = (i64)(N + 1) * ROW;
+      T* dst = x_out + (theta0 * (i64)(N + 1) + n0) * ROW + lane;
+      const int nth = (a.B - theta0) < TW ? (int)(a.B - theta0) : TW;
+      RD_UNROLL4 for (int th = 0; th < nth; ++th) {
+        RD_UNROLL for (int it = 0; it < NIT; ++it) {
+          const int rr = lane + 32 * it;
+          if (rr < run) dst[32 * it] = buf[rr * PITCH + th];
+        }
+        dst += stride;
+      }
+      __syncwarp();
+    }
+  }
+  if (sl.out != nullptr) {
+    // sum the blocks of a theta in block order (lane c * TW + tl holds block c), as solve_sim_bl_kernel does
+    MT tot = MT(0);
+    RD_UNROLL for (int c = 0; c < NB; ++c) tot += __shfl_sync(0xffffffffu, la.ll, c * TW + tl);
+    if (live && b == 0) sl.out[idx] = (T)tot;
+  }
+}
+
 }  // namespace rodeo

@@ -133,4 +133,7 @@ def sharded_loglik(loglik_fn, theta, ode_init, group=None):
         rank, world = 0, 1
     lo, hi = shard_bounds(len(theta), rank, world)
     local = loglik_fn(theta[lo:hi], ode_init[lo:hi], lo)
+    # a log-likelihood of host arrays comes back on the host (rodeo_b200.inference.dalton): NCCL gathers device tensors
+    if world > 1 and dist.get_backend(group) == "nccl" and not local.is_cuda:
+        local = local.to(torch.device("cuda", torch.cuda.current_device()))
     return all_gather_loglik(local, len(theta), group)

@@ -34,7 +34,8 @@ def main():
 
     full = parallel.sharded_loglik(loglik, pr["theta"], pr["X0"])         # all-gather with padding (uneven shards)
     alone = loglik(pr["theta"], pr["X0"], 0)                              # this GPU, the whole batch
-    assert full.shape == (B,) and torch.equal(full, alone), "sharded != unsharded"
+    assert full.is_cuda and not alone.is_cuda        # host arrays in: the unsharded result comes back on the host
+    assert full.shape == (B,) and torch.equal(full.cpu(), alone), "sharded != unsharded"
     want = orc.dalton(orc.MODELS["fitzhugh_nagumo"], pr["W"], pr["X0"], 0.0, tm, N, orc.interrogate_kramer,
                       (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
     err = np.max(np.abs(full.cpu().numpy() - want) / np.maximum(1, np.abs(want)))
@@ -45,7 +46,7 @@ def main():
     pr2 = P.fitz_problem(Be, n_steps=N, t_max=tm, seed=52)
     lo, hi = parallel.shard_bounds(Be, rank, world)
     pipe = parallel.GatherPipeline(hi - lo, dev)
-    ref = loglik(pr2["theta"], pr2["X0"], 0)
+    ref = loglik(pr2["theta"], pr2["X0"], 0).to(dev)
     slots = []
     for k in range(3):
         buf = pipe.local_buffer()

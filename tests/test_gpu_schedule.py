@@ -42,9 +42,10 @@ def _problem(name, B):
     return P.second_order_problem(B, n_steps=64, t_max=1.0, sigma=0.1, seed=73)
 
 
-def _both(monkeypatch, fn):
-    """fn() through the full kernels (one lane per theta) and through the schedule"""
-    monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", "0")
+def _both(monkeypatch, fn, lanes="0"):
+    """fn() through the full kernels and through the schedule, both with one lane per theta (lanes = "0") or one lane
+    per (theta, block) where the model allows it (lanes = "1")"""
+    monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", lanes)
     monkeypatch.setenv("RODEO_SIM_SCHEDULE", "0")
     full = fn()
     monkeypatch.setenv("RODEO_SIM_SCHEDULE", "1")
@@ -52,17 +53,21 @@ def _both(monkeypatch, fn):
     return full, sched
 
 
+@pytest.mark.parametrize("lanes", ["0", "1"])
 @pytest.mark.parametrize("interr", ["chkrebtii", "schober", "rodeo"])
 @pytest.mark.parametrize("model,B", [("fitzhugh_nagumo", 40), ("lorenz63", 23), ("second_order_sin", 33),
                                      ("fitzhugh_nagumo", 1)])
-def test_schedule_draws_are_bitwise_the_full_kernels(rb, monkeypatch, model, B, interr):
+def test_schedule_draws_are_bitwise_the_full_kernels(rb, monkeypatch, model, B, interr, lanes):
     pr = _problem(model, B)
     key = np.array([11, 5], dtype=np.uint32)
     run = lambda: _np(rb.solve_sim(key, getattr(rb.models, model), pr["W"], pr["X0"], 0.0, pr["t_max"], pr["n_steps"],
                                    _interr(rb, interr), prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"]))
-    full, sched = _both(monkeypatch, run)
+    full, sched = _both(monkeypatch, run, lanes)
     assert np.isfinite(full).all() and np.array_equal(sched[:, 0], pr["X0"])
     assert np.array_equal(full, sched)
+    if lanes == "1":                                   # ... and the lane mapping does not change a single bit either
+        monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", "0")
+        assert np.array_equal(run(), sched)
 
 
 def test_schedule_injected_normals_bitwise_and_against_the_oracle(rb, monkeypatch):
@@ -123,7 +128,8 @@ def test_schedule_with_a_per_theta_prior_scale(rb, monkeypatch):
     assert P.maxnorm_rel(x, want) < 1e-8
 
 
-def test_schedule_fused_loglik(rb, monkeypatch):
+@pytest.mark.parametrize("lanes", ["0", "1"])
+def test_schedule_fused_loglik(rb, monkeypatch, lanes):
     N, tm, B = 160, 8.0, 77
     pr = P.fitz_problem(B, n_steps=N, t_max=tm, seed=37)
     ob = P.fitz_obs(pr, None, n_obs=9)
@@ -131,7 +137,7 @@ def test_schedule_fused_loglik(rb, monkeypatch):
     key = np.array([3, 9], dtype=np.uint32)
     args = (key, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, tm, N, _interr(rb, "chkrebtii"))
     kw = dict(prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"], obs_data=Y, obs_times=ob["obs_times"], noise_sd=0.07)
-    full, sched = _both(monkeypatch, lambda: _np(rb.solve_sim_loglik(*args, **kw)))
+    full, sched = _both(monkeypatch, lambda: _np(rb.solve_sim_loglik(*args, **kw)), lanes)
     assert np.array_equal(full, sched)
     ll2, x2 = rb.solve_sim_loglik(*args, return_draws=True, **kw)
     assert np.array_equal(_np(ll2), sched)
