@@ -520,6 +520,38 @@ def test_float32_solve_mv_and_dalton(rb):
     assert ll.dtype == torch.float32 and e < 1e-5
 
 
+def test_float32_fenrir_and_solve_sim(rb):
+    """The float32 fenrir log-likelihood and the float32 solve_sim draws (injected normals) against the FLOAT64 oracle,
+    at BASELINE's float32 gate of 1e-5 (measured: fenrir 9.8e-8, draws 4.9e-6 -- means and residuals are carried in
+    double, only covariances / gains / factors in float)."""
+    import torch
+    kr = rb.interrogate.interrogate_kramer
+    pr = P.fitz_problem(64, n_steps=200, t_max=10.0, seed=33)
+    ob = P.fitz_obs(pr, None, n_obs=11)
+    th32, X32 = pr["theta"].astype(np.float32), pr["X0"].astype(np.float32)
+    ll = rb.inference.fenrir(None, rb.models.fitzhugh_nagumo, pr["W"], X32, 0.0, 10.0, 200, kr,
+                             prior_pars=(pr["Q"], pr["R"]), theta=th32, **ob)
+    want = orc.fenrir(orc.MODELS["fitzhugh_nagumo"], pr["W"], X32.astype(np.float64), 0.0, 10.0, 200,
+                      orc.interrogate_kramer, (pr["Q"], pr["R"]), th32.astype(np.float64), ob["obs_data"],
+                      ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    e = ll_err(_np(ll).astype(np.float64), want)
+    print(f"float32 fenrir: {e:.2e}")
+    assert ll.dtype == torch.float32 and np.isfinite(_np(ll)).all() and e < 1e-5
+    # solve_sim, float32, the same standard normals as the oracle (kramer: the full kernels)
+    N = 120
+    pr = P.fitz_problem(24, n_steps=N, t_max=6.0, seed=34)
+    th32, X32 = pr["theta"].astype(np.float32), pr["X0"].astype(np.float32)
+    zs = np.random.default_rng(8).standard_normal((24, N + 1, 2, 3))
+    x = rb.solve_sim(0, rb.models.fitzhugh_nagumo, pr["W"], X32, 0.0, 6.0, N, kr, prior_pars=(pr["Q"], pr["R"]),
+                     theta=th32, _z_smooth=zs.astype(np.float32))
+    want = orc.solve_sim(orc.MODELS["fitzhugh_nagumo"], pr["W"], X32.astype(np.float64), 0.0, 6.0, N,
+                         orc.interrogate_kramer, (pr["Q"], pr["R"]), th32.astype(np.float64),
+                         z_smooth=zs.astype(np.float32).astype(np.float64), factor="ldl")
+    ex = P.maxnorm_rel(_np(x).astype(np.float64), want)
+    print(f"float32 solve_sim draws: {ex:.2e}")
+    assert x.dtype == torch.float32 and ex < 1e-5
+
+
 # ---- per-theta prior ---------------------------------------------------------------------------------------------------
 def test_theta_dependent_prior_scale(rb):
     """sigma as part of theta (reference docs/examples/parameter.md:218-222: prior_pars rebuilt per theta under vmap):
