@@ -140,13 +140,30 @@ static int dalton_host_body(const RodeoProblem* p, const double* ode_weight, con
     const int v = atoi(e);
     if (v >= 1 && v <= Arena::NCHUNK && (size_t)v <= B) nchunk = v;
   }
-  const size_t per = (B + nchunk - 1) / nchunk;
+  // chunk boundaries: equal chunks, or (RODEO_HOST_SPLIT="f0,f1,..": tuning experiments) the given fractions of the batch.
+  // Measured (tools/e2e_split.py, B200, 65,536 thetas, pinned buffers): 1 chunk 0.861 ms, 2 equal chunks 0.826,
+  // 1/8 + 1/4 + 5/8 0.816, 1/4 + 3/4 0.820, 1/16 + 3/16 + 3/4 0.867, 1/8 + 7/8 0.861 -- nothing beats two equal chunks by
+  // more than 1.3 %: 0.73 ms of kernel, the first chunk's rows, the result's way back and two event hand-overs are the floor
+  size_t bound[Arena::NCHUNK + 1];
+  {
+    const size_t per = (B + nchunk - 1) / nchunk;
+    for (int c = 0; c <= nchunk; ++c) bound[c] = (size_t)c * per < B ? (size_t)c * per : B;
+    if (const char* e = getenv("RODEO_HOST_SPLIT")) {
+      double f[Arena::NCHUNK]; int nf = 0; const char* q = e;
+      while (nf < Arena::NCHUNK && *q) { char* end; const double v = strtod(q, &end); if (end == q) break; f[nf++] = v; q = *end ? end + 1 : end; }
+      if (nf >= 1) {
+        nchunk = nf; double acc = 0; bound[0] = 0;
+        for (int c = 0; c < nf; ++c) { acc += f[c]; size_t x = (size_t)(acc * (double)B) / 32 * 32; bound[c + 1] = x < B ? x : B; }
+        bound[nf] = B;
+      }
+    }
+  }
   const size_t row_init = nb * ps, row_theta = (size_t)p->n_theta;
-  int launched = 0;
+  bool launched[Arena::NCHUNK] = {};
   for (int c = 0; c < nchunk; ++c) {
-    const size_t b0 = (size_t)c * per;
-    if (b0 >= B) break;
-    const size_t bn = b0 + per <= B ? per : B - b0;
+    const size_t b0 = bound[c];
+    if (b0 >= B || bound[c + 1] <= b0) continue;
+    const size_t bn = bound[c + 1] - b0;
     RODEO_CUDA_OK(cudaMemcpyAsync(d_init + b0 * row_init, ode_init + b0 * row_init, bn * row_init * 8,
                                   cudaMemcpyHostToDevice, s));
     RODEO_CUDA_OK(cudaMemcpyAsync(d_theta + b0 * row_theta, theta + b0 * row_theta, bn * row_theta * 8,
@@ -164,10 +181,11 @@ static int dalton_host_body(const RodeoProblem* p, const double* ode_weight, con
                                        g_arena.lane[c]))
       return rc;
     RODEO_CUDA_OK(cudaEventRecord(g_arena.done[c], g_arena.lane[c]));
-    ++launched;
+    launched[c] = true;
   }
   // only now does the copy stream wait for the kernels: waiting inside the loop would hold back the next chunk's copies
-  for (int c = 0; c < launched; ++c) RODEO_CUDA_OK(cudaStreamWaitEvent(s, g_arena.done[c], 0));
+  for (int c = 0; c < nchunk; ++c)
+    if (launched[c]) RODEO_CUDA_OK(cudaStreamWaitEvent(s, g_arena.done[c], 0));
   RODEO_CUDA_OK(cudaMemcpyAsync(loglik_out, d_ll, b_ll, cudaMemcpyDeviceToHost, s));
   RODEO_CUDA_OK(cudaStreamSynchronize(s));
   return RODEO_OK;
