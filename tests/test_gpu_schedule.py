@@ -182,3 +182,41 @@ def test_schedule_float32(rb, monkeypatch):
     e = P.maxnorm_rel(sched, full)
     print(f"float32 schedule vs full kernel: {e:.2e}")
     assert full.dtype == np.float32 and e < 5e-6
+
+
+@pytest.mark.parametrize("lanes", ["0", "1"])
+@pytest.mark.parametrize("B", [1, 5, 33, 47])
+def test_schedule_ragged_batches_and_output_canaries(rb, monkeypatch, B, lanes):
+    """Ragged batch sizes through both lane mappings of the schedule kernels, straight through the C ABI: rows equal those
+    of a larger batch, the draws are fully written, nothing is written outside the output / workspace buffers (guard
+    words on both sides; compute-sanitizer is closed on this pool)."""
+    import ctypes
+    import torch
+    from rodeo_b200 import _host, _lib
+    monkeypatch.setenv("RODEO_SIM_SCHEDULE", "1")
+    monkeypatch.setenv("RODEO_SIM_BLOCK_LANES", lanes)
+    N, tm = 37, 1.85
+    big = P.fitz_problem(64, n_steps=N, t_max=tm, seed=91)
+    key = np.array([21, 4], dtype=np.uint32)
+    chk = _interr(rb, "chkrebtii")
+    args = (rb.models.fitzhugh_nagumo, big["W"])
+    ref = rb.solve_sim(key, *args, big["X0"], 0.0, tm, N, chk, prior_pars=(big["Q"], big["R"]), theta=big["theta"])
+    pb = _host.Problem(key, *args, big["X0"][:B], 0.0, tm, N, chk, (big["Q"], big["R"]), None, None, "standard",
+                       {"theta": big["theta"][:B]})
+    G, SENT = 4096, -777.25
+
+    def guarded(n):
+        t = torch.full((n + 2 * G,), SENT, dtype=torch.float64, device="cuda")
+        return t, t[G:G + n]
+
+    nx = B * (N + 1) * 6
+    wsb = pb.lib.rodeo_b200_workspace_bytes(_lib.OP_SOLVE_SIM, ctypes.byref(pb.c), 8)
+    (gx, x), (gw, w) = guarded(nx), guarded(max(wsb // 8, 1))
+    rc = pb.fn("solve_sim")(ctypes.byref(pb.c), _host.ptr(pb.W), _host.ptr(pb.Q), _host.ptr(pb.R), _host.ptr(pb.x0),
+                            _host.ptr(pb.theta), None, None, _host.ptr(x), _host.ptr(w), wsb, pb.stream())
+    _lib.check(rc, "solve_sim")
+    torch.cuda.synchronize()
+    for g, n in ((gx, nx), (gw, max(wsb // 8, 1))):
+        assert bool((g[:G] == SENT).all()) and bool((g[G + n:] == SENT).all()), "write outside the buffer"
+    assert not bool((x == SENT).any()), "draws not fully written"
+    assert torch.equal(x.view(B, N + 1, 2, 3), ref[:B])
