@@ -10,7 +10,7 @@ CSRC      := rodeo_b200/csrc
 OBJDIR    := build/obj$(if $(FAST),_fast,)$(if $(VARIANT),_$(VARIANT),)
 OUT       ?= rodeo_b200/librodeo_b200.so
 TUS       := abi_common abi_dalton abi_solve abi_solve_sim abi_fenrir abi_hostbuf abi_nvrtc embedded_headers \
-             abi_dalton_f32 abi_solve_f32 abi_solve_sim_f32 abi_fenrir_f32 abi_dalton_solve_mv abi_dalton_solve_sim abi_solve_sqrt abi_solve_sqrt_f32 abi_fenrir_solve abi_kalmantv abi_kalmantv_sqrt abi_magi abi_mcmc
+             abi_dalton_f32 abi_solve_f32 abi_solve_sim_f32 abi_fenrir_f32 abi_dalton_solve_mv abi_dalton_solve_sim abi_solve_sqrt abi_solve_sqrt_f32 abi_fenrir_solve abi_kalmantv abi_kalmantv_sqrt abi_magi abi_mcmc abi_peer
 OBJS      := $(TUS:%=$(OBJDIR)/%.o)
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(CSRC)/rodeo_host.h include/rodeo_b200.h
 

@@ -354,6 +354,60 @@ def run_ours(args):
             fullN = spipe.result((spipe.k - 1) % spipe.depth)
             rec.update({"one_gpu_ms_per_step": float(t1.item()), "speedup_vs_one_gpu": float(t1.item()) / s_ms,
                         "sharded_equals_unsharded_bitwise": bool(torch.equal(full1, fullN))})
+            rec["collective"] = ("NCCL all-gather of the shard's log-likelihoods through GatherPipeline (side stream, "
+                                 "overlapping the next launch); at this batch the step is bound by the host's launch "
+                                 "path, see graph_peer")
+            # The same step as ONE CUDA graph per rank -- output memset, dalton kernel, and the all-gather as a kernel of
+            # peer stores over NVLink (rodeo_b200.parallel.PeerGather) -- replayed back to back: no per-step host work.
+            gp, t_gp, ok_local, same_gp = {}, float("nan"), 1, False
+            pg = None
+            try:
+                pg = parallel.PeerGather(B_PER_GPU)
+            except Exception as e:                                      # raised on every rank alike (collective agreement)
+                gp = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            if pg is not None:
+                try:
+                    gbuf = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+                    n_calls = 0
+                    for _ in range(3):
+                        sh(gbuf); pg.gather(gbuf, device_epoch=True); n_calls += 1
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        sh(gbuf); pg.gather(gbuf, device_epoch=True)
+                    for _ in range(3):
+                        graph.replay(); n_calls += 1
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        graph.replay()
+                    e1.record(); torch.cuda.synchronize()
+                    n_calls += steps
+                    t_gp = e0.elapsed_time(e1) / steps
+                    pg.check()
+                    same_gp = bool(torch.equal(pg.result(n_calls), fullN))
+                except Exception as e:
+                    ok_local = 0
+                    gp = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+                agree = torch.tensor([float(ok_local), float(same_gp)], dtype=torch.float64, device=dev)
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+                tg = torch.tensor([t_gp if ok_local else 0.0], dtype=torch.float64, device=dev)
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+                if bool(agree[0].item()):
+                    gp = {"ms_per_step": float(tg.item()), "value": B_PER_GPU * N / (float(tg.item()) * 1e-3), "unit": UNIT,
+                          "speedup_vs_one_gpu": float(t1.item()) / float(tg.item()),
+                          "equals_nccl_gather_bitwise": bool(agree[1].item()),
+                          "what": "one CUDA graph per rank (output memset + dalton kernel + peer-store all-gather kernel "
+                                  "over NVLink, CUDA-IPC mapped regions), replayed back to back; device time, max over ranks"}
+                elif not gp:
+                    gp = {"unavailable": "failed on another rank"}
+                try:
+                    barrier()
+                    pg.close()
+                except Exception:
+                    pass
+            rec["graph_peer"] = gp
         strong = rec
 
     # ---- BASELINE configs[4] at its stated total: 262,144 particles of one pseudo-marginal iteration (solve_sim +

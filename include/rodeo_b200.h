@@ -353,6 +353,32 @@ int64_t rodeo_b200_launch_count(void);
 int64_t rodeo_b200_schedule_builds(void);
 void rodeo_b200_schedule_clear(void);
 
+/*
+ * Peer-memory all-gather of per-theta log-likelihoods (rodeo_b200/csrc/abi_peer.cu), one process per GPU on one node.
+ * The reference has no multi-device path; this replaces the NCCL all-gather that follows a log-likelihood kernel
+ *  where the step's latency matters: one kernel per rank stores its shard into every rank's gathered vector
+ * through CUDA-IPC mappings (NVLink / NVSwitch peer stores), publishes a flag per peer and waits -- bounded -- for theirs.
+ *   peer_region_bytes  size of a rank's region for n_total elements: [2 slots][n_total] doubles + flags
+ *   peer_alloc         cudaMalloc a zeroed region and export its IPC handle (64 bytes) for the other ranks
+ *   peer_open / close  map / unmap another rank's region from its handle
+ *   peer_free          free a region obtained from peer_alloc
+ *   peer_allgather     regions: HOST array of `world` device pointers (own region at [rank]); the caller's shard
+ *                      local[0 .. n_local) lands at element `offset` of slot (epoch & 1) of every region.  epoch >= 1 and
+ *                      increases by one per call on every rank -- or epoch = 0 and epoch_counter a DEVICE counter (zeroed
+ *                      by the caller) that the kernel itself advances, so that the launch can be replayed from a CUDA
+ *                      graph; the result (own region, that slot) must be consumed on `stream` before the next call.
+ *                      *status (a DEVICE int the caller zeroes) becomes 1 if a peer's flag did not arrive within
+ *                      spin_limit polls (0 = default, about a second): the kernel never hangs.
+ */
+size_t rodeo_b200_peer_region_bytes(long long n_total, int world);
+int rodeo_b200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int rodeo_b200_peer_open(const unsigned char* handle64, void** ptr);
+int rodeo_b200_peer_close(void* ptr);
+int rodeo_b200_peer_free(void* ptr);
+int rodeo_b200_peer_allgather_f64(const double* local, long long n_local, long long offset, long long n_total, int rank,
+                                  int world, void* const* regions, unsigned epoch, unsigned* epoch_counter,
+                                  unsigned long long spin_limit, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,13 @@ SIGNATURES = {
     "rodeo_b200_host_arena_release": (None, []),
     "rodeo_b200_fp64_peak_probe": (_i, [_i, _vp]),
     "rodeo_b200_register_model_nvrtc": (_i, [ctypes.c_char_p, ctypes.c_char_p, _i, _i, _i, _i, _vp]),
+    "rodeo_b200_peer_region_bytes": (_sz, [ctypes.c_longlong, _i]),
+    "rodeo_b200_peer_alloc": (_i, [_sz, ctypes.POINTER(_vp), _vp]),
+    "rodeo_b200_peer_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "rodeo_b200_peer_close": (_i, [_vp]),
+    "rodeo_b200_peer_free": (_i, [_vp]),
+    "rodeo_b200_peer_allgather_f64": (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _vp,
+                                           ctypes.c_uint, _vp, ctypes.c_ulonglong, _vp, _vp]),
 }
 
 _lib = None

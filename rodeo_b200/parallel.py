@@ -137,3 +137,105 @@ def sharded_loglik(loglik_fn, theta, ode_init, group=None):
     if world > 1 and dist.get_backend(group) == "nccl" and not local.is_cuda:
         local = local.to(torch.device("cuda", torch.cuda.current_device()))
     return all_gather_loglik(local, len(theta), group)
+
+
+class _DevPtr:
+    """a raw device allocation as a __cuda_array_interface__ object (so that torch can view it without copying)"""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """All-gather of the per-theta log-likelihoods through peer memory instead of NCCL (one process per GPU, one node).
+
+    Every rank owns a region (two slots of ``B_total`` float64 + flags) allocated by the library and mapped into the
+    other ranks with CUDA IPC; ``gather(local)`` is ONE kernel on the current stream that stores the rank's shard into
+    every region over NVLink / NVSwitch, publishes a flag per peer and waits -- bounded -- for the peers' flags
+    (rodeo_b200/csrc/abi_peer.cu).  It returns a view of the rank's own slot: consume it on the same stream before the
+    next ``gather``.  Construction is collective (handles are exchanged through ``torch.distributed``) and raises if the
+    mappings cannot be made; callers fall back to :func:`all_gather_loglik`.  ``check()`` synchronises and raises if a
+    peer's flag ever failed to arrive.
+    """
+
+    def __init__(self, B_total, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self._lib = _lib
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.B_total = int(B_total)
+        self.lo, self.hi = shard_bounds(self.B_total, self.rank, self.world)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = self.lib.rodeo_b200_peer_region_bytes(self.B_total, self.world)
+        if nbytes == 0:
+            raise ValueError("PeerGather: world size out of range")
+        own, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.rodeo_b200_peer_alloc(nbytes, ctypes.byref(own), ctypes.cast(handle, ctypes.c_void_p)),
+                   "peer_alloc")
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs, self.opened, err = [None] * self.world, [], None
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs[r] = self.own
+                continue
+            p = ctypes.c_void_p()
+            hb = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            rc = self.lib.rodeo_b200_peer_open(ctypes.cast(hb, ctypes.c_void_p), ctypes.byref(p))
+            if rc != 0:
+                err = self.lib.rodeo_b200_last_error().decode(errors="replace")
+                break
+            self.ptrs[r] = p.value
+            self.opened.append(p.value)
+        # every rank must agree before anyone stores into a peer
+        ok = torch.tensor([0 if err else 1], device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise _lib.RodeoError(f"PeerGather: CUDA IPC mapping failed on some rank ({err})")
+        self.regions = (ctypes.c_void_p * self.world)(*self.ptrs)
+        self.status = torch.zeros(2, dtype=torch.int32, device=self.dev)       # [0] failure flag, [1] device-side epoch
+        self.data = torch.as_tensor(_DevPtr(self.own, 2 * self.B_total), device=self.dev).view(2, self.B_total)
+        self.epoch = 0
+        dist.barrier(group=group)
+
+    def gather(self, local, device_epoch=False):
+        """local: this rank's (hi - lo,) float64 CUDA tensor -> (B_total,) view of the gathered vector.
+
+        ``device_epoch=True`` keeps the call counter on the device so that the launch can be captured in a CUDA graph
+        and replayed (every rank must then use it for every call); after ``n`` calls / replays in total the result is
+        ``self.data[n & 1]`` (:meth:`result`)."""
+        import ctypes
+        if local.numel() != self.hi - self.lo or local.dtype != torch.float64 or not local.is_cuda:
+            raise ValueError("PeerGather.gather: the rank's shard as a float64 CUDA tensor")
+        if not local.is_contiguous():
+            raise ValueError("PeerGather.gather: contiguous shard expected")
+        if not device_epoch:
+            self.epoch += 1
+        rc = self.lib.rodeo_b200_peer_allgather_f64(
+            ctypes.c_void_p(local.data_ptr()), local.numel(), self.lo, self.B_total, self.rank, self.world,
+            ctypes.cast(self.regions, ctypes.c_void_p), 0 if device_epoch else self.epoch,
+            ctypes.c_void_p(self.status.data_ptr() + 4), 0, ctypes.c_void_p(self.status.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check(rc, "peer_allgather")
+        return None if device_epoch else self.data[self.epoch & 1]
+
+    def result(self, n_calls):
+        """the gathered vector after ``n_calls`` calls in total (device-epoch mode)"""
+        return self.data[n_calls & 1]
+
+    def check(self):
+        if int(self.status[0].item()) != 0:
+            raise self._lib.RodeoError("PeerGather: a peer's flag did not arrive (a rank missed a gather call?)")
+
+    def close(self):
+        for p in getattr(self, "opened", []):
+            self.lib.rodeo_b200_peer_close(p)
+        self.opened = []
+        if getattr(self, "own", None):
+            torch.cuda.synchronize()
+            self.lib.rodeo_b200_peer_free(self.own)
+            self.own = None

@@ -56,6 +56,20 @@ def main():
             assert torch.equal(pipe.result(slots[k - 1]), ref + float(k - 1))
     assert torch.equal(pipe.result(slots[2]), ref + 2.0)
 
+    # the peer-memory all-gather (one kernel of peer stores over NVLink instead of the NCCL collective): uneven shards,
+    # many calls so that both slots and the flag epochs are reused, every result equal to NCCL's bitwise
+    pg = parallel.PeerGather(B, None)
+    lo_u, hi_u = parallel.shard_bounds(B, rank, world)
+    mine = full[lo_u:hi_u].clone()
+    for k in range(40):
+        loc = mine + float(k)
+        got = pg.gather(loc)
+        want_k = parallel.all_gather_loglik(loc, B)
+        assert torch.equal(got, want_k), f"peer gather != NCCL gather at call {k}"
+    pg.check()
+    dist.barrier()
+    pg.close()
+
     # solve_sim: random streams are keyed by the GLOBAL particle index, so a shard reproduces its rows of the whole
     chk = functools.partial(rb.interrogate.interrogate_chkrebtii, kalman_type="standard")
     key = np.array([5, 7], dtype=np.uint32)
