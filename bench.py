@@ -373,7 +373,7 @@ def run_ours(args):
                         sh(gbuf); pg.gather(gbuf, device_epoch=True); n_calls += 1
                     torch.cuda.synchronize()
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # (other threads: NCCL watchdog, clock sampler)
                         sh(gbuf); pg.gather(gbuf, device_epoch=True)
                     for _ in range(3):
                         graph.replay(); n_calls += 1

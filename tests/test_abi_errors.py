@@ -102,3 +102,19 @@ def test_two_measurement_rows_model_is_compiled_for_the_float64_solvers_only():
     rc = lib.rodeo_b200_solve_mv_f32(ctypes.byref(c), p(W), p(Q), p(Q), None, None, None, None, None,
                                      ctypes.cast(ws, ctypes.c_void_p), 1 << 20, None)
     assert rc == 1 and "not compiled" in _err(lib)
+
+
+def test_peer_gather_argument_checks():
+    lib = _lib.load()
+    assert lib.rodeo_b200_peer_region_bytes(1000, 8) >= 2 * 1000 * 8 + 2 * 8 * 4
+    assert lib.rodeo_b200_peer_region_bytes(1000, 17) == 0 and lib.rodeo_b200_peer_region_bytes(-1, 2) == 0
+    # NULL shard / regions, rank out of range, shard past the end, no epoch source: refused before any CUDA call
+    assert lib.rodeo_b200_peer_allgather_f64(None, 4, 0, 8, 0, 2, None, 1, None, 0, None, None) == 2
+    dummy = ctypes.create_string_buffer(64)
+    regs = (ctypes.c_void_p * 2)(ctypes.addressof(dummy), ctypes.addressof(dummy))
+    p = ctypes.cast(dummy, ctypes.c_void_p)
+    for args in ((p, 4, 0, 8, 2, 2, regs, 1, None, 0, p, None),          # rank >= world
+                 (p, 4, 6, 8, 0, 2, regs, 1, None, 0, p, None),          # offset + n_local > n_total
+                 (p, 4, 0, 8, 0, 2, regs, 0, None, 0, p, None)):         # epoch 0 without a device counter
+        assert lib.rodeo_b200_peer_allgather_f64(*args[:6], ctypes.cast(args[6], ctypes.c_void_p), *args[7:]) == 2
+        assert "peer_allgather" in _err(lib)
