@@ -13,7 +13,8 @@ and ``tests/golden/make_reference_golden.py`` commits what they compute as ``tes
 solve_mv (all four interrogations, chkrebtii on logged normals), solve_sim (logged normals, SVD factor), dalton,
 fenrir, basic, dalton.solve_mv, fenrir.solve_mv, the square-root family, the Kalman primitives, the log-pdf's 1e-8
 cut-off, ibm_init and first_order_pad, on FitzHugh-Nagumo (incl. the README's N = 800 walkthrough), Lorenz63 and the
-second-order ODE.  ``tests/test_reference_golden.py`` holds this oracle to those vectors at 1e-10 .. 1e-12 on the CPU
+second-order ODE; per-theta priors (a theta-dependent sigma, and arbitrary per-theta (Q, R)), two observation rows per
+block (n_bobs = 2, correlated noise) and two measurement rows per block (n_bmeas = 2).  ``tests/test_reference_golden.py`` holds this oracle to those vectors at 1e-10 .. 1e-12 on the CPU
 and the CUDA path at 1e-10 on the GPU.  What stays unpinned: XLA's own operation order (expected ~1e-13) and JAX's
 threefry random streams (draws are compared on injected normals only).
 
