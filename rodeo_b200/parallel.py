@@ -237,5 +237,6 @@ class PeerGather:
         self.opened = []
         if getattr(self, "own", None):
             torch.cuda.synchronize()
+            self.data = None                              # the view below dies with the region
             self.lib.rodeo_b200_peer_free(self.own)
             self.own = None
