@@ -209,7 +209,9 @@ size_t rodeo_b200_workspace_bytes(int op, const RodeoProblem* p, int elem_bytes)
       // history of filtered states, theta-innermost: entries filt[KC], filt[2 KC], ... < N.  solve_mv keeps one
       // checkpoint per shared-memory segment (KC = seg_len(nstate)) and recomputes; solve_sim / fenrir keep every
       // state (KC = 1).  See rodeo_kernels.cuh.
-      const int nstate = nstate_of(p->n_block, p->n_bstate);
+      // (solve_sim over a covariance schedule keeps the block means only: n_block * n_bstate values per entry)
+      const bool means_only = op == RODEO_OP_SOLVE_SIM && sim_schedule_selected(*p);
+      const int nstate = means_only ? p->n_block * p->n_bstate : nstate_of(p->n_block, p->n_bstate);
       // solve_mv of a built-in model with n_block >= 2 runs the (theta, block)-lane kernel, whose segments are longer
       // (a per-theta prior runs the one-lane-per-theta kernel)
       const bool bl = p->n_block >= 2 && p->model_id < RODEO_MODEL_USER_BASE && !p->prior_batched;

@@ -37,9 +37,7 @@ struct SolveSimRun {
     // carries the block means only (rodeo_sched.cuh).  interrogate_schober with a per-theta prior scale keeps the full
     // kernels (singular filtered variance: the sign of a rounding-noise pivot is not scale invariant).
     if constexpr (INTERR != INTERR_KRAMER && !BATCH) {
-      bool use = !(INTERR == INTERR_SCHOBER && a.r_scale != nullptr);
-      if (const char* e = getenv("RODEO_SIM_SCHEDULE")) use = use && e[0] != '0';
-      if (use) {
+      if (sim_schedule_selected(p)) {
         typedef Sched<real_t, Model, INTERR, QK> SC;
         struct Key {
           int tag, model, interr, qk, n_steps, elem;

@@ -2,6 +2,7 @@
 // kernel-parameter struct, and the (model, interrogation, Q-structure) dispatch over the ahead-of-time
 // instantiations.  One translation unit per op keeps nvcc compile times parallel.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -106,6 +107,17 @@ inline int check_common(const RodeoProblem* p) {
     return RODEO_ERR_UNSUPPORTED;
   }
   return RODEO_OK;
+}
+
+// solve_sim runs over a cached covariance schedule (rodeo_sched.cuh) -- and then keeps a history of block MEANS only --
+// under the state-independent interrogations of built-in models with a shared prior; interrogate_schober with a
+// per-theta prior scale keeps the full kernels (singular filtered variance: the sign of a rounding-noise pivot is not
+// scale invariant).  One predicate for the dispatch (abi_solve_sim.cu) and the workspace size (abi_common.cu).
+inline bool sim_schedule_selected(const RodeoProblem& p) {
+  if (p.interrogate == RODEO_INTERROGATE_KRAMER || p.prior_batched || p.model_id >= RODEO_MODEL_USER_BASE) return false;
+  if (p.interrogate == RODEO_INTERROGATE_SCHOBER && p.prior_var_scale != nullptr) return false;
+  if (const char* e = getenv("RODEO_SIM_SCHEDULE")) { if (e[0] == '0') return false; }
+  return true;
 }
 
 inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
