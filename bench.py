@@ -354,9 +354,9 @@ def run_ours(args):
             fullN = spipe.result((spipe.k - 1) % spipe.depth)
             rec.update({"one_gpu_ms_per_step": float(t1.item()), "speedup_vs_one_gpu": float(t1.item()) / s_ms,
                         "sharded_equals_unsharded_bitwise": bool(torch.equal(full1, fullN))})
-            rec["collective"] = ("NCCL all-gather of the shard's log-likelihoods through GatherPipeline (side stream, "
-                                 "overlapping the next launch); at this batch the step is bound by the host's launch "
-                                 "path, see graph_peer")
+            rec["collective"] = ("nccl_pipeline: NCCL all-gather of the shard's log-likelihoods through GatherPipeline "
+                                 "(side stream, overlapping the next launch; host-driven); graph_peer: a kernel of peer "
+                                 "stores behind the dalton kernel, both in one CUDA graph per rank")
             # The same step as ONE CUDA graph per rank -- output memset, dalton kernel, and the all-gather as a kernel of
             # peer stores over NVLink (rodeo_b200.parallel.PeerGather) -- replayed back to back: no per-step host work.
             gp, t_gp, ok_local, same_gp = {}, float("nan"), 1, False
