@@ -124,9 +124,11 @@ class GatherPipeline:
                     torch.cuda.current_stream().wait_event(self.done[slot])
 
 
-def sharded_loglik(loglik_fn, theta, ode_init, group=None):
+def sharded_loglik(loglik_fn, theta, ode_init, group=None, peer=None):
     """Run ``loglik_fn(theta_shard, ode_init_shard, particle_offset) -> (B_local,) tensor`` on this rank's shard
-    and all-gather.  ``loglik_fn`` is typically a closure over ``rodeo_b200.inference.dalton`` / ``fenrir``."""
+    and all-gather.  ``loglik_fn`` is typically a closure over ``rodeo_b200.inference.dalton`` / ``fenrir``.
+    ``peer``: a :class:`PeerGather` built for ``len(theta)`` -- the gather is then its one kernel of peer stores instead of
+    the NCCL collective, and the result a view of its buffer (valid until the next-but-one gather)."""
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
@@ -136,6 +138,8 @@ def sharded_loglik(loglik_fn, theta, ode_init, group=None):
     # a log-likelihood of host arrays comes back on the host (rodeo_b200.inference.dalton): NCCL gathers device tensors
     if world > 1 and dist.get_backend(group) == "nccl" and not local.is_cuda:
         local = local.to(torch.device("cuda", torch.cuda.current_device()))
+    if peer is not None and world > 1:
+        return peer.gather(local.contiguous())
     return all_gather_loglik(local, len(theta), group)
 
 

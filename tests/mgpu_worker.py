@@ -66,6 +66,7 @@ def main():
         got = pg.gather(loc)
         want_k = parallel.all_gather_loglik(loc, B)
         assert torch.equal(got, want_k), f"peer gather != NCCL gather at call {k}"
+    assert torch.equal(parallel.sharded_loglik(loglik, pr["theta"], pr["X0"], peer=pg), full)     # the helper's peer path
     pg.check()
     dist.barrier()
     pg.close()
