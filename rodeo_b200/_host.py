@@ -124,6 +124,8 @@ class Problem:
             # the user vmaps over, docs/examples/parameter.md:218-236) goes to the device as (B, n_block, p, p) arrays.
             Qb = Qh if Qh.ndim == 4 else np.broadcast_to(Qh, (Rh.shape[0],) + Qh.shape)
             Rb = Rh if Rh.ndim == 4 else np.broadcast_to(Rh, (Qh.shape[0],) + Rh.shape)
+            if Rb.shape[0] == 0:                      # an empty batch: nothing to solve, any prior of the right shape
+                Qb, Rb = np.zeros((1,) + Qb.shape[1:]), np.zeros((1,) + Rb.shape[1:])
             ref = Rb[0]
             with np.errstate(all="ignore"):
                 scale = Rb[:, :, -1, -1] / ref[None, :, -1, -1]
