@@ -147,6 +147,31 @@ def test_fenrir_second_order(rb):
     assert ll_err(_np(got), want) < TOL
 
 
+@pytest.mark.parametrize("N", [1, 2, 7, 16, 17, 33, 100])
+def test_fenrir_forcing_buffer_chunk_edges(rb, monkeypatch, N):
+    """The warp-specialised fenrir kernel evaluates the right-hand side's forcing term ahead, in 16-step chunks handed
+    over with named barriers: step counts below / at / just above a chunk and ragged batches must give bitwise the
+    one-warp kernel's log-likelihoods (the same functions in the same order)."""
+    import torch
+    for B in (5, 48):
+        pr = P.second_order_problem(B, n_steps=N, t_max=0.05 * N, sigma=0.1, seed=20 + N)
+        obs_t = np.array([0.0, 0.05 * N])
+        D = np.zeros((2, 1, 1, 4)); D[..., 0] = 1.0
+        ob = dict(obs_data=np.array([[[-1.0]], [[-0.9]]]), obs_times=obs_t, obs_weight=D, obs_var=np.full((2, 1, 1, 1), 0.01))
+        run = lambda: rb.inference.fenrir(None, rb.models.second_order_sin, pr["W"], pr["X0"], 0.0, 0.05 * N, N,
+                                          rb.interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]),
+                                          theta=pr["theta"], **ob)
+        monkeypatch.setenv("RODEO_FENRIR_WS", "0")
+        one = run()
+        monkeypatch.setenv("RODEO_FENRIR_WS", "1")
+        ws = run()
+        assert bool(torch.isfinite(ws).all()) and torch.equal(one, ws)
+        want = orc.fenrir(orc.MODELS["second_order_sin"], pr["W"], pr["X0"], 0.0, 0.05 * N, N, orc.interrogate_kramer,
+                          (pr["Q"], pr["R"]), pr["theta"], ob["obs_data"], ob["obs_times"], ob["obs_weight"],
+                          ob["obs_var"])
+        assert ll_err(_np(ws), want) < 1e-9
+
+
 def test_fenrir_fitz(rb):
     pr = P.fitz_problem(40, n_steps=200, t_max=10.0, seed=11)
     ob = P.fitz_obs(pr, None, n_obs=11)
