@@ -220,3 +220,24 @@ def test_schedule_ragged_batches_and_output_canaries(rb, monkeypatch, B, lanes):
         assert bool((g[:G] == SENT).all()) and bool((g[G + n:] == SENT).all()), "write outside the buffer"
     assert not bool((x == SENT).any()), "draws not fully written"
     assert torch.equal(x.view(B, N + 1, 2, 3), ref[:B])
+
+
+@pytest.mark.parametrize("lanes", ["0", "1"])
+@pytest.mark.parametrize("N", [1, 2, 3, 15, 16, 17, 32, 33])
+def test_schedule_step_counts_at_the_chunk_edges(rb, monkeypatch, N, lanes):
+    """Table rows are streamed through shared memory in chunks (16 backward rows, up to 32 forward rows): step counts
+    below / at / just above a chunk, draws and fused log-likelihood, bitwise the full kernels."""
+    B = 19
+    pr = P.fitz_problem(B, n_steps=N, t_max=0.05 * N, seed=100 + N)
+    key = np.array([7, N], dtype=np.uint32)
+    obs_t = np.array([0.0, 0.05 * N])
+    Y = np.array([[-1.0, 1.0], [-0.9, 0.9]])
+    args = (key, rb.models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 0.05 * N, N, _interr(rb, "chkrebtii"))
+    kw = dict(prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"])
+
+    def run():
+        ll, x = rb.solve_sim_loglik(*args, obs_data=Y, obs_times=obs_t, noise_sd=0.1, return_draws=True, **kw)
+        return np.concatenate([_np(ll).ravel(), _np(x).ravel(), _np(rb.solve_sim(*args, **kw)).ravel(),
+                               _np(rb.solve_sim_loglik(*args, obs_data=Y, obs_times=obs_t, noise_sd=0.1, **kw)).ravel()])
+    full, sched = _both(monkeypatch, run, lanes)
+    assert np.isfinite(full).all() and np.array_equal(full, sched)
