@@ -108,7 +108,7 @@ extern "C" int rodeo_b200_peer_allgather_f64(const double* local, long long n_lo
                                              long long n_total, int rank, int world, void* const* regions,
                                              unsigned epoch, unsigned* epoch_counter, unsigned long long spin_limit,
                                              int* status, void* stream) {
-  if (!local || !regions || !status || world < 1 || world > PEER_MAX || rank < 0 || rank >= world || n_local < 0 ||
+  if ((!local && n_local > 0) || !regions || !status || world < 1 || world > PEER_MAX || rank < 0 || rank >= world || n_local < 0 ||
       offset < 0 || offset + n_local > n_total || (epoch == 0 && !epoch_counter)) {
     set_error("peer_allgather: bad arguments (world <= %d, epoch >= 1 or a device counter, offset + n_local <= n_total)",
               PEER_MAX);

@@ -70,6 +70,15 @@ def main():
     pg.check()
     dist.barrier()
     pg.close()
+    # fewer elements than ranks: some shards are empty
+    tiny = parallel.PeerGather(max(1, world - 1), None)
+    tl, th_ = parallel.shard_bounds(max(1, world - 1), rank, world)
+    vals = torch.arange(tl, th_, dtype=torch.float64, device=dev) + 0.5
+    got = tiny.gather(vals)
+    assert torch.equal(got, torch.arange(max(1, world - 1), dtype=torch.float64, device=dev) + 0.5)
+    tiny.check()
+    dist.barrier()
+    tiny.close()
 
     # solve_sim: random streams are keyed by the GLOBAL particle index, so a shard reproduces its rows of the whole
     chk = functools.partial(rb.interrogate.interrogate_chkrebtii, kalman_type="standard")

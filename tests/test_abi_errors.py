@@ -110,6 +110,7 @@ def test_peer_gather_argument_checks():
     assert lib.rodeo_b200_peer_region_bytes(1000, 17) == 0 and lib.rodeo_b200_peer_region_bytes(-1, 2) == 0
     # NULL shard / regions, rank out of range, shard past the end, no epoch source: refused before any CUDA call
     assert lib.rodeo_b200_peer_allgather_f64(None, 4, 0, 8, 0, 2, None, 1, None, 0, None, None) == 2
+    # (an empty shard may come with a NULL pointer: only a NULL shard of positive length is refused)
     dummy = ctypes.create_string_buffer(64)
     regs = (ctypes.c_void_p * 2)(ctypes.addressof(dummy), ctypes.addressof(dummy))
     p = ctypes.cast(dummy, ctypes.c_void_p)
