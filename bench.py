@@ -321,6 +321,43 @@ def run_ours(args):
         if not gather_ok:
             raise SystemExit("bench.py: the gathered log-likelihoods do not match the per-rank outputs")
 
+    # ---- the same weak-scaling step with the all-gather as the library's peer-store kernel on the side stream instead
+    #      of NCCL's (GatherPipeline(peer=PeerGather)): reported next to the headline, which stays on NCCL
+    weak_peer = None
+    if world > 1:
+        pgw = None
+        try:
+            pgw = parallel.PeerGather(world * B)
+        except Exception as e:                                              # raised on every rank alike
+            weak_peer = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        if pgw is not None:
+            ok_w, t_w, same_w = 1, float("nan"), False
+            try:
+                ppipe = parallel.GatherPipeline(B, dev, peer=pgw)
+                for _ in range(warm):
+                    weak(ppipe.local_buffer()); ppipe.submit()
+                ppipe.drain()
+                t_w, _ = timed_steps(torch, dist, world, dev, weak, ppipe, steps)
+                pgw.check()
+                same_w = bool(torch.equal(ppipe.result((ppipe.k - 1) % ppipe.depth), full))
+            except Exception as e:
+                ok_w = 0
+                weak_peer = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            agree = torch.tensor([float(ok_w), float(same_w)], dtype=torch.float64, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if bool(agree[0].item()):
+                weak_peer = {"ms_per_step": t_w, "value": world * B * N / (t_w * 1e-3), "unit": UNIT,
+                             "equals_nccl_gather_bitwise": bool(agree[1].item()),
+                             "what": "GatherPipeline(peer=PeerGather): the gather of step k is one kernel of NVLink peer "
+                                     "stores on the side stream while the dalton kernel of step k+1 runs"}
+            elif weak_peer is None:
+                weak_peer = {"unavailable": "failed on another rank"}
+            try:
+                barrier()
+                pgw.close()
+            except Exception:
+                pass
+
     # ---- strong scaling at BASELINE configs[1]'s stated total: 65,536 thetas over `world` GPUs
     strong = None
     if args.thetas == B_PER_GPU:
@@ -624,7 +661,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "rodeo_b200_dalton_f64_host (C ABI, pinned host buffers)", "matches_device_path": same},
-        "e2e_python": e2e_py, "strong": strong, "strong_c5": strong_c5, "sustained": sustained, "configs": configs,
+        "e2e_python": e2e_py, "weak_peer_gather": weak_peer, "strong": strong, "strong_c5": strong_c5, "sustained": sustained, "configs": configs,
         "gather_matches_rank_outputs": gather_ok,
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "wall_s_timed_region": t_wall,

@@ -72,8 +72,13 @@ class GatherPipeline:
     buffer.  Equal shard sizes only (pad with :func:`all_gather_loglik` otherwise).
     """
 
-    def __init__(self, B_local, device, dtype=torch.float64, group=None, depth=2, collective=True):
+    def __init__(self, B_local, device, dtype=torch.float64, group=None, depth=2, collective=True, peer=None):
+        """``peer``: a :class:`PeerGather` for ``world * B_local`` elements -- the collective on the side stream is then its
+        kernel of peer stores instead of NCCL's all-gather (depth must stay 2: the peer regions have two slots)."""
         self.group = group
+        self.peer = peer
+        if peer is not None and depth != 2:
+            raise ValueError("GatherPipeline with a PeerGather needs depth == 2")
         self.world = (dist.get_world_size(group)
                       if (collective and dist.is_available() and dist.is_initialized()) else 1)
         self.depth, self.k = depth, 0
@@ -104,7 +109,10 @@ class GatherPipeline:
         self.ready[slot].record(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.ready[slot])
-            dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group)
+            if self.peer is not None:
+                self.gathered[slot] = self.peer.gather(self.local[slot])     # a view of the peer region's slot
+            else:
+                dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group)
             self.done[slot].record(self.comm)
         self.pending[slot] = True
         return slot
