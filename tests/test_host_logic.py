@@ -78,3 +78,42 @@ def test_key_parsing():
     assert _host.parse_key(5) == (0, 5)
     with pytest.raises(ValueError):
         _host.parse_key([1, 2, 3])
+
+
+def test_host_input_marshalling_needs_no_device():
+    """Problem(host_inputs=True) keeps theta / ode_init / observation arrays as zero-copy CPU tensors for the *_host entry
+    points: the struct, the broadcasting and the per-theta prior scale are the same as on the device path."""
+    import torch
+    from rodeo_b200 import _host
+    import problems as P
+    B = 5
+    pr = P.fitz_problem(B, n_steps=20, t_max=1.0, seed=3)
+    ob = P.fitz_obs(pr, None, n_obs=3)
+    assert _host.on_host(pr["theta"], pr["X0"], None, [1.0, 2.0], torch.zeros(2))
+    pb = _host.Problem(None, models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 1.0, 20, interrogate.interrogate_kramer,
+                       (pr["Q"], pr["R"]), None, None, "standard", {"theta": pr["theta"]}, host_inputs=True)
+    pb.set_obs(ob["obs_data"], ob["obs_times"], ob["obs_weight"], ob["obs_var"])
+    assert pb.B == B and pb.c.B == B and pb.c.n_obs == 3 and pb.c.n_bobs == 1 and pb.c.prior_batched == 0
+    assert not pb.theta.is_cuda and not pb.x0.is_cuda and not pb.obs_data.is_cuda and not pb.obs_ind.is_cuda
+    assert pb.theta.data_ptr() == pr["theta"].ctypes.data          # zero-copy view of the caller's array
+    assert np.array_equal(pb.obs_ind.numpy(), orc.obs_index(0.0, 1.0, 20, ob["obs_times"]))
+    # un-batched theta with batched ode_init broadcasts; sigma part of theta becomes a host scale array
+    Q, Rb = prior.ibm_init(1.0 / 20, 3, 0.1 * np.ones((B, 2)) * np.arange(1, B + 1)[:, None])
+    pb = _host.Problem(None, models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 1.0, 20, interrogate.interrogate_kramer,
+                       (Q, Rb), None, None, "standard", {"theta": pr["theta"][0]}, host_inputs=True)
+    assert pb.B == B and tuple(pb.theta.shape) == (B, 3) and not pb.r_scale.is_cuda
+    assert np.allclose(pb.r_scale.numpy()[:, 0], np.arange(1, B + 1) ** 2)
+
+
+def test_host_path_without_gpu_fails_loudly():
+    """dalton() on NumPy inputs goes through rodeo_b200_dalton_f64_host: without a GPU it must raise, not fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import problems as P
+    pr = P.fitz_problem(3, n_steps=10, t_max=0.5, seed=1)
+    ob = P.fitz_obs(pr, None, n_obs=2)
+    with pytest.raises(Exception) as e:
+        rodeo_b200.inference.dalton(None, models.fitzhugh_nagumo, pr["W"], pr["X0"], 0.0, 0.5, 10,
+                                    interrogate.interrogate_kramer, prior_pars=(pr["Q"], pr["R"]), theta=pr["theta"], **ob)
+    assert "CUDA" in str(e.value) or "cuda" in str(e.value)
