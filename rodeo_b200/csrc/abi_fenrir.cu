@@ -52,7 +52,7 @@ struct FenrirRun {
     if (p.B == 0) return RODEO_OK;
     // warp-specialised backward sweep (rodeo_kernels.cuh) while all of its CTAs are resident at once, i.e. while the
     // one-warp kernel would be bound by a theta's serial chain; measured on B200: second-order ODE, 16,384 thetas x 2,000
-    // steps 2.65 -> 2.0-2.2 ms; FitzHugh-Nagumo, 65,536 thetas x 800 steps 3.54 -> 3.64 ms (throughput-bound: not used)
+    // steps 2.65 -> 1.95 ms; FitzHugh-Nagumo, 65,536 thetas x 800 steps 3.54 -> 3.64 ms (throughput-bound: not used)
     bool ws = !BATCH && sizeof(real_t) == 8 && (long long)grid_for(p.B, 32) <= 4LL * sm_count();
     if (const char* e = getenv("RODEO_FENRIR_WS")) ws = ws && e[0] == '1';      // tuning / tests
     if constexpr (sizeof(real_t) == 8 && !BATCH) {
